@@ -1,0 +1,106 @@
+/*
+ * aadg_b200 — C ABI of the B200-native AADG hot path (libaadg_b200.so, sm_100a).
+ *
+ * The reference (CRazorback/AADG) has no FFI: its hot path sits behind Python call shapes and runs
+ * on Pillow (CPU), geomloss/KeOps and cuDNN.  Each entry point below names the reference
+ * interface it replaces (file:line under /root/reference).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; device pointers unless a parameter says HOST;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated, freed or
+ *     synchronised inside; all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative AADG_E* code otherwise; `aadg_last_error()` returns the
+ *     calling thread's last message; no exception crosses the boundary;
+ *   - re-entrant; no global mutable state.
+ */
+#ifndef AADG_B200_H
+#define AADG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AADG_OK 0
+#define AADG_EINVAL (-1)   /* bad argument */
+#define AADG_ENOSPC (-2)   /* workspace too small */
+#define AADG_ECUDA (-3)    /* CUDA launch / runtime failure */
+
+#define AADG_ABI_VERSION 1
+
+int aadg_version(void);
+const char* aadg_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * uint8 augmentation bank — replaces data/basic.py:70-167,231-260 (the ten live Pillow ops and the
+ * geometric ops), data/policy.py:15-61 (Policy / DGMultiPolicy application) and, for the epilogue,
+ * data/transform.py:97-236 (DGRandomScaleCrop, Normalize_dg, ToTensor) + :323-340 (collate order).
+ * ---------------------------------------------------------------------------------------------- */
+
+#define AADG_MAX_OPS 4
+
+enum aadg_op {           /* index into the reference's augment_list(), data/basic.py:231-243 ... */
+  AADG_OP_AUTOCONTRAST = 0, AADG_OP_INVERT = 1, AADG_OP_EQUALIZE = 2, AADG_OP_SOLARIZE = 3,
+  AADG_OP_POSTERIZE = 4, AADG_OP_CONTRAST = 5, AADG_OP_COLOR = 6, AADG_OP_BRIGHTNESS = 7,
+  AADG_OP_SHARPNESS = 8, AADG_OP_CUTOUT = 9,
+  /* ... then the ops the reference defines but never samples, data/basic.py:12-67,82 */
+  AADG_OP_SHEAR_X = 10, AADG_OP_SHEAR_Y = 11, AADG_OP_TRANSLATE_X = 12, AADG_OP_TRANSLATE_Y = 13,
+  AADG_OP_ROTATE = 14, AADG_OP_FLIP = 15,
+  AADG_OP_COUNT = 16
+};
+
+enum aadg_dataset { AADG_DATASET_OPTIC = 0, AADG_DATASET_VESSEL = 1 };
+
+/* One output image = one row of the decision table (every random draw of the reference resolved to
+ * integers / C floats on the host; see aadg_b200/data/decisions.py).  160 bytes, little endian. */
+typedef struct aadg_aug_row {
+  int32_t src;                      /* source image index                                         */
+  int32_t n_ops;                    /* ops of the chosen sub-policy, applied in order              */
+  int32_t op[AADG_MAX_OPS];         /* enum aadg_op                                               */
+  float fparam[AADG_MAX_OPS];       /* Contrast/Color/Brightness/Sharpness: blend factor          */
+  int32_t iparam[AADG_MAX_OPS][6];  /* Solarize: [0]=ceil(threshold); Posterize: [0]=AND mask;    */
+                                    /* Cutout: inclusive x0,y0,x1,y1 (x1<x0: no-op);              */
+                                    /* Shear/Translate/Rotate: Pillow 16.16 a0,a1,a2,a3,a4,a5     */
+  int32_t do_scale, scale_w, scale_h; /* DGRandomScaleCrop.scale (data/transform.py:104-112)      */
+  int32_t pad, crop_x, crop_y;        /* RandomCrop (data/transform.py:35-55)                      */
+} aadg_aug_row_t;
+
+/* Bytes of workspace needed by aadg_u8_apply_policy / aadg_u8_policy_batch. */
+size_t aadg_u8_workspace_bytes(int n_rows, int n_src, int height, int width, int max_scale_w,
+                               int max_scale_h);
+
+/* Post-policy images: out_u8[r] = chain(rows[r])(src_images[rows[r].src]).
+ *   src_images uint8 [n_src,H,W,3]; src_masks uint8 [n_src,H,W] or NULL; rows HOST [n_rows];
+ *   out_u8 uint8 [n_rows,H,W,3]; out_masks uint8 [n_rows,H,W] or NULL (Cutout/geometric ops edit
+ *   the mask like data/basic.py does; the train transform later discards it).                    */
+int aadg_u8_apply_policy(const uint8_t* src_images, const uint8_t* src_masks,
+                         const aadg_aug_row_t* rows, int n_rows, int n_src, int height, int width,
+                         uint8_t* out_u8, uint8_t* out_masks, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* Scale + crop + normalise + to-tensor of n_rows images.
+ *   images uint8 [n_images,H,W,3]: image r is images[r] if image_by_row else images[rows[r].src];
+ *   masks uint8 [n_src,H,W]: the ORIGINAL masks, indexed rows[r].src (data/transform.py:127-131);
+ *   out_images float32 [n_rows,3,crop_h,crop_w] = x/127.5-1; out_labels float32
+ *   [n_rows,C,crop_h,crop_w], C=2 (optic multilabel) or 1 (vessel); either may be NULL.          */
+int aadg_u8_scale_crop_normalize(const uint8_t* images, int image_by_row, const uint8_t* masks,
+                                 const aadg_aug_row_t* rows, int n_rows, int n_src, int height,
+                                 int width, int crop_w, int crop_h, int dataset, float* out_images,
+                                 float* out_labels, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
+/* Whole batch in one call: policy -> (scale, crop) -> normalise; crop_w == 0 skips scale/crop and
+ * fuses the normalise/to-tensor epilogue into the chain kernel.  Row order is the caller's
+ * (collate order (b*D+d)*M+j, data/transform.py:323-340).                                        */
+int aadg_u8_policy_batch(const uint8_t* src_images, const uint8_t* src_masks,
+                         const aadg_aug_row_t* rows, int n_rows, int n_src, int height, int width,
+                         int crop_w, int crop_h, int dataset, float* out_images, float* out_labels,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AADG_B200_H */
