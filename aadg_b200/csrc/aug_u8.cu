@@ -1,0 +1,811 @@
+// uint8 augmentation bank for sm_100a.
+//
+// Replaces, for whole batches on the device, what the reference does per image on the CPU through
+// Pillow: data/basic.py:70-167 (ten live ops), :12-67,82 (geometric ops), data/policy.py:15-61
+// (sub-policy application) and the Normalize_dg / ToTensor epilogue of data/transform.py:138-236.
+//
+// Design (HBM-bound byte work, no tensor cores):
+//   * every output image is one row of the decision table; the host part of this file compiles the
+//     row into a short "program" of steps (LUT / COLOR / CUTOUT / SHARP / AFFINE / FLIP);
+//   * ops that are per-channel functions of the byte value (Invert, Solarize, Posterize,
+//     Brightness, Contrast, AutoContrast, Equalize) become 3x256 look-up tables built on the device;
+//     the three statistics ops take their histogram from a per-SOURCE histogram pass whenever the
+//     ops before them are look-up tables too (the histogram is pushed through the tables instead
+//     of re-reading the image), so the common case reads each source once for statistics;
+//   * one tile kernel evaluates a whole program per pixel: image rows are staged in shared memory
+//     with 1-D TMA bulk copies (cp.async.bulk -> mbarrier), the 3x3 SMOOTH stencil of Sharpness runs
+//     on the staged tile, and the epilogue writes either uint8 HWC or the normalised float32 CHW
+//     tensor the model consumes (x/127.5-1) with 16-byte stores.
+//   * float arithmetic that must match Pillow bit for bit (blend, SMOOTH, autocontrast) uses
+//     explicit round-to-nearest intrinsics so nothing is contracted into an FMA.
+#include "common.cuh"
+
+#include <string.h>
+#include <vector>
+
+namespace aadg {
+namespace u8 {
+
+constexpr int TW = 128;          // tile width in pixels
+constexpr int TH = 8;            // tile height in pixels
+constexpr int NT = 256;          // threads per CTA: 32 threads x 4 pixels per tile row
+constexpr int RS = 432;           // shared-memory bytes per staged row: (TW+2)*3 + 2x15 alignment slack, 16-B multiple
+static_assert(RS % 16 == 0 && RS >= (TW + 2) * 3 + 30, "row stride must keep 16-byte alignment for bulk copies");
+
+enum StepKind { K_LUT = 0, K_COLOR = 1, K_CUTOUT = 2, K_SHARP = 3, K_AFFINE = 4, K_FLIP = 5 };
+enum LutKind { L_INVERT = 0, L_SOLARIZE, L_POSTERIZE, L_BRIGHT, L_CONTRAST, L_AUTOCONTRAST, L_EQUALIZE };
+
+struct DevStep {
+  int kind;
+  int lut_kind;
+  float f;      // blend factor
+  int p[6];     // CUTOUT: x0,y0,x1,y1 | AFFINE: a0..a5 (16.16) | LUT: p[0]=param, p[1]=stat slot, p[2]=derive
+};
+struct DevRow {
+  int src;
+  int n_steps;
+  DevStep s[AADG_MAX_OPS];
+};
+struct PassItem {
+  int row;
+  int s0, s1;      // steps [s0, s1) are evaluated
+  int base;        // -1: source image rows[row].src; else scratch image index
+  int out;         // output image index (scratch slot or final row) / statistics slot
+  int sharp;       // index of the SHARP step inside [s0,s1) or -1
+  int gather;      // 1 if [s0,s1) contains AFFINE/FLIP (then sharp == -1 or gathers precede it)
+  int pad_;
+};
+struct Stat {      // one statistics slot
+  unsigned int hist[3][256];
+  unsigned long long luma_sum;
+  unsigned long long pad_;
+};
+
+// ---- Pillow arithmetic ---------------------------------------------------------------------------
+__device__ __forceinline__ int luma_u8(int r, int g, int b) {
+  return (19595 * r + 38470 * g + 7471 * b + 0x8000) >> 16;   // Convert.c rgb2l
+}
+// ImagingBlend: a + alpha*(b-a) in float32, mul then add (no FMA), truncated; clipped outside [0,1]
+__device__ __forceinline__ int blend_u8(int a, int b, float alpha, bool inside01) {
+  float t = __fadd_rn((float)a, __fmul_rn(alpha, (float)(b - a)));
+  if (!inside01) t = t <= 0.f ? 0.f : (t >= 255.f ? 255.f : t);
+  return (int)t;
+}
+
+struct Ctx {
+  const DevRow* row;
+  const uint8_t* luts;   // this row's tables [MAX_OPS][3][256]
+};
+
+// pointwise steps [s0,s1) on one pixel at coordinate (x,y) of the level it lives on
+__device__ __forceinline__ void apply_point(const DevStep& st, const uint8_t* lut, int x, int y,
+                                            int& r, int& g, int& b) {
+  if (st.kind == K_LUT) {
+    r = lut[r]; g = lut[256 + g]; b = lut[512 + b];
+  } else if (st.kind == K_COLOR) {
+    const bool in01 = st.f >= 0.f && st.f <= 1.f;
+    const int l = luma_u8(r, g, b);
+    r = blend_u8(l, r, st.f, in01); g = blend_u8(l, g, st.f, in01); b = blend_u8(l, b, st.f, in01);
+  } else if (st.kind == K_CUTOUT) {
+    if (x >= st.p[0] && x <= st.p[2] && y >= st.p[1] && y <= st.p[3]) r = g = b = 127;
+  }
+}
+
+// Pull evaluation of steps [s0,s1) (no SHARP inside) at output pixel (x,y): walks the gathers
+// backwards to find the source pixel, then applies the pointwise steps forwards.
+__device__ __forceinline__ void eval_gather(const DevRow& row, const uint8_t* luts, int s0, int s1,
+                                            const uint8_t* base, int W, int H, int x, int y,
+                                            int& r, int& g, int& b) {
+  int cx[AADG_MAX_OPS + 1], cy[AADG_MAX_OPS + 1];
+  cx[s1 - s0] = x; cy[s1 - s0] = y;
+  int dead = -1;   // highest step index whose gather fell outside (value is 0 after that step)
+#pragma unroll
+  for (int k = AADG_MAX_OPS - 1; k >= 0; --k) {
+    if (k >= s1 - s0) continue;
+    const DevStep& st = row.s[s0 + k];
+    int px = cx[k + 1], py = cy[k + 1];
+    if (dead < 0) {
+      if (st.kind == K_AFFINE) {
+        // Geometry.c affine_fixed + nearest: xx = a2 + y*a1 + x*a0 (16.16), sample [yy>>16][xx>>16]
+        long long xx = (long long)st.p[2] + (long long)py * st.p[1] + (long long)px * st.p[0];
+        long long yy = (long long)st.p[5] + (long long)py * st.p[4] + (long long)px * st.p[3];
+        long long xi = xx >> 16, yi = yy >> 16;
+        if (xi < 0 || xi >= W || yi < 0 || yi >= H) { dead = k; xi = 0; yi = 0; }
+        px = (int)xi; py = (int)yi;
+      } else if (st.kind == K_FLIP) {
+        px = W - 1 - px;
+      }
+    }
+    cx[k] = px; cy[k] = py;
+  }
+  if (dead < 0) {
+    const uint8_t* p = base + ((size_t)cy[0] * W + cx[0]) * 3;
+    r = p[0]; g = p[1]; b = p[2];
+  } else {
+    r = g = b = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < AADG_MAX_OPS; ++k) {
+    if (k >= s1 - s0 || k <= dead) continue;
+    apply_point(row.s[s0 + k], luts + (size_t)(s0 + k) * 768, cx[k + 1], cy[k + 1], r, g, b);
+  }
+}
+
+// ImageFilter.SMOOTH through ImagingFilter3x3 (Filter.c): float32, starts at 0.5, rows y+1, y, y-1,
+// each row (a*k0 + b*k1) + c*k2, then clip8 by truncation.
+__device__ __forceinline__ int smooth_1ch(const uint8_t* up, const uint8_t* mid, const uint8_t* dn,
+                                          float k1, float k5) {
+  // up = row y-1, mid = row y, dn = row y+1; pointers at the centre pixel's channel byte
+  float ss = 0.5f;
+  float t = __fadd_rn(__fadd_rn(__fmul_rn((float)dn[-3], k1), __fmul_rn((float)dn[0], k1)),
+                      __fmul_rn((float)dn[3], k1));
+  ss = __fadd_rn(ss, t);
+  t = __fadd_rn(__fadd_rn(__fmul_rn((float)mid[-3], k1), __fmul_rn((float)mid[0], k5)),
+                __fmul_rn((float)mid[3], k1));
+  ss = __fadd_rn(ss, t);
+  t = __fadd_rn(__fadd_rn(__fmul_rn((float)up[-3], k1), __fmul_rn((float)up[0], k1)),
+                __fmul_rn((float)up[3], k1));
+  ss = __fadd_rn(ss, t);
+  return ss <= 0.f ? 0 : (ss >= 255.f ? 255 : (int)ss);
+}
+
+enum Mode { MODE_STATS = 0, MODE_U8 = 1, MODE_F32 = 2 };
+
+struct PassArgs {
+  const DevRow* rows;
+  const PassItem* items;
+  const uint8_t* luts;        // [n_rows][MAX_OPS][768]
+  const uint8_t* src;         // [n_src][H][W][3]
+  const uint8_t* scratch;     // [*][H][W][3]
+  uint8_t* out_u8;            // MODE_U8: [*][H][W][3]
+  float* out_f32;             // MODE_F32: [*][3][H][W]
+  Stat* stats;                // MODE_STATS
+  int H, W;
+  int aligned;                // rows can be staged with 16-byte bulk copies
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
+  __shared__ __align__(128) uint8_t tile[(TH + 2) * RS];
+  __shared__ __align__(16) uint8_t s_luts[AADG_MAX_OPS * 768];
+  __shared__ float s_norm[256];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ unsigned int s_hist[MODE == MODE_STATS ? (NT / 32) * 768 : 1];
+  __shared__ DevRow s_row;
+
+  const PassItem it = a.items[blockIdx.y];
+  const int W = a.W, H = a.H;
+  const int tiles_x = (W + TW - 1) / TW;
+  const int x0 = (blockIdx.x % tiles_x) * TW;
+  const int y0 = (blockIdx.x / tiles_x) * TH;
+  const int tid = threadIdx.x;
+
+  if (tid < (int)(sizeof(DevRow) / 4)) ((int*)&s_row)[tid] = ((const int*)&a.rows[it.row])[tid];
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  const DevRow& row = s_row;
+  const uint8_t* base = it.base < 0 ? a.src + (size_t)row.src * H * W * 3
+                                    : a.scratch + (size_t)it.base * H * W * 3;
+  const int halo = it.sharp >= 0 ? 1 : 0;
+  const int ya = max(y0 - halo, 0), yb = min(y0 + TH + halo, H);   // staged image rows [ya,yb)
+  const int bx0 = max((x0 - halo) * 3, 0), bx1 = min((x0 + TW + halo) * 3, W * 3);
+  int sbase;   // byte column of the image row that sits at tile row offset 0
+
+  if (!it.gather) {
+    if (a.aligned) {
+      sbase = bx0 & ~15;
+      const int send = min(W * 3, (bx1 + 15) & ~15);
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&bar, (uint32_t)((send - sbase) * (yb - ya)));
+        for (int yy = ya; yy < yb; ++yy)
+          tma_bulk_g2s(tile + (yy - (y0 - 1)) * RS, base + (size_t)yy * W * 3 + sbase,
+                       (uint32_t)(send - sbase), &bar);
+      }
+    } else {
+      sbase = bx0;
+      const int nb = bx1 - bx0;
+      for (int i = tid; i < nb * (yb - ya); i += NT) {
+        const int yy = ya + i / nb, xb = i % nb;
+        tile[(yy - (y0 - 1)) * RS + xb] = base[(size_t)yy * W * 3 + bx0 + xb];
+      }
+    }
+  } else {
+    sbase = bx0;
+  }
+  // tables and the normalisation map while the copies fly
+  {
+    const uint4* g = (const uint4*)(a.luts + (size_t)it.row * AADG_MAX_OPS * 768);
+    uint4* s = (uint4*)s_luts;
+    for (int i = tid; i < AADG_MAX_OPS * 768 / 16; i += NT) s[i] = g[i];
+    if (MODE == MODE_F32) s_norm[tid] = __fsub_rn(__fdiv_rn((float)tid, 127.5f), 1.0f);
+    if (MODE == MODE_STATS)
+      for (int i = tid; i < (NT / 32) * 768; i += NT) s_hist[i] = 0;
+  }
+  __syncthreads();
+
+  const int pre_end = it.sharp >= 0 ? it.sharp : it.s1;   // steps [s0,pre_end) before the stencil
+  if (it.gather) {
+    // every staged pixel is produced by a pull through the gathers (+ pointwise steps up to pre_end)
+    const int nx = (bx1 - bx0) / 3;
+    for (int i = tid; i < nx * (yb - ya); i += NT) {
+      const int yy = ya + i / nx, xx = bx0 / 3 + i % nx;
+      int r, g, b;
+      eval_gather(row, s_luts, it.s0, pre_end, base, W, H, xx, yy, r, g, b);
+      uint8_t* p = tile + (yy - (y0 - 1)) * RS + (xx * 3 - sbase);
+      p[0] = (uint8_t)r; p[1] = (uint8_t)g; p[2] = (uint8_t)b;
+    }
+    __syncthreads();
+  } else {
+    if (a.aligned) mbar_wait(&bar, 0);
+    if (it.sharp >= 0 && pre_end > it.s0) {
+      // pointwise prefix applied in place on tile + halo before the stencil reads neighbours
+      const int nx = (bx1 - bx0) / 3;
+      for (int i = tid; i < nx * (yb - ya); i += NT) {
+        const int yy = ya + i / nx, xx = bx0 / 3 + i % nx;
+        uint8_t* p = tile + (yy - (y0 - 1)) * RS + (xx * 3 - sbase);
+        int r = p[0], g = p[1], b = p[2];
+        for (int k = it.s0; k < pre_end; ++k) apply_point(row.s[k], s_luts + k * 768, xx, yy, r, g, b);
+        p[0] = (uint8_t)r; p[1] = (uint8_t)g; p[2] = (uint8_t)b;
+      }
+      __syncthreads();
+    } else if (!a.aligned) {
+      // generic loads were already followed by the barrier above
+    }
+  }
+
+  // ---- compute phase: 4 consecutive pixels per thread -------------------------------------------
+  const int ty = tid >> 5, y = y0 + ty;
+  const int xq = x0 + (tid & 31) * 4;
+  int vr[4], vg[4], vb[4];
+  const bool row_ok = y < H;
+  const float k1 = __fdiv_rn(1.0f, 13.0f), k5 = __fdiv_rn(5.0f, 13.0f);
+  const bool pre_applied = it.gather || it.sharp >= 0;   // steps < pre_end already in the tile
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = xq + i;
+    int r = 0, g = 0, b = 0;
+    if (row_ok && x < W) {
+      const uint8_t* p = tile + (ty + 1) * RS + (x * 3 - sbase);
+      r = p[0]; g = p[1]; b = p[2];
+      int k = pre_applied ? pre_end : it.s0;
+      if (it.sharp >= 0) {
+        const DevStep& st = row.s[it.sharp];
+        if (x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2) {
+          const bool in01 = st.f >= 0.f && st.f <= 1.f;
+          const int dr = smooth_1ch(p - RS, p, p + RS, k1, k5);
+          const int dg = smooth_1ch(p - RS + 1, p + 1, p + RS + 1, k1, k5);
+          const int db = smooth_1ch(p - RS + 2, p + 2, p + RS + 2, k1, k5);
+          r = blend_u8(dr, r, st.f, in01); g = blend_u8(dg, g, st.f, in01); b = blend_u8(db, b, st.f, in01);
+        }
+        k = it.sharp + 1;
+      }
+      for (; k < it.s1; ++k) apply_point(row.s[k], s_luts + k * 768, x, y, r, g, b);
+    }
+    vr[i] = r; vg[i] = g; vb[i] = b;
+  }
+
+  if (MODE == MODE_STATS) {
+    unsigned int* hh = s_hist + (tid >> 5) * 768;
+    unsigned int lsum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (row_ok && xq + i < W) {
+        atomicAdd(&hh[vr[i]], 1u); atomicAdd(&hh[256 + vg[i]], 1u); atomicAdd(&hh[512 + vb[i]], 1u);
+        lsum += luma_u8(vr[i], vg[i], vb[i]);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    __syncthreads();
+    Stat* st = a.stats + it.out;
+    for (int i = tid; i < 768; i += NT) {
+      unsigned int v = 0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) v += s_hist[w * 768 + i];
+      if (v) atomicAdd(&st->hist[0][0] + i, v);
+    }
+    if ((tid & 31) == 0 && lsum) atomicAdd(&st->luma_sum, (unsigned long long)lsum);
+  } else if (MODE == MODE_U8) {
+    if (row_ok) {
+      uint8_t* o = a.out_u8 + ((size_t)it.out * H + y) * W * 3 + (size_t)xq * 3;
+      if (xq + 3 < W && (W & 3) == 0) {
+        uint32_t w0 = vr[0] | (vg[0] << 8) | (vb[0] << 16) | (vr[1] << 24);
+        uint32_t w1 = vg[1] | (vb[1] << 8) | (vr[2] << 16) | (vg[2] << 24);
+        uint32_t w2 = vb[2] | (vr[3] << 8) | (vg[3] << 16) | (vb[3] << 24);
+        uint32_t* ow = (uint32_t*)o;
+        ow[0] = w0; ow[1] = w1; ow[2] = w2;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (xq + i < W) { o[i * 3] = (uint8_t)vr[i]; o[i * 3 + 1] = (uint8_t)vg[i]; o[i * 3 + 2] = (uint8_t)vb[i]; }
+      }
+    }
+  } else {
+    if (row_ok) {
+      const size_t plane = (size_t)H * W;
+      float* o = a.out_f32 + (size_t)it.out * 3 * plane + (size_t)y * W + xq;
+      if (xq + 3 < W && (W & 3) == 0) {
+        __stcs((float4*)o, make_float4(s_norm[vr[0]], s_norm[vr[1]], s_norm[vr[2]], s_norm[vr[3]]));
+        __stcs((float4*)(o + plane), make_float4(s_norm[vg[0]], s_norm[vg[1]], s_norm[vg[2]], s_norm[vg[3]]));
+        __stcs((float4*)(o + 2 * plane), make_float4(s_norm[vb[0]], s_norm[vb[1]], s_norm[vb[2]], s_norm[vb[3]]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (xq + i < W) { o[i] = s_norm[vr[i]]; o[plane + i] = s_norm[vg[i]]; o[2 * plane + i] = s_norm[vb[i]]; }
+      }
+    }
+  }
+}
+
+// ---- look-up table construction ------------------------------------------------------------------
+// One CTA of 256 threads per (row, step): thread i owns entry i of the three channel tables.
+struct LutItem { int row; int step; };
+
+__global__ void __launch_bounds__(256) lut_kernel(const DevRow* rows, const LutItem* items,
+                                                  uint8_t* luts, const Stat* stats, int n_pix) {
+  __shared__ unsigned int h[3][256];
+  __shared__ unsigned int cum[3][256];
+  __shared__ int s_lo[3], s_hi[3], s_nnz[3];
+  const LutItem it = items[blockIdx.x];
+  const DevRow& row = rows[it.row];
+  const DevStep st = row.s[it.step];
+  const int i = threadIdx.x;
+  uint8_t* out = luts + ((size_t)it.row * AADG_MAX_OPS + it.step) * 768;
+  if (st.kind != K_LUT) return;
+
+  if (st.lut_kind == L_INVERT) {
+    out[i] = out[256 + i] = out[512 + i] = (uint8_t)(255 - i);
+    return;
+  }
+  if (st.lut_kind == L_SOLARIZE) {          // ImageOps.solarize: i < threshold ? i : 255-i
+    const uint8_t v = (uint8_t)(i < st.p[0] ? i : 255 - i);
+    out[i] = out[256 + i] = out[512 + i] = v;
+    return;
+  }
+  if (st.lut_kind == L_POSTERIZE) {         // ImageOps.posterize: i & mask
+    out[i] = out[256 + i] = out[512 + i] = (uint8_t)(i & st.p[0]);
+    return;
+  }
+  const bool in01 = st.f >= 0.f && st.f <= 1.f;
+  if (st.lut_kind == L_BRIGHT) {            // ImageEnhance.Brightness: blend(0, x, f)
+    out[i] = out[256 + i] = out[512 + i] = (uint8_t)blend_u8(0, i, st.f, in01);
+    return;
+  }
+  const Stat& sg = stats[st.p[1]];
+  if (st.lut_kind == L_CONTRAST) {
+    // ImageEnhance.Contrast: mean = int(ImageStat.Stat(L).mean[0] + 0.5); blend(mean, x, f)
+    const double mean = __dadd_rn(__ddiv_rn((double)sg.luma_sum, (double)n_pix), 0.5);
+    const int m = (int)mean;
+    out[i] = out[256 + i] = out[512 + i] = (uint8_t)blend_u8(m, i, st.f, in01);
+    return;
+  }
+  // histogram ops: fetch (or derive through the earlier tables) the histogram of the current image
+  for (int c = 0; c < 3; ++c) { h[c][i] = 0; }
+  if (i < 3) { s_lo[i] = 256; s_hi[i] = -1; s_nnz[i] = 0; }
+  __syncthreads();
+  if (st.p[2]) {
+    for (int c = 0; c < 3; ++c) {
+      int v = i;
+      for (int k = 0; k < it.step; ++k)
+        v = luts[((size_t)it.row * AADG_MAX_OPS + k) * 768 + c * 256 + v];
+      const unsigned int cnt = sg.hist[c][i];
+      if (cnt) atomicAdd(&h[c][v], cnt);
+    }
+  } else {
+    for (int c = 0; c < 3; ++c) h[c][i] = sg.hist[c][i];
+  }
+  __syncthreads();
+  for (int c = 0; c < 3; ++c)
+    if (h[c][i]) { atomicMin(&s_lo[c], i); atomicMax(&s_hi[c], i); atomicAdd(&s_nnz[c], 1); }
+  // exclusive prefix sums of each channel histogram: warp c scans channel c, 8 bins per lane
+  {
+    const int w = i >> 5, lane = i & 31;
+    if (w < 3) {
+      unsigned int loc[8], run = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = run; run += h[w][lane * 8 + j]; }
+      unsigned int inc = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      const unsigned int excl = inc - run;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cum[w][lane * 8 + j] = excl + loc[j];
+    }
+  }
+  __syncthreads();
+  for (int c = 0; c < 3; ++c) {
+    int v = i;
+    if (st.lut_kind == L_AUTOCONTRAST) {
+      // ImageOps.autocontrast(cutoff=0): ix = int(ix*scale + offset) in doubles, clipped
+      const int lo = s_lo[c], hi = s_hi[c];
+      if (hi > lo) {
+        const double scale = __ddiv_rn(255.0, (double)(hi - lo));
+        const double offset = __dmul_rn(-(double)lo, scale);
+        const double t = __dadd_rn(__dmul_rn((double)i, scale), offset);
+        const int q = (int)t;
+        v = q < 0 ? 0 : (q > 255 ? 255 : q);
+      }
+    } else {
+      // ImageOps.equalize: step = (sum(nonzero) - last nonzero) // 255; lut[i] = (step//2 + cum[i]) // step
+      if (s_nnz[c] > 1) {
+        const unsigned int total = cum[c][255] + h[c][255];
+        const unsigned int step = (total - h[c][s_hi[c]]) / 255u;
+        if (step) {
+          const unsigned int q = (step / 2 + cum[c][i]) / step;
+          v = q > 255u ? 255 : (int)q;
+        }
+      }
+    }
+    out[c * 256 + i] = (uint8_t)v;
+  }
+}
+
+// ---- masks and labels ----------------------------------------------------------------------------
+// data/basic.py edits the mask in Cutout (fill 0) and the geometric ops (same warp as the image).
+__global__ void mask_kernel(const DevRow* rows, const uint8_t* src_masks, uint8_t* out, int n_rows,
+                            int H, int W) {
+  const int r = blockIdx.y;
+  const DevRow row = rows[r];
+  const uint8_t* base = src_masks + (size_t)row.src * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    int x = i % W, y = i / W;
+    int cx[AADG_MAX_OPS + 1], cy[AADG_MAX_OPS + 1];
+    cx[row.n_steps] = x; cy[row.n_steps] = y;
+    int dead = -1;
+    for (int k = row.n_steps - 1; k >= 0; --k) {
+      const DevStep& st = row.s[k];
+      int px = cx[k + 1], py = cy[k + 1];
+      if (dead < 0) {
+        if (st.kind == K_AFFINE) {
+          long long xx = (long long)st.p[2] + (long long)py * st.p[1] + (long long)px * st.p[0];
+          long long yy = (long long)st.p[5] + (long long)py * st.p[4] + (long long)px * st.p[3];
+          long long xi = xx >> 16, yi = yy >> 16;
+          if (xi < 0 || xi >= W || yi < 0 || yi >= H) { dead = k; xi = 0; yi = 0; }
+          px = (int)xi; py = (int)yi;
+        }
+        // Flip: the reference mirrors the image only (data/basic.py:82-83)
+      }
+      cx[k] = px; cy[k] = py;
+    }
+    int v = dead < 0 ? base[(size_t)cy[0] * W + cx[0]] : 0;
+    for (int k = dead + 1; k < row.n_steps; ++k) {
+      const DevStep& st = row.s[k];
+      if (st.kind == K_CUTOUT && cx[k + 1] >= st.p[0] && cx[k + 1] <= st.p[2] &&
+          cy[k + 1] >= st.p[1] && cy[k + 1] <= st.p[3])
+        v = 0;
+    }
+    out[(size_t)r * H * W + i] = (uint8_t)v;
+  }
+}
+
+// Normalize_dg mask branch + to_multilabel + ToTensor (data/transform.py:153-172,244-249,217-236):
+// optic: >200 -> [0,0]; (50,201) -> [0,1]; else [1,1];  vessel: != 0 -> [1].
+__global__ void label_kernel(const DevRow* rows, const uint8_t* src_masks, float* out, int H, int W,
+                             int dataset) {
+  const int r = blockIdx.y;
+  const int src = rows[r].src;
+  const size_t plane = (size_t)H * W;
+  const uint8_t* m = src_masks + (size_t)src * plane;
+  const int nch = dataset == AADG_DATASET_OPTIC ? 2 : 1;
+  float* o = out + (size_t)r * nch * plane;
+  const size_t n4 = plane / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const uchar4 v = ((const uchar4*)m)[i];
+    const int vv[4] = {v.x, v.y, v.z, v.w};
+    float c0[4], c1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (dataset == AADG_DATASET_OPTIC) {
+        const bool bg = vv[j] > 200, ring = vv[j] > 50 && vv[j] < 201;
+        c0[j] = (!bg && !ring) ? 1.f : 0.f;
+        c1[j] = bg ? 0.f : 1.f;
+      } else {
+        c0[j] = vv[j] != 0 ? 1.f : 0.f;
+      }
+    }
+    __stcs((float4*)o + i, make_float4(c0[0], c0[1], c0[2], c0[3]));
+    if (nch == 2) __stcs((float4*)(o + plane) + i, make_float4(c1[0], c1[1], c1[2], c1[3]));
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < plane; i += blockDim.x) {
+      const int v = m[i];
+      if (dataset == AADG_DATASET_OPTIC) {
+        const bool bg = v > 200, ring = v > 50 && v < 201;
+        o[i] = (!bg && !ring) ? 1.f : 0.f;
+        o[plane + i] = bg ? 0.f : 1.f;
+      } else {
+        o[i] = v != 0 ? 1.f : 0.f;
+      }
+    }
+}
+
+// ---- host: compile rows into programs and schedule the passes ---------------------------------------
+struct Plan {
+  std::vector<DevRow> rows;
+  std::vector<PassItem> src_stats;                    // one per source that needs statistics
+  std::vector<PassItem> mat[AADG_MAX_OPS + 1];        // materialise before step k
+  std::vector<PassItem> stat[AADG_MAX_OPS];           // statistics pass feeding step k
+  std::vector<LutItem> lut[AADG_MAX_OPS];             // tables of step k
+  std::vector<PassItem> fin;                          // final pass per row
+  int n_stat_slots = 0;
+  int n_scratch = 0;
+};
+
+static bool is_stat_op(int op) {
+  return op == AADG_OP_AUTOCONTRAST || op == AADG_OP_EQUALIZE || op == AADG_OP_CONTRAST;
+}
+
+static int compile(const aadg_aug_row_t* in, int n_rows, int n_src, Plan& pl) {
+  pl.rows.resize(n_rows);
+  std::vector<int> src_slot(n_src, -1);
+  pl.n_stat_slots = 0;
+  auto slot_for_src = [&](int s) {
+    if (src_slot[s] < 0) {
+      src_slot[s] = pl.n_stat_slots++;
+      PassItem it{};  // row filled below: any row with this src works as a carrier
+      it.row = -1; it.s0 = 0; it.s1 = 0; it.base = -1; it.out = src_slot[s]; it.sharp = -1; it.gather = 0;
+      it.pad_ = s;
+      pl.src_stats.push_back(it);
+    }
+    return src_slot[s];
+  };
+  for (int r = 0; r < n_rows; ++r) {
+    const aadg_aug_row_t& a = in[r];
+    AADG_REQUIRE(a.src >= 0 && a.src < n_src, "row %d: src %d out of range [0,%d)", r, a.src, n_src);
+    AADG_REQUIRE(a.n_ops >= 0 && a.n_ops <= AADG_MAX_OPS, "row %d: n_ops %d out of range", r, a.n_ops);
+    DevRow& d = pl.rows[r];
+    memset(&d, 0, sizeof(d));
+    d.src = a.src;
+    d.n_steps = a.n_ops;
+    int seg = 0, base = -1;
+    bool sharp_seen = false, all_lut = true;
+    int sharp_idx = -1;
+    bool gather_seen = false;
+    auto item = [&](int s1) {
+      PassItem it{};
+      it.row = r; it.s0 = seg; it.s1 = s1; it.base = base; it.sharp = -1; it.gather = 0;
+      for (int k = seg; k < s1; ++k) {
+        if (d.s[k].kind == K_SHARP) it.sharp = k;
+        if (d.s[k].kind == K_AFFINE || d.s[k].kind == K_FLIP) it.gather = 1;
+      }
+      return it;
+    };
+    for (int k = 0; k < a.n_ops; ++k) {
+      const int op = a.op[k];
+      AADG_REQUIRE(op >= 0 && op < AADG_OP_COUNT, "row %d: unknown op id %d", r, op);
+      DevStep& st = d.s[k];
+      const bool barrier = op == AADG_OP_SHARPNESS || (op >= AADG_OP_SHEAR_X && op <= AADG_OP_FLIP);
+      if (barrier && sharp_seen) {
+        // a stencil's output is needed at arbitrary neighbours/positions: materialise it first
+        PassItem it = item(k);
+        it.out = pl.n_scratch++;
+        pl.mat[k].push_back(it);
+        base = it.out; seg = k; sharp_seen = false; sharp_idx = -1; gather_seen = false;
+      }
+      (void)sharp_idx; (void)gather_seen;
+      switch (op) {
+        case AADG_OP_INVERT: st.kind = K_LUT; st.lut_kind = L_INVERT; break;
+        case AADG_OP_SOLARIZE: st.kind = K_LUT; st.lut_kind = L_SOLARIZE; st.p[0] = a.iparam[k][0]; break;
+        case AADG_OP_POSTERIZE: st.kind = K_LUT; st.lut_kind = L_POSTERIZE; st.p[0] = a.iparam[k][0]; break;
+        case AADG_OP_BRIGHTNESS: st.kind = K_LUT; st.lut_kind = L_BRIGHT; st.f = a.fparam[k]; break;
+        case AADG_OP_CONTRAST: st.kind = K_LUT; st.lut_kind = L_CONTRAST; st.f = a.fparam[k]; break;
+        case AADG_OP_AUTOCONTRAST: st.kind = K_LUT; st.lut_kind = L_AUTOCONTRAST; break;
+        case AADG_OP_EQUALIZE: st.kind = K_LUT; st.lut_kind = L_EQUALIZE; break;
+        case AADG_OP_COLOR: st.kind = K_COLOR; st.f = a.fparam[k]; break;
+        case AADG_OP_SHARPNESS: st.kind = K_SHARP; st.f = a.fparam[k]; sharp_seen = true; break;
+        case AADG_OP_CUTOUT:
+          st.kind = K_CUTOUT;
+          for (int j = 0; j < 4; ++j) st.p[j] = a.iparam[k][j];
+          break;
+        case AADG_OP_FLIP: st.kind = K_FLIP; break;
+        default:
+          st.kind = K_AFFINE;
+          for (int j = 0; j < 6; ++j) st.p[j] = a.iparam[k][j];
+      }
+      if (is_stat_op(op)) {
+        if (k == 0) {
+          st.p[1] = slot_for_src(a.src); st.p[2] = 0;
+        } else if (all_lut && op != AADG_OP_CONTRAST) {
+          st.p[1] = slot_for_src(a.src); st.p[2] = 1;      // histogram pushed through the tables
+        } else {
+          PassItem it = item(k);
+          it.out = -1 - (r * AADG_MAX_OPS + k);             // own slot, numbered after the sources
+          pl.stat[k].push_back(it);
+          st.p[1] = it.out; st.p[2] = 0;
+        }
+      }
+      if (st.kind == K_LUT) pl.lut[k].push_back(LutItem{r, k});
+      else all_lut = false;
+    }
+    PassItem it = item(a.n_ops);
+    it.out = r;
+    pl.fin.push_back(it);
+  }
+  // own statistics slots follow the per-source ones
+  int next = pl.n_stat_slots;
+  for (int k = 0; k < AADG_MAX_OPS; ++k)
+    for (PassItem& it : pl.stat[k]) {
+      const int key = -1 - it.out;
+      it.out = next++;
+      pl.rows[key / AADG_MAX_OPS].s[key % AADG_MAX_OPS].p[1] = it.out;
+    }
+  pl.n_stat_slots = next;
+  // carriers for source statistics: any row of that source; steps [0,0) of it
+  for (PassItem& it : pl.src_stats) {
+    const int s = it.pad_;
+    for (int r = 0; r < n_rows; ++r)
+      if (pl.rows[r].src == s) { it.row = r; break; }
+    it.pad_ = 0;
+  }
+  return AADG_OK;
+}
+
+struct Layout {
+  size_t rows, items, lut_items, luts, stats, scratch, mask_dummy, total;
+  size_t n_items, n_lut_items;
+};
+
+static Layout layout(int n_rows, int n_src, int H, int W) {
+  Layout L{};
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = align_up(off, 256); off = o + b; return o; };
+  L.n_items = (size_t)n_src + (size_t)n_rows * (2 * AADG_MAX_OPS + 2);
+  L.n_lut_items = (size_t)n_rows * AADG_MAX_OPS;
+  L.rows = take(sizeof(DevRow) * n_rows);
+  L.items = take(sizeof(PassItem) * L.n_items);
+  L.lut_items = take(sizeof(LutItem) * L.n_lut_items);
+  L.luts = take((size_t)n_rows * AADG_MAX_OPS * 768);
+  L.stats = take(sizeof(Stat) * ((size_t)n_src + (size_t)n_rows * AADG_MAX_OPS));
+  L.scratch = take((size_t)n_rows * (AADG_MAX_OPS - 1) * H * W * 3);
+  L.total = align_up(off, 256);
+  return L;
+}
+
+template <int MODE>
+static int launch_pass(const PassArgs& base, const PassItem* d_items, int n, cudaStream_t st) {
+  if (n == 0) return AADG_OK;
+  const int tiles = ((base.W + TW - 1) / TW) * ((base.H + TH - 1) / TH);
+  for (int done = 0; done < n; done += 65535) {
+    PassArgs a = base;
+    a.items = d_items + done;
+    dim3 grid(tiles, std::min(n - done, 65535));
+    pass_kernel<MODE><<<grid, NT, 0, st>>>(a);
+  }
+  return check_launch("aug_u8 pass kernel");
+}
+
+// mode: 0 = uint8 HWC images (+ optional masks), 1 = float32 CHW images (+ optional labels)
+static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_aug_row_t* rows,
+               int n_rows, int n_src, int H, int W, int mode, int dataset, uint8_t* out_u8,
+               uint8_t* out_masks, float* out_f32, float* out_labels, void* ws, size_t ws_bytes,
+               cudaStream_t st) {
+  AADG_REQUIRE(n_rows >= 0 && n_src > 0 && H > 0 && W > 0, "bad sizes n_rows=%d n_src=%d H=%d W=%d",
+               n_rows, n_src, H, W);
+  if (n_rows == 0) return AADG_OK;
+  AADG_REQUIRE(src_images && rows, "null src_images / rows");
+  AADG_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  Plan pl;
+  int rc = compile(rows, n_rows, n_src, pl);
+  if (rc) return rc;
+  const Layout L = layout(n_rows, n_src, H, W);
+  // scratch is sized for the worst case; the rest of the workspace is always needed
+  const size_t need = L.scratch + (size_t)pl.n_scratch * H * W * 3;
+  if (ws_bytes < need || !ws) {
+    set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    return AADG_ENOSPC;
+  }
+  char* w = (char*)ws;
+  // one host blob -> one copy: rows, then every launch's item list back to back
+  std::vector<PassItem> items;
+  std::vector<LutItem> litems;
+  size_t o_src = items.size();
+  items.insert(items.end(), pl.src_stats.begin(), pl.src_stats.end());
+  size_t o_mat[AADG_MAX_OPS + 1], o_stat[AADG_MAX_OPS], o_lut[AADG_MAX_OPS];
+  for (int k = 0; k < AADG_MAX_OPS; ++k) {
+    o_mat[k] = items.size(); items.insert(items.end(), pl.mat[k].begin(), pl.mat[k].end());
+    o_stat[k] = items.size(); items.insert(items.end(), pl.stat[k].begin(), pl.stat[k].end());
+    o_lut[k] = litems.size(); litems.insert(litems.end(), pl.lut[k].begin(), pl.lut[k].end());
+  }
+  size_t o_fin = items.size();
+  items.insert(items.end(), pl.fin.begin(), pl.fin.end());
+  AADG_REQUIRE(items.size() <= L.n_items && litems.size() <= L.n_lut_items, "internal: plan overflow");
+
+  AADG_CUDA_TRY(cudaMemcpyAsync(w + L.rows, pl.rows.data(), sizeof(DevRow) * n_rows, cudaMemcpyHostToDevice, st));
+  AADG_CUDA_TRY(cudaMemcpyAsync(w + L.items, items.data(), sizeof(PassItem) * items.size(), cudaMemcpyHostToDevice, st));
+  if (!litems.empty())
+    AADG_CUDA_TRY(cudaMemcpyAsync(w + L.lut_items, litems.data(), sizeof(LutItem) * litems.size(), cudaMemcpyHostToDevice, st));
+  if (pl.n_stat_slots)
+    AADG_CUDA_TRY(cudaMemsetAsync(w + L.stats, 0, sizeof(Stat) * pl.n_stat_slots, st));
+
+  PassArgs a{};
+  a.rows = (const DevRow*)(w + L.rows);
+  a.luts = (const uint8_t*)(w + L.luts);
+  a.src = src_images;
+  a.scratch = (const uint8_t*)(w + L.scratch);
+  a.stats = (Stat*)(w + L.stats);
+  a.H = H; a.W = W;
+  a.aligned = ((W * 3) % 16 == 0) && (((uintptr_t)src_images & 15) == 0);
+  const PassItem* d_items = (const PassItem*)(w + L.items);
+  const LutItem* d_litems = (const LutItem*)(w + L.lut_items);
+
+  rc = launch_pass<MODE_STATS>(a, d_items + o_src, (int)pl.src_stats.size(), st);
+  if (rc) return rc;
+  for (int k = 0; k < AADG_MAX_OPS; ++k) {
+    PassArgs am = a;
+    am.out_u8 = (uint8_t*)(w + L.scratch);
+    rc = launch_pass<MODE_U8>(am, d_items + o_mat[k], (int)pl.mat[k].size(), st);
+    if (rc) return rc;
+    rc = launch_pass<MODE_STATS>(a, d_items + o_stat[k], (int)pl.stat[k].size(), st);
+    if (rc) return rc;
+    if (!pl.lut[k].empty()) {
+      lut_kernel<<<(unsigned)pl.lut[k].size(), 256, 0, st>>>(a.rows, d_litems + o_lut[k], (uint8_t*)(w + L.luts),
+                                                            a.stats, H * W);
+      rc = check_launch("aug_u8 lut kernel");
+      if (rc) return rc;
+    }
+  }
+  if (mode == 0) {
+    AADG_REQUIRE(out_u8, "null out_u8");
+    PassArgs af = a;
+    af.out_u8 = out_u8;
+    rc = launch_pass<MODE_U8>(af, d_items + o_fin, n_rows, st);
+    if (rc) return rc;
+    if (out_masks) {
+      AADG_REQUIRE(src_masks, "out_masks requested without src_masks");
+      dim3 grid(std::min((H * W + 255) / 256, 1024), n_rows);
+      mask_kernel<<<grid, 256, 0, st>>>(a.rows, src_masks, out_masks, n_rows, H, W);
+      rc = check_launch("aug_u8 mask kernel");
+    }
+  } else {
+    if (out_f32) {
+      PassArgs af = a;
+      af.out_f32 = out_f32;
+      rc = launch_pass<MODE_F32>(af, d_items + o_fin, n_rows, st);
+      if (rc) return rc;
+    }
+    if (out_labels) {
+      AADG_REQUIRE(src_masks, "out_labels requested without src_masks");
+      AADG_REQUIRE(((uintptr_t)src_masks & 3) == 0 && ((size_t)H * W) % 4 == 0,
+                   "label path needs 4-byte aligned masks and H*W %% 4 == 0");
+      dim3 grid(std::min((H * W / 4 + 255) / 256, 512), n_rows);
+      label_kernel<<<grid, 256, 0, st>>>(a.rows, src_masks, out_labels, H, W, dataset);
+      rc = check_launch("aug_u8 label kernel");
+    }
+  }
+  return rc;
+}
+
+}  // namespace u8
+}  // namespace aadg
+
+extern "C" {
+
+size_t aadg_u8_workspace_bytes(int n_rows, int n_src, int height, int width) {
+  if (n_rows <= 0 || n_src <= 0 || height <= 0 || width <= 0) return 0;
+  return aadg::u8::layout(n_rows, n_src, height, width).total;
+}
+
+int aadg_u8_apply_policy(const uint8_t* src_images, const uint8_t* src_masks,
+                         const aadg_aug_row_t* rows, int n_rows, int n_src, int height, int width,
+                         uint8_t* out_u8, uint8_t* out_masks, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return aadg::u8::run(src_images, src_masks, rows, n_rows, n_src, height, width, 0, 0, out_u8,
+                       out_masks, nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int aadg_u8_policy_normalize(const uint8_t* src_images, const uint8_t* src_masks,
+                             const aadg_aug_row_t* rows, int n_rows, int n_src, int height,
+                             int width, int dataset, float* out_images, float* out_labels,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (dataset != AADG_DATASET_OPTIC && dataset != AADG_DATASET_VESSEL) {
+    aadg::set_error("unknown dataset %d", dataset);
+    return AADG_EINVAL;
+  }
+  return aadg::u8::run(src_images, src_masks, rows, n_rows, n_src, height, width, 1, dataset,
+                       nullptr, nullptr, out_images, out_labels, workspace, workspace_bytes,
+                       (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -68,11 +68,12 @@ typedef struct aadg_aug_row {
   int32_t pad, crop_x, crop_y;        /* RandomCrop (data/transform.py:35-55)                      */
 } aadg_aug_row_t;
 
-/* Bytes of workspace needed by aadg_u8_apply_policy / aadg_u8_policy_batch. */
-size_t aadg_u8_workspace_bytes(int n_rows, int n_src, int height, int width, int max_scale_w,
-                               int max_scale_h);
+/* Bytes of workspace that is always enough for the u8 entry points below (worst case: every row
+ * materialises AADG_MAX_OPS-1 intermediate images).  0 for non-positive sizes. */
+size_t aadg_u8_workspace_bytes(int n_rows, int n_src, int height, int width);
 
-/* Post-policy images: out_u8[r] = chain(rows[r])(src_images[rows[r].src]).
+/* Post-policy images: out_u8[r] = chain(rows[r])(src_images[rows[r].src])   — what
+ * DGMultiPolicy.__call__ returns as sample['aug_images'] (data/policy.py:51-61).
  *   src_images uint8 [n_src,H,W,3]; src_masks uint8 [n_src,H,W] or NULL; rows HOST [n_rows];
  *   out_u8 uint8 [n_rows,H,W,3]; out_masks uint8 [n_rows,H,W] or NULL (Cutout/geometric ops edit
  *   the mask like data/basic.py does; the train transform later discards it).                    */
@@ -81,24 +82,14 @@ int aadg_u8_apply_policy(const uint8_t* src_images, const uint8_t* src_masks,
                          uint8_t* out_u8, uint8_t* out_masks, void* workspace,
                          size_t workspace_bytes, void* stream);
 
-/* Scale + crop + normalise + to-tensor of n_rows images.
- *   images uint8 [n_images,H,W,3]: image r is images[r] if image_by_row else images[rows[r].src];
- *   masks uint8 [n_src,H,W]: the ORIGINAL masks, indexed rows[r].src (data/transform.py:127-131);
- *   out_images float32 [n_rows,3,crop_h,crop_w] = x/127.5-1; out_labels float32
- *   [n_rows,C,crop_h,crop_w], C=2 (optic multilabel) or 1 (vessel); either may be NULL.          */
-int aadg_u8_scale_crop_normalize(const uint8_t* images, int image_by_row, const uint8_t* masks,
-                                 const aadg_aug_row_t* rows, int n_rows, int n_src, int height,
-                                 int width, int crop_w, int crop_h, int dataset, float* out_images,
-                                 float* out_labels, void* workspace, size_t workspace_bytes,
-                                 void* stream);
-
-/* Whole batch in one call: policy -> (scale, crop) -> normalise; crop_w == 0 skips scale/crop and
- * fuses the normalise/to-tensor epilogue into the chain kernel.  Row order is the caller's
- * (collate order (b*D+d)*M+j, data/transform.py:323-340).                                        */
-int aadg_u8_policy_batch(const uint8_t* src_images, const uint8_t* src_masks,
-                         const aadg_aug_row_t* rows, int n_rows, int n_src, int height, int width,
-                         int crop_w, int crop_h, int dataset, float* out_images, float* out_labels,
-                         void* workspace, size_t workspace_bytes, void* stream);
+/* Policy + Normalize_dg + ToTensor in one pass (no scale/crop): data/policy.py:51-61 followed by
+ * data/transform.py:149-186,217-236 and the collate order of :323-340 (row order is the caller's).
+ *   out_images float32 [n_rows,3,H,W] = x/127.5-1; out_labels float32 [n_rows,C,H,W] from the
+ *   ORIGINAL masks, C=2 (optic multilabel) or 1 (vessel); either output may be NULL.             */
+int aadg_u8_policy_normalize(const uint8_t* src_images, const uint8_t* src_masks,
+                             const aadg_aug_row_t* rows, int n_rows, int n_src, int height,
+                             int width, int dataset, float* out_images, float* out_labels,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
