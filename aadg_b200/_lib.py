@@ -21,6 +21,14 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "aadg_u8_policy_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                           c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "aadg_sinkhorn_small_max_points": (c_int, []),
+    "aadg_sinkhorn_small_batched": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "aadg_sinkhorn_rewards_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "aadg_sinkhorn_diversity_rewards": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "aadg_sinkhorn_large_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "aadg_sinkhorn_large": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
 }
 
 

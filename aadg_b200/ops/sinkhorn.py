@@ -1,0 +1,109 @@
+"""Sinkhorn diversity reward: torch-facing wrappers over aadg_sinkhorn_* (csrc/sinkhorn.cu).
+
+`SamplesLoss` keeps the constructor/call shape of geomloss.SamplesLoss as the reference uses it
+(search_dg.py:116,158-160): `SamplesLoss("sinkhorn", cost=<cosine KeOps formula>, backend="online")`
+then `loss(x[N,d], y[M,d]) -> 0-d tensor`, forward value only.  There is no CPU path."""
+import numpy as np
+import torch
+
+from .. import _lib
+
+COSINE_COST = "( IntCst(1) - (X | Y) / ( Norm2(X) * Norm2(Y) ) )"
+
+
+def _check(x):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise RuntimeError("aadg_b200.ops.sinkhorn: inputs must be CUDA tensors (no CPU path)")
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise ValueError("clouds must be float32 [N, d]")
+    return x.detach().contiguous()
+
+
+def small_max_points():
+    return _lib.lib().aadg_sinkhorn_small_max_points()
+
+
+def divergence_batched(points, problems):
+    """points float32 [R,d] (CUDA); problems int [P,4] rows (x_off, x_n, y_off, y_n) -> float32 [P],
+    one launch, no host sync."""
+    points = _check(points)
+    prob = torch.as_tensor(np.ascontiguousarray(problems, dtype=np.int32)).to(points.device, non_blocking=True)
+    out = torch.empty(prob.shape[0], dtype=torch.float32, device=points.device)
+    L = _lib.lib()
+    with torch.cuda.device(points.device):
+        _lib.check(L.aadg_sinkhorn_small_batched(_lib.ptr(points), _lib.ptr(prob), prob.shape[0],
+                                                 points.shape[1], _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def divergence_large(x, y, diameter=None):
+    """One divergence on big clouds (streamed cost matrices). Returns (0-d tensor, n_eps)."""
+    x, y = _check(x), _check(y)
+    if x.shape[1] != y.shape[1]:
+        raise ValueError("feature dimensions differ")
+    L = _lib.lib()
+    n, m, d = x.shape[0], y.shape[0], x.shape[1]
+    ws = _lib.workspace(L.aadg_sinkhorn_large_workspace_bytes(n, m, d), x.device)
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    nit = np.zeros(1, np.int32)
+    with torch.cuda.device(x.device):
+        _lib.check(L.aadg_sinkhorn_large(_lib.ptr(x), n, _lib.ptr(y), m, d,
+                                         float(diameter) if diameter else 0.0, _lib.ptr(out),
+                                         nit.ctypes.data, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return out[0], int(nit[0])
+
+
+def divergence(x, y, diameter=None):
+    x, y = _check(x), _check(y)
+    if max(x.shape[0], y.shape[0]) <= small_max_points() and diameter is None:
+        pts = torch.cat([x, y])
+        return divergence_batched(pts, [[0, x.shape[0], x.shape[0], y.shape[0]]])[0]
+    return divergence_large(x, y, diameter)[0]
+
+
+class SamplesLoss:
+    """geomloss.SamplesLoss call shape for the one configuration the reference uses."""
+
+    def __init__(self, loss="sinkhorn", p=2, blur=.05, reach=None, diameter=None, scaling=.5, truncate=5,
+                 cost=None, kernel=None, cluster_scale=None, debias=True, potentials=False, verbose=False,
+                 backend="auto"):
+        if loss != "sinkhorn" or p != 2 or blur != .05 or reach is not None or scaling != .5 \
+                or not debias or potentials:
+            raise NotImplementedError("only the reference's configuration is implemented: "
+                                      "sinkhorn, p=2, blur=.05, scaling=.5, debiased, balanced")
+        if cost is not None and "".join(cost.split()) != "".join(COSINE_COST.split()):
+            raise NotImplementedError("only the cosine cost of search_dg.py:116 is implemented")
+        if cost is None:
+            raise NotImplementedError("the squared-Euclidean default cost is not on the reference's path")
+        self.diameter = diameter
+
+    def __call__(self, x, y):
+        return divergence(x, y, self.diameter)
+
+    forward = __call__
+
+
+def diversity_rewards(domain_feature, domain_code, M, rewards=None):
+    """search_dg.py:150-162 in one launch.  domain_feature float32 [n,d], domain_code float32 [n,D]
+    (soft one-hot), rows ordered (b*D+d)*M+j.  Adds (d12+d13)+d23 to rewards[j] (created if None);
+    returns (rewards [M], pair_values [M, pairs])."""
+    f, dc = _check(domain_feature), _check(domain_code)
+    n, d = f.shape
+    nd = dc.shape[1]
+    if dc.shape[0] != n:
+        raise ValueError("domain_code rows != feature rows")
+    if rewards is None:
+        rewards = torch.zeros(M, dtype=torch.float32, device=f.device)
+    pairs = torch.empty((M, nd * (nd - 1) // 2), dtype=torch.float32, device=f.device)
+    L = _lib.lib()
+    ws = _lib.workspace(L.aadg_sinkhorn_rewards_workspace_bytes(M, nd), f.device)
+    with torch.cuda.device(f.device):
+        _lib.check(L.aadg_sinkhorn_diversity_rewards(_lib.ptr(f), _lib.ptr(dc), n, d, nd, M, _lib.ptr(rewards),
+                                                     _lib.ptr(pairs), _lib.ptr(ws), ws.numel(),
+                                                     _lib.stream_ptr()))
+    return rewards, pairs
+
+
+def normalize_rewards(rewards):
+    """search_dg.py:214."""
+    return (rewards - torch.mean(rewards)) / (torch.std(rewards) + 1e-5)

@@ -91,6 +91,43 @@ int aadg_u8_policy_normalize(const uint8_t* src_images, const uint8_t* src_masks
                              int width, int dataset, float* out_images, float* out_labels,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Sinkhorn diversity reward — replaces geomloss.SamplesLoss("sinkhorn", cost=<cosine KeOps formula>,
+ * backend="online") constructed at search_dg.py:116 / search_dg_2d.py:116 and called at
+ * search_dg.py:158-160 / search_dg_2d.py:159-161 (p=2, blur=.05, scaling=.5, debiased, uniform
+ * weights, forward value only), and the reward assembly of search_dg.py:150-162.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Largest cloud (points) the one-launch shared-memory kernels accept. */
+int aadg_sinkhorn_small_max_points(void);
+
+/* n_problems independent divergences in ONE launch, no host sync.
+ *   points float32 [*, dim] (device); problems int32 [n_problems,4] (device) = x_off, x_n, y_off, y_n
+ *   (row ranges of `points`, each 1..aadg_sinkhorn_small_max_points()); out float32 [n_problems]. */
+int aadg_sinkhorn_small_batched(const float* points, const int32_t* problems, int n_problems, int dim,
+                                float* out, void* stream);
+
+size_t aadg_sinkhorn_rewards_workspace_bytes(int n_policies, int n_domains);
+
+/* search_dg.py:150-162 in one launch: for every policy j the rows j::n_policies of `features`
+ * float32 [n_rows,dim] are split by argmax(domain_code[row,:]) (float32 [n_rows,n_domains]) into
+ * domain clouds; pair_values float32 [n_policies, n_pairs] receives the pairwise divergences in the
+ * reference's call order ((1,2),(2,3),(1,3) for three domains) and rewards[j] += (d12+d13)+d23.
+ * A cloud that is empty or larger than the small-kernel limit yields NaN for that pair. */
+int aadg_sinkhorn_diversity_rewards(const float* features, const float* domain_code, int n_rows, int dim,
+                                    int n_domains, int n_policies, float* rewards, float* pair_values,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
+size_t aadg_sinkhorn_large_workspace_bytes(int n, int m, int dim);
+
+/* One divergence between big clouds x float32 [n,dim], y float32 [m,dim]; out float32 [1] (device).
+ * The four cost matrices are materialised in the workspace (about 4*4*n*m bytes).  diameter > 0
+ * skips the data-diameter reduction and its host sync (geomloss' `diameter=` argument); otherwise
+ * the stream is synchronised once, like the reference's `.item()`.  n_iterations_out (HOST, may be
+ * NULL) receives the number of epsilon values (soft-min sweeps executed = that + 2). */
+int aadg_sinkhorn_large(const float* x, int n, const float* y, int m, int dim, float diameter, float* out,
+                        int* n_iterations_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,135 @@
+"""GPU: CUDA Sinkhorn (C ABI) against the float64 oracle.  Tolerance: 1e-4 relative (north star);
+the oracle's own fp32 restatement sits at ~1e-5 of the fp64 one on these inputs."""
+import numpy as np
+import pytest
+import torch
+
+from aadg_b200.synth import feature_cloud
+from oracle import sinkhorn as S
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def sk():
+    assert torch.cuda.is_available()
+    from aadg_b200.ops import sinkhorn as mod
+    return mod
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_native_shape_18_problems_one_launch(sk):
+    """the reference's real workload: 6 policies x 3 domain pairs of 8 points, d=128."""
+    clouds = [feature_cloud(8, 128, k, seed=100 + 7 * k) for k in range(18)]
+    pts = np.concatenate(clouds)
+    probs, want = [], []
+    for j in range(6):
+        for a, b in ((0, 1), (1, 2), (0, 2)):
+            ia, ib = 3 * j + a, 3 * j + b
+            probs.append([8 * ia, 8, 8 * ib, 8])
+            want.append(S.sinkhorn_divergence(clouds[ia], clouds[ib]))
+    got = sk.divergence_batched(dev(pts), probs).cpu().numpy()
+    assert np.allclose(got, want, rtol=RTOL, atol=1e-7), np.abs(got / np.array(want) - 1).max()
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 1, 4), (5, 8, 16), (37, 50, 32), (64, 64, 256), (64, 3, 7)])
+def test_small_shapes(sk, n, m, d):
+    x, y = feature_cloud(n, d, 0, seed=n), feature_cloud(m, d, 2, seed=m + 50)
+    got = float(sk.divergence(dev(x), dev(y)))
+    want = S.sinkhorn_divergence(x, y)
+    assert abs(got - want) <= RTOL * abs(want) + 2e-6, (got, want)
+
+
+def test_small_identity_and_symmetry(sk):
+    x, y = feature_cloud(16, 128, 0), feature_cloud(16, 128, 1)
+    assert abs(float(sk.divergence(dev(x), dev(x.copy())))) < 1e-5
+    a, b = float(sk.divergence(dev(x), dev(y))), float(sk.divergence(dev(y), dev(x)))
+    assert abs(a - b) <= 1e-5 * abs(a)
+
+
+def test_samples_loss_call_shape(sk):
+    loss = sk.SamplesLoss("sinkhorn", cost='( IntCst(1) - (X | Y) / ( Norm2(X) * Norm2(Y) ) )', backend='online')
+    x, y = feature_cloud(8, 128, 0), feature_cloud(8, 128, 1)
+    v = loss(dev(x), dev(y))
+    assert v.dim() == 0 and v.is_cuda
+    assert abs(float(v) - S.sinkhorn_divergence(x, y)) <= RTOL * abs(float(v))
+    with pytest.raises(NotImplementedError):
+        sk.SamplesLoss("sinkhorn", blur=0.1, cost=sk.COSINE_COST)
+    with pytest.raises(RuntimeError):
+        loss(torch.zeros(4, 4), torch.zeros(4, 4))
+
+
+def make_step_features(B=8, D=3, M=6, d=128, seed=0):
+    rng = np.random.RandomState(seed)
+    n = B * D * M
+    feat = np.zeros((n, d), np.float32)
+    dc = np.zeros((n, D), np.float32)
+    for b in range(B):
+        for k in range(D):
+            for j in range(M):
+                r = (b * D + k) * M + j
+                v = rng.randn(d).astype(np.float32) + 0.3 * k + 0.1 * j
+                feat[r] = np.where(v > 0, v, 0.2 * v)
+                soft = rng.rand(D) * 0.1
+                soft[k] = 0.8 + 0.2 * rng.rand()
+                dc[r] = soft
+    return feat, dc
+
+
+def test_diversity_rewards_fused(sk):
+    """search_dg.py:150-162 with the reference's row order (b*D+d)*M+j."""
+    feat, dc = make_step_features()
+    want_inc, want_vals = S.diversity_rewards(feat, dc, 6)
+    rewards = torch.full((6,), 1.5, device="cuda")
+    r, pairs = sk.diversity_rewards(dev(feat), dev(dc), 6, rewards)
+    assert np.allclose(pairs.cpu().numpy(), want_vals, rtol=RTOL, atol=1e-7)
+    assert np.allclose(r.cpu().numpy(), 1.5 + want_inc, rtol=RTOL)
+    # accumulates over steps and matches the normalisation of search_dg.py:214
+    r2, _ = sk.diversity_rewards(dev(feat), dev(dc), 6, r)
+    assert np.allclose(r2.cpu().numpy(), 1.5 + 2 * want_inc, rtol=RTOL)
+    nr = sk.normalize_rewards(r2 - 1.5).cpu().numpy()
+    assert np.allclose(nr, S.normalize_rewards(2 * want_inc), rtol=1e-3, atol=1e-4)
+
+
+def test_diversity_rewards_unbalanced_domains(sk):
+    feat, dc = make_step_features(B=5, seed=3)
+    # move a few rows to another domain so the clouds differ in size
+    dc[0:6] = dc[6:12]
+    want_inc, want_vals = S.diversity_rewards(feat, dc, 6)
+    r, pairs = sk.diversity_rewards(dev(feat), dev(dc), 6)
+    assert np.allclose(pairs.cpu().numpy(), want_vals, rtol=RTOL, atol=1e-7)
+    assert np.allclose(r.cpu().numpy(), want_inc, rtol=RTOL)
+
+
+@pytest.mark.parametrize("n,m,d", [(65, 70, 32), (300, 257, 64), (1024, 1024, 256), (1500, 901, 128)])
+def test_large_path_vs_oracle(sk, n, m, d):
+    x, y = feature_cloud(n, d, 0, seed=11), feature_cloud(m, d, 1, seed=12)
+    got, n_eps = sk.divergence_large(dev(x), dev(y))
+    want, info = S.sinkhorn_divergence(x, y, return_info=True)
+    assert n_eps == len(info["eps"])
+    assert abs(float(got) - want) <= RTOL * abs(want) + 1e-6, (float(got), want)
+
+
+def test_large_path_on_small_problem_matches_small_kernel(sk):
+    x, y = feature_cloud(40, 128, 0), feature_cloud(33, 128, 2)
+    a = float(sk.divergence(dev(x), dev(y)))
+    b = float(sk.divergence_large(dev(x), dev(y))[0])
+    assert abs(a - b) <= 2e-5 * abs(a)
+
+
+def test_large_properties_at_sweep_size(sk):
+    """N = 8192, d = 256 (BASELINE sweep point): symmetry, S(x,x) ~ 0, positivity, diameter override."""
+    x, y = dev(feature_cloud(8192, 256, 0)), dev(feature_cloud(8192, 256, 1))
+    sxy, n1 = sk.divergence_large(x, y)
+    syx, n2 = sk.divergence_large(y, x)
+    sxx, _ = sk.divergence_large(x, x.clone())
+    assert n1 == n2 and float(sxy) > 0
+    assert abs(float(sxy) - float(syx)) <= 1e-4 * float(sxy)
+    assert abs(float(sxx)) <= 1e-4 * float(sxy)
+    diam = S.max_diameter(x.cpu().numpy(), y.cpu().numpy())
+    sd, _ = sk.divergence_large(x, y, diameter=diam)
+    assert abs(float(sd) - float(sxy)) <= 1e-5 * float(sxy)
