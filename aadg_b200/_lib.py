@@ -29,6 +29,9 @@ SIGNATURES = {
     "aadg_sinkhorn_large_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "aadg_sinkhorn_large": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
                                      c_void_p, c_size_t, c_void_p]),
+    "aadg_conv_fprop_bf16": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 6 + [c_void_p] + [c_int] * 5 + [c_void_p]),
+    "aadg_conv_dgrad_bf16": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 6 + [c_void_p] + [c_int] * 5 + [c_void_p]),
+    "aadg_conv_wgrad_bf16": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 9 + [c_void_p, c_void_p]),
 }
 
 

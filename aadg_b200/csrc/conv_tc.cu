@@ -1,0 +1,567 @@
+// Convolution forward / data-gradient / weight-gradient as implicit GEMMs on tcgen05 + TMEM, operands
+// staged by tensor-map TMA (sm_100a only).
+//
+// Replaces the cuDNN convolutions behind `model(input)` / `seg_loss.backward()` of the reference
+// (search_dg.py:132,171; models/__init__.py:17-23 -> segmentation_models_pytorch DeepLabV3+/UNet).
+//
+// Data layout: activations bf16 NHWC (channel stride `ld` may exceed the channel count so that a
+// tensor can be a channel slice of a concat buffer), weights bf16 [tap][Cout][Cin] (forward / wgrad)
+// and [tap][Cin][Cout] (data gradient), fp32 accumulation in tensor memory.
+//
+//   fprop / dgrad ("igemm"): D[128 pixels, BN channels] = sum over taps and 64-channel blocks of
+//     A_tap[128 px, 64 ch] * W_tap[BN, 64 ch]^T.  The A tile of a tap is ONE 4-D TMA box
+//     (64 ch, TW, TH, TN) of the NHWC input shifted by the tap offset; image borders are the TMA's
+//     zero fill, strided convolutions use the box's element strides, dilation is just the offset.
+//     Both operands are K-major with the 128-byte swizzle.  Warp 0 = TMA producer, warp 1 = MMA
+//     issuer (one elected thread), warps 2-5 = epilogue (TMEM -> registers -> bf16 NHWC stores).
+//   wgrad: D[128 Cout, BN Cin] = sum over pixels dY[px, Cout]^T X[px + tap, Cin]: the pixel axis is K,
+//     so both operands are MN-major tiles (64-channel x 64-pixel boxes); split over pixel ranges
+//     across CTAs, fp32 `red.add` into dW.
+#include "tc_common.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace aadg {
+namespace tc {
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+int make_map_bf16(CUtensorMap* map, const void* base, int rank, const long long* dims,
+                  const long long* strides_elems, const int* box, const int* elem_strides) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return AADG_ECUDA; }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = (cuuint32_t)(elem_strides ? elem_strides[i] : 1);
+    if (i > 0) gs[i - 1] = (cuuint64_t)strides_elems[i - 1] * 2;
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %lld %lld %lld %lld box %d %d %d %d", (int)r, rank,
+              dims[0], rank > 1 ? dims[1] : 0, rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return AADG_ECUDA;
+  }
+  return AADG_OK;
+}
+
+constexpr int MAX_TAPS = 49;
+struct Taps {
+  int n;
+  short dy[MAX_TAPS], dx[MAX_TAPS], w[MAX_TAPS];
+};
+
+struct IgemmArgs {
+  int lg_tw, lg_th;             // log2 tile extents in x, y (the rest of the 128 rows spans images)
+  int tiles_x, tiles_y, tiles_n;
+  int Wsub, Hsub, Nimg;         // logical output grid of this launch
+  int in_step;                  // input coordinate = output coordinate * in_step + tap offset
+  int k_blocks;                 // ceil(Cin / 64)
+  __nv_bfloat16* out;
+  int ldc, c_off, Cout;         // output channel stride / offset / valid channel count
+  int Hout, Wout;               // physical output image size
+  int o_step, o_y0, o_x0;       // physical pixel = logical pixel * o_step + (o_y0, o_x0)
+  int accumulate;               // out += result
+  Taps taps;
+};
+
+constexpr int IG_THREADS = 192;
+constexpr int A_BYTES = 128 * 128;      // 128 pixel rows x 64 bf16
+
+template <int BN, int STAGES>
+constexpr int igemm_smem_bytes() { return STAGES * (A_BYTES + BN * 128) + 1024 + 256; }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const IgemmArgs a) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_map(&tmA); prefetch_map(&tmB); }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> logical output origin
+  int t = blockIdx.x;
+  const int tile_x = t % a.tiles_x; t /= a.tiles_x;
+  const int tile_y = t % a.tiles_y; t /= a.tiles_y;
+  const int tile_n = t;
+  const int lg_tn = 7 - a.lg_tw - a.lg_th;
+  const int sx0 = tile_x << a.lg_tw, sy0 = tile_y << a.lg_th, n_img0 = tile_n << lg_tn;
+  const int n0 = blockIdx.y * BN;
+  const int total_k = a.taps.n * a.k_blocks;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0, phase = 0;
+      for (int tap = 0; tap < a.taps.n; ++tap) {
+        const int ix = sx0 * a.in_step + a.taps.dx[tap], iy = sy0 * a.in_step + a.taps.dy[tap];
+        const int wi = a.taps.w[tap];
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_4d(sa, &tmA, &full[stage], kb * 64, ix, iy, n_img0);
+          tma_load_3d(sa + A_BYTES, &tmB, &full[stage], kb * 64, n0, wi);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0, phase = 0;
+      for (int k = 0; k < total_k; ++k) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = make_sdesc(sa, 16, 1024);
+        const uint64_t bdesc = make_sdesc(sa + A_BYTES, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte swizzled row
+          umma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 ; row m of the tile = lane of TMEM
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int tw = m & ((1 << a.lg_tw) - 1);
+    const int th = (m >> a.lg_tw) & ((1 << a.lg_th) - 1);
+    const int tn = m >> (a.lg_tw + a.lg_th);
+    const int sx = sx0 + tw, sy = sy0 + th, img = n_img0 + tn;
+    const bool valid = sx < a.Wsub && sy < a.Hsub && img < a.Nimg;
+    const size_t pix = ((size_t)img * a.Hout + (size_t)(sy * a.o_step + a.o_y0)) * a.Wout + (sx * a.o_step + a.o_x0);
+    __nv_bfloat16* orow = a.out + pix * a.ldc + a.c_off + n0;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (n0 + c + g * 8 < a.Cout) {
+            uint4* dst = (uint4*)(orow + c + g * 8);
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[g * 8 + e]);
+            if (a.accumulate) {
+              const uint4 old = *dst;
+              const __nv_bfloat162* ob = (const __nv_bfloat162*)&old;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 o2 = __bfloat1622float2(ob[e]);
+                f[2 * e] += o2.x; f[2 * e + 1] += o2.y;
+              }
+            }
+            uint4 v;
+            v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+            v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+            *dst = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- wgrad --------------------------------------------------------------------------------------------
+struct WgradArgs {
+  int lg_tw, lg_th;            // log2 extents of the 64-pixel K tile in x, y
+  int tiles_x, tiles_y, tiles_n;
+  int in_step;                 // X coordinate = dY coordinate * in_step + tap offset
+  int ksplit;                  // pixel tiles are dealt round-robin to ksplit CTAs
+  int Cout, Cin;
+  float* dw;                   // [taps][Cout][Cin] fp32, accumulated with red.add
+  Taps taps;
+};
+constexpr int WG_PIX = 64;
+constexpr int WG_A_BYTES = 2 * WG_PIX * 128;     // two 64-channel blocks of Cout
+
+template <int BN, int STAGES>
+constexpr int wgrad_smem_bytes() { return STAGES * (WG_A_BYTES + (BN / 64) * WG_PIX * 128) + 1024 + 256; }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(IG_THREADS) wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                           const __grid_constant__ CUtensorMap tmX,
+                                                           const WgradArgs a) {
+  constexpr int B_BYTES = (BN / 64) * WG_PIX * 128;
+  constexpr int STAGE_BYTES = WG_A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_map(&tmDY); prefetch_map(&tmX); }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int co0 = blockIdx.x * 128, ci0 = blockIdx.y * BN;
+  const int tap = blockIdx.z / a.ksplit, split = blockIdx.z % a.ksplit;
+  const int n_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int my_tiles = split < n_tiles ? (n_tiles - split + a.ksplit - 1) / a.ksplit : 0;
+  const int lg_tn = 6 - a.lg_tw - a.lg_th;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0, phase = 0;
+      const int dx = a.taps.dx[tap], dy = a.taps.dy[tap];
+      for (int i = 0; i < my_tiles; ++i) {
+        int t = split + i * a.ksplit;
+        const int tx = t % a.tiles_x; t /= a.tiles_x;
+        const int ty = t % a.tiles_y; t /= a.tiles_y;
+        const int ox = tx << a.lg_tw, oy = ty << a.lg_th, img = t << lg_tn;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        tma_load_4d(sa, &tmDY, &full[stage], co0, ox, oy, img);
+        tma_load_4d(sa + WG_PIX * 128, &tmDY, &full[stage], co0 + 64, ox, oy, img);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          tma_load_4d(sa + WG_A_BYTES + b * WG_PIX * 128, &tmX, &full[stage], ci0 + b * 64,
+                      ox * a.in_step + dx, oy * a.in_step + dy, img);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      int stage = 0, phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < WG_PIX / 16; ++kk) {   // 16 pixels = two 8-row groups = 2048 bytes per step
+          const uint64_t adesc = make_sdesc(sa + kk * 2048, WG_PIX * 128, 1024);
+          const uint64_t bdesc = make_sdesc(sa + WG_A_BYTES + kk * 2048, WG_PIX * 128, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | kk) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (my_tiles > 0) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    float* drow = a.dw + ((size_t)tap * a.Cout + co) * a.Cin + ci0;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      if (co < a.Cout) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (ci0 + c + g * 4 < a.Cin) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c + g * 4),
+                         "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
+                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                         : "memory");
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host ---------------------------------------------------------------------------------------------
+static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// split 2^total rows of a tile between x, y (and images): x first, then y
+static void pick_tile(int W, int H, int total_lg, int* lg_tw, int* lg_th) {
+  *lg_tw = std::min(ilog2_ceil(W), total_lg);
+  *lg_th = std::min(ilog2_ceil(H), total_lg - *lg_tw);
+}
+
+struct ConvGeom {
+  int N, H, W, Cin, ldx;        // input
+  int Ho, Wo, Cout, ldy;        // output
+  int R, S, stride, pad, dil;
+};
+
+template <int BN, int STAGES>
+static int launch_igemm_t(const CUtensorMap& mA, const CUtensorMap& mB, const IgemmArgs& args, int cout_tiles,
+                          cudaStream_t st) {
+  const int smem = igemm_smem_bytes<BN, STAGES>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(args.tiles_x * args.tiles_y * args.tiles_n, cout_tiles);
+  igemm_kernel<BN, STAGES><<<grid, IG_THREADS, smem, st>>>(mA, mB, args);
+  return check_launch("igemm kernel");
+}
+
+// One implicit-GEMM launch.  in: bf16 [Nimg, Hin, Win, ld_in] (Cin channels used); wgt: bf16 [n_w_taps][Cn][Cin];
+// logical output grid Wsub x Hsub mapped to physical pixels by (o_step, o_y0, o_x0).
+static int launch_igemm(const void* in, int Nimg, int Hin, int Win, int Cin, int ld_in, int in_step,
+                        const void* wgt, int n_w_taps, int Cn, const Taps& taps, int Wsub, int Hsub, void* out,
+                        int Hout, int Wout, int ldc, int c_off, int o_step, int o_y0, int o_x0, int accumulate,
+                        cudaStream_t st) {
+  AADG_REQUIRE(ld_in % 8 == 0 && ldc % 8 == 0 && c_off % 8 == 0 && Cn % 8 == 0 && Cin % 8 == 0,
+               "channel counts/strides must be multiples of 8 (Cin %d ld_in %d Cout %d ldc %d off %d)", Cin, ld_in,
+               Cn, ldc, c_off);
+  AADG_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)wgt & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "tensors must be 16-byte aligned");
+  IgemmArgs a{};
+  pick_tile(Wsub, Hsub, 7, &a.lg_tw, &a.lg_th);
+  const int lg_tn = 7 - a.lg_tw - a.lg_th;
+  a.tiles_x = (Wsub + (1 << a.lg_tw) - 1) >> a.lg_tw;
+  a.tiles_y = (Hsub + (1 << a.lg_th) - 1) >> a.lg_th;
+  a.tiles_n = (Nimg + (1 << lg_tn) - 1) >> lg_tn;
+  a.Wsub = Wsub; a.Hsub = Hsub; a.Nimg = Nimg;
+  a.in_step = in_step;
+  a.k_blocks = (Cin + 63) / 64;
+  a.out = (__nv_bfloat16*)out;
+  a.ldc = ldc; a.c_off = c_off; a.Cout = Cn;
+  a.Hout = Hout; a.Wout = Wout;
+  a.o_step = o_step; a.o_y0 = o_y0; a.o_x0 = o_x0;
+  a.accumulate = accumulate;
+  a.taps = taps;
+  AADG_REQUIRE((1 << a.lg_tw) * in_step <= 256 && (1 << a.lg_th) * in_step <= 256, "tile box too large");
+
+  CUtensorMap mA, mB;
+  {
+    const long long dims[4] = {Cin, Win, Hin, Nimg};
+    const long long strides[3] = {ld_in, (long long)Win * ld_in, (long long)Hin * Win * ld_in};
+    const int box[4] = {64, (1 << a.lg_tw) * in_step, (1 << a.lg_th) * in_step, 1 << lg_tn};
+    const int es[4] = {1, in_step, in_step, 1};
+    int rc = make_map_bf16(&mA, in, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  const int bn = Cn <= 64 ? 64 : 128;
+  {
+    const long long dims[3] = {Cin, Cn, n_w_taps};
+    const long long strides[2] = {Cin, (long long)Cn * Cin};
+    const int box[3] = {64, bn, 1};
+    int rc = make_map_bf16(&mB, wgt, 3, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  const int cout_tiles = (Cn + bn - 1) / bn;
+  if (bn == 64) return launch_igemm_t<64, 4>(mA, mB, a, cout_tiles, st);
+  return launch_igemm_t<128, 4>(mA, mB, a, cout_tiles, st);
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad_t(const CUtensorMap& mDY, const CUtensorMap& mX, const WgradArgs& args, dim3 grid,
+                          cudaStream_t st) {
+  const int smem = wgrad_smem_bytes<BN, STAGES>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  wgrad_kernel<BN, STAGES><<<grid, IG_THREADS, smem, st>>>(mDY, mX, args);
+  return check_launch("wgrad kernel");
+}
+
+}  // namespace tc
+}  // namespace aadg
+
+using namespace aadg;
+using namespace aadg::tc;
+
+static int check_geom(const ConvGeom& g) {
+  AADG_REQUIRE(g.N > 0 && g.H > 0 && g.W > 0 && g.Cin > 0 && g.Cout > 0, "bad tensor sizes");
+  AADG_REQUIRE(g.R > 0 && g.S > 0 && g.R * g.S <= MAX_TAPS, "filter %dx%d not supported (max %d taps)", g.R, g.S, MAX_TAPS);
+  AADG_REQUIRE(g.stride == 1 || g.stride == 2, "stride %d not supported", g.stride);
+  AADG_REQUIRE(g.dil >= 1 && g.pad >= 0, "bad dilation/padding");
+  const int ho = (g.H + 2 * g.pad - g.dil * (g.R - 1) - 1) / g.stride + 1;
+  const int wo = (g.W + 2 * g.pad - g.dil * (g.S - 1) - 1) / g.stride + 1;
+  AADG_REQUIRE(ho == g.Ho && wo == g.Wo, "output size mismatch: expected %dx%d, got %dx%d", ho, wo, g.Ho, g.Wo);
+  return AADG_OK;
+}
+
+extern "C" {
+
+/* y[n,oy,ox,c_off+co] (+)= sum_{r,s,ci} x[n, oy*stride-pad+r*dil, ox*stride-pad+s*dil, ci] * w[r*S+s][co][ci] */
+int aadg_conv_fprop_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* wgt, int cout, int r,
+                         int s, int stride, int pad, int dil, void* y, int ho, int wo, int ldy, int y_c_off,
+                         int accumulate, void* stream) {
+  ConvGeom g{n, h, w, cin, ldx, ho, wo, cout, ldy, r, s, stride, pad, dil};
+  int rc = check_geom(g);
+  if (rc) return rc;
+  Taps taps{};
+  taps.n = r * s;
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < s; ++j) {
+      taps.dy[i * s + j] = (short)(i * dil - pad);
+      taps.dx[i * s + j] = (short)(j * dil - pad);
+      taps.w[i * s + j] = (short)(i * s + j);
+    }
+  return launch_igemm(x, n, h, w, cin, ldx, stride, wgt, r * s, cout, taps, wo, ho, y, ho, wo, ldy, y_c_off, 1, 0, 0,
+                      accumulate, (cudaStream_t)stream);
+}
+
+/* dx[n,iy,ix,c_off+ci] (+)= sum over (r,s,co) with iy = oy*stride-pad+r*dil of dy[n,oy,ox,co] * wt[r*S+s][ci][co]
+ * (wt = the forward weights with the two channel axes swapped).  Geometry arguments are the FORWARD
+ * convolution's. */
+int aadg_conv_dgrad_bf16(const void* dy, int n, int ho, int wo, int cout, int lddy, const void* wgt_t, int cin,
+                         int r, int s, int stride, int pad, int dil, void* dx, int h, int w, int lddx,
+                         int dx_c_off, int accumulate, void* stream) {
+  ConvGeom g{n, h, w, cin, lddx, ho, wo, cout, lddy, r, s, stride, pad, dil};
+  int rc = check_geom(g);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int py = 0; py < stride; ++py)
+    for (int px = 0; px < stride; ++px) {
+      const int hsub = (h - py + stride - 1) / stride, wsub = (w - px + stride - 1) / stride;
+      if (hsub <= 0 || wsub <= 0) continue;
+      Taps taps{};
+      for (int i = 0; i < r; ++i) {
+        const int ty = py + pad - i * dil;
+        if (ty % stride) continue;
+        for (int j = 0; j < s; ++j) {
+          const int tx = px + pad - j * dil;
+          if (tx % stride) continue;
+          // floor division is exact here (ty, tx are multiples of stride, possibly negative)
+          taps.dy[taps.n] = (short)(ty / stride);
+          taps.dx[taps.n] = (short)(tx / stride);
+          taps.w[taps.n] = (short)(i * s + j);
+          ++taps.n;
+        }
+      }
+      if (taps.n == 0) {
+        // positions of this parity class receive no gradient: write zeros unless accumulating
+        if (!accumulate) {
+          AADG_REQUIRE(stride == 2 && cin == lddx && dx_c_off == 0,
+                       "zero-fill of untouched pixels needs a dense dx tensor");
+          // rows py, py+2, ...: every pixel px, px+2, ... -> strided 2-D memset
+          for (int img = 0; img < n; ++img)
+            for (int yy = py; yy < h; yy += stride) {
+              char* row = (char*)dx + (((size_t)img * h + yy) * w + px) * (size_t)lddx * 2;
+              AADG_CUDA_TRY(cudaMemset2DAsync(row, (size_t)stride * lddx * 2, 0, (size_t)cin * 2, wsub, st));
+            }
+        }
+        continue;
+      }
+      rc = launch_igemm(dy, n, ho, wo, cout, lddy, 1, wgt_t, r * s, cin, taps, wsub, hsub, dx, h, w, lddx, dx_c_off,
+                        stride, py, px, accumulate, st);
+      if (rc) return rc;
+    }
+  return AADG_OK;
+}
+
+/* dw[r*S+s][co][ci] += sum_{n,oy,ox} dy[n,oy,ox,co] * x[n, oy*stride-pad+r*dil, ox*stride-pad+s*dil, ci]
+ * (fp32, accumulated: zero dw first for a fresh gradient). */
+int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo,
+                         int cout, int lddy, int r, int s, int stride, int pad, int dil, float* dw, void* stream) {
+  ConvGeom g{n, h, w, cin, ldx, ho, wo, cout, lddy, r, s, stride, pad, dil};
+  int rc = check_geom(g);
+  if (rc) return rc;
+  AADG_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && cin % 8 == 0 && cout % 8 == 0, "channels must be multiples of 8");
+  AADG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dw & 15) == 0 && cin % 4 == 0,
+               "tensors must be 16-byte aligned");
+  WgradArgs a{};
+  pick_tile(wo, ho, 6, &a.lg_tw, &a.lg_th);
+  const int lg_tn = 6 - a.lg_tw - a.lg_th;
+  a.tiles_x = (wo + (1 << a.lg_tw) - 1) >> a.lg_tw;
+  a.tiles_y = (ho + (1 << a.lg_th) - 1) >> a.lg_th;
+  a.tiles_n = (n + (1 << lg_tn) - 1) >> lg_tn;
+  a.in_step = stride;
+  a.Cout = cout; a.Cin = cin; a.dw = dw;
+  a.taps.n = r * s;
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < s; ++j) {
+      a.taps.dy[i * s + j] = (short)(i * dil - pad);
+      a.taps.dx[i * s + j] = (short)(j * dil - pad);
+      a.taps.w[i * s + j] = (short)(i * s + j);
+    }
+  const int bn = cin <= 64 ? 64 : 128;
+  const int n_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int base_ctas = ((cout + 127) / 128) * ((cin + bn - 1) / bn) * r * s;
+  int ksplit = (148 * 4 + base_ctas - 1) / base_ctas;
+  ksplit = std::max(1, std::min(ksplit, (n_tiles + 7) / 8));
+  ksplit = std::min(ksplit, 65535 / (r * s));
+  a.ksplit = ksplit;
+  CUtensorMap mDY, mX;
+  {
+    const long long dims[4] = {cout, wo, ho, n};
+    const long long strides[3] = {lddy, (long long)wo * lddy, (long long)ho * wo * lddy};
+    const int box[4] = {64, 1 << a.lg_tw, 1 << a.lg_th, 1 << lg_tn};
+    rc = make_map_bf16(&mDY, dy, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    const long long dims[4] = {cin, w, h, n};
+    const long long strides[3] = {ldx, (long long)w * ldx, (long long)h * w * ldx};
+    const int box[4] = {64, (1 << a.lg_tw) * stride, (1 << a.lg_th) * stride, 1 << lg_tn};
+    const int es[4] = {1, stride, stride, 1};
+    AADG_REQUIRE(box[1] <= 256 && box[2] <= 256, "tile box too large");
+    rc = make_map_bf16(&mX, x, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  dim3 grid((cout + 127) / 128, (cin + bn - 1) / bn, r * s * ksplit);
+  if (bn == 64) return launch_wgrad_t<64, 4>(mDY, mX, a, grid, (cudaStream_t)stream);
+  return launch_wgrad_t<128, 4>(mDY, mX, a, grid, (cudaStream_t)stream);
+}
+
+}  // extern "C"

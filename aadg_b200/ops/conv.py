@@ -1,0 +1,69 @@
+"""Convolutions on tcgen05 tensor cores: torch-facing wrappers over aadg_conv_* (csrc/conv_tc.cu).
+
+Tensors are bf16 NHWC views (`[N,H,W,C]`, channel stride = x.stride(2), which may exceed C when the
+tensor is a channel slice of a concat buffer).  Weights: bf16 `[R*S, Cout, Cin]` (fprop/wgrad) and
+`[R*S, Cin, Cout]` (dgrad).  There is no CPU path."""
+import torch
+
+from .. import _lib
+
+
+def _nhwc(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4):
+        raise RuntimeError("%s must be a CUDA bf16 [N,H,W,C] tensor (no CPU path)" % name)
+    n, h, w, c = t.shape
+    ld = t.stride(2)
+    if t.stride(3) != 1 or t.stride(1) != w * ld or t.stride(0) != h * w * ld:
+        raise ValueError("%s must be NHWC-contiguous up to a channel stride" % name)
+    return n, h, w, c, ld
+
+
+def out_size(h, w, r, s, stride, pad, dil):
+    return ((h + 2 * pad - dil * (r - 1) - 1) // stride + 1, (w + 2 * pad - dil * (s - 1) - 1) // stride + 1)
+
+
+def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False):
+    """x [N,H,W,Cin] bf16, wgt [R*S,Cout,Cin] bf16 -> y [N,Ho,Wo,Cout] bf16 (or written into `out`)."""
+    n, h, w, cin, ldx = _nhwc(x, "x")
+    cout = wgt.shape[1]
+    assert wgt.shape == (r * s, cout, cin) and wgt.dtype == torch.bfloat16 and wgt.is_contiguous()
+    ho, wo = out_size(h, w, r, s, stride, pad, dil)
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+    _, oh, ow, oc, ldy = _nhwc(out, "out")
+    assert (oh, ow, oc) == (ho, wo, cout)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().aadg_conv_fprop_bf16(x.data_ptr(), n, h, w, cin, ldx, wgt.data_ptr(), cout, r, s, stride,
+                                                   pad, dil, out.data_ptr(), ho, wo, ldy, 0, int(accumulate),
+                                                   _lib.stream_ptr()))
+    return out
+
+
+def dgrad(dy, wgt_t, r, s, stride, pad, dil, in_hw, out=None, accumulate=False):
+    """dy [N,Ho,Wo,Cout] bf16, wgt_t [R*S,Cin,Cout] bf16 -> dx [N,H,W,Cin] bf16."""
+    n, ho, wo, cout, lddy = _nhwc(dy, "dy")
+    cin = wgt_t.shape[1]
+    assert wgt_t.shape == (r * s, cin, cout) and wgt_t.dtype == torch.bfloat16 and wgt_t.is_contiguous()
+    h, w = in_hw
+    if out is None:
+        out = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=dy.device)
+    _, xh, xw, xc, lddx = _nhwc(out, "out")
+    assert (xh, xw, xc) == (h, w, cin)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.lib().aadg_conv_dgrad_bf16(dy.data_ptr(), n, ho, wo, cout, lddy, wgt_t.data_ptr(), cin, r, s,
+                                                   stride, pad, dil, out.data_ptr(), h, w, lddx, 0, int(accumulate),
+                                                   _lib.stream_ptr()))
+    return out
+
+
+def wgrad(x, dy, r, s, stride, pad, dil, out=None):
+    """x [N,H,W,Cin], dy [N,Ho,Wo,Cout] bf16 -> dw [R*S,Cout,Cin] fp32 (accumulated into `out`)."""
+    n, h, w, cin, ldx = _nhwc(x, "x")
+    _, ho, wo, cout, lddy = _nhwc(dy, "dy")
+    if out is None:
+        out = torch.zeros((r * s, cout, cin), dtype=torch.float32, device=x.device)
+    assert out.shape == (r * s, cout, cin) and out.dtype == torch.float32 and out.is_contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().aadg_conv_wgrad_bf16(x.data_ptr(), n, h, w, cin, ldx, dy.data_ptr(), ho, wo, cout, lddy,
+                                                   r, s, stride, pad, dil, out.data_ptr(), _lib.stream_ptr()))
+    return out

@@ -128,6 +128,30 @@ size_t aadg_sinkhorn_large_workspace_bytes(int n, int m, int dim);
 int aadg_sinkhorn_large(const float* x, int n, const float* y, int m, int dim, float diameter, float* out,
                         int* n_iterations_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Segmentation-net convolutions — replace the cuDNN convolutions behind `model(input)` and
+ * `seg_loss.backward()` (search_dg.py:132,171; models/__init__.py:17-23: smp.DeepLabV3Plus / Unet).
+ * Activations bf16 NHWC with a channel stride (`ld*`, elements) so a tensor may be a channel slice
+ * of a wider (concat) buffer; fp32 accumulation on tcgen05 tensor cores; channel counts, strides and
+ * offsets are multiples of 8; stride 1 or 2; any dilation; filters up to 7x7.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* y[n,oy,ox,y_c_off+co] (+)= sum x[n, oy*stride-pad+r*dil, ox*stride-pad+s*dil, ci] * w[r*S+s][co][ci]
+ *   x bf16 [n,h,w,ldx]; w bf16 [R*S][cout][cin]; y bf16 [n,ho,wo,ldy]. */
+int aadg_conv_fprop_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* wgt, int cout, int r,
+                         int s, int stride, int pad, int dil, void* y, int ho, int wo, int ldy, int y_c_off,
+                         int accumulate, void* stream);
+
+/* Data gradient of the same convolution: dx (+)= conv_transpose(dy, w).  wgt_t bf16 [R*S][cin][cout]
+ * (channel axes swapped); all geometry arguments are the forward convolution's. */
+int aadg_conv_dgrad_bf16(const void* dy, int n, int ho, int wo, int cout, int lddy, const void* wgt_t, int cin,
+                         int r, int s, int stride, int pad, int dil, void* dx, int h, int w, int lddx,
+                         int dx_c_off, int accumulate, void* stream);
+
+/* Weight gradient: dw fp32 [R*S][cout][cin] += sum over pixels of dy (x) x  (zero dw for a fresh one). */
+int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo,
+                         int cout, int lddy, int r, int s, int stride, int pad, int dil, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

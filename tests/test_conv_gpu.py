@@ -1,0 +1,116 @@
+"""GPU: tcgen05 convolution kernels (C ABI) against torch fp32 convolutions of the same bf16-rounded
+operands.  Tolerance: fp32 accumulation of bf16 products, bf16 output rounding (2^-8 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def conv():
+    assert torch.cuda.is_available()
+    from aadg_b200.ops import conv as mod
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return mod
+
+
+def rand_case(n, h, w, cin, cout, r, s, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, r, s, device="cuda", generator=g) / (cin * r * s) ** 0.5).bfloat16()
+    return x, wt
+
+
+def to_taps(wt):       # [Cout,Cin,R,S] -> [R*S,Cout,Cin]
+    co, ci, r, s = wt.shape
+    return wt.permute(2, 3, 0, 1).reshape(r * s, co, ci).contiguous()
+
+
+def to_taps_t(wt):     # [Cout,Cin,R,S] -> [R*S,Cin,Cout]
+    co, ci, r, s = wt.shape
+    return wt.permute(2, 3, 1, 0).reshape(r * s, ci, co).contiguous()
+
+
+CASES = [
+    # n, h, w, cin, cout, r, s, stride, pad, dil
+    (2, 16, 16, 64, 64, 1, 1, 1, 0, 1),
+    (2, 16, 16, 64, 128, 3, 3, 1, 1, 1),
+    (3, 20, 12, 128, 64, 3, 3, 1, 1, 1),
+    (2, 32, 32, 64, 256, 1, 1, 1, 0, 1),
+    (2, 32, 32, 128, 128, 3, 3, 2, 1, 1),
+    (2, 32, 32, 256, 512, 1, 1, 2, 0, 1),
+    (2, 16, 16, 512, 512, 3, 3, 1, 2, 2),
+    (1, 32, 32, 256, 256, 3, 3, 1, 12, 12),
+    (5, 8, 8, 2048, 256, 1, 1, 1, 0, 1),
+    (2, 64, 64, 304, 256, 3, 3, 1, 1, 1),
+    (2, 64, 64, 256, 48, 1, 1, 1, 0, 1),
+    (1, 130, 70, 64, 64, 3, 3, 1, 1, 1),
+    (2, 17, 19, 192, 64, 1, 1, 1, 0, 1),
+    (1, 30, 30, 64, 64, 7, 7, 2, 3, 1),
+]
+
+
+def ref_conv(x, wt, stride, pad, dil):
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), stride=stride, padding=pad, dilation=dil)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def close(got, want, what):
+    err = (got.float() - want).abs().max().item()
+    scale = want.abs().max().item() + 1e-6
+    assert err <= 1.2e-2 * scale, (what, err, scale)
+    # bf16 output rounding dominates: mean error must be far smaller
+    assert (got.float() - want).abs().mean().item() <= 2.5e-3 * scale, what
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fprop(conv, case):
+    n, h, w, cin, cout, r, s, stride, pad, dil = case
+    x, wt = rand_case(n, h, w, cin, cout, r, s)
+    y = conv.fprop(x, to_taps(wt), r, s, stride, pad, dil)
+    close(y, ref_conv(x, wt, stride, pad, dil), case)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_dgrad(conv, case):
+    n, h, w, cin, cout, r, s, stride, pad, dil = case
+    x, wt = rand_case(n, h, w, cin, cout, r, s, seed=1)
+    ho, wo = conv.out_size(h, w, r, s, stride, pad, dil)
+    dy = torch.randn(n, ho, wo, cout, device="cuda").bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.conv2d(xr, wt.float(), stride=stride, padding=pad, dilation=dil).backward(dy.float().permute(0, 3, 1, 2))
+    want = xr.grad.permute(0, 2, 3, 1).contiguous()
+    got = conv.dgrad(dy, to_taps_t(wt), r, s, stride, pad, dil, (h, w))
+    close(got, want, case)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_wgrad(conv, case):
+    n, h, w, cin, cout, r, s, stride, pad, dil = case
+    x, wt = rand_case(n, h, w, cin, cout, r, s, seed=2)
+    ho, wo = conv.out_size(h, w, r, s, stride, pad, dil)
+    dy = torch.randn(n, ho, wo, cout, device="cuda").bfloat16()
+    wr = wt.float().requires_grad_(True)
+    F.conv2d(x.float().permute(0, 3, 1, 2), wr, stride=stride, padding=pad, dilation=dil).backward(
+        dy.float().permute(0, 3, 1, 2))
+    want = wr.grad.permute(2, 3, 0, 1).reshape(r * s, cout, cin)
+    got = conv.wgrad(x, dy, r, s, stride, pad, dil)
+    err = (got - want).abs().max().item()
+    assert err <= 2e-3 * (want.abs().max().item() + 1e-6), (case, err)
+
+
+def test_channel_slices_and_accumulate(conv):
+    """concat buffers: read a channel slice, write into a channel slice, accumulate into the output."""
+    x_full = torch.randn(2, 16, 16, 192, device="cuda").bfloat16()
+    x = x_full[..., 64:192]
+    _, wt = rand_case(1, 1, 1, 128, 64, 3, 3, seed=3)
+    out_full = torch.zeros(2, 16, 16, 256, device="cuda", dtype=torch.bfloat16)
+    out = out_full[..., 128:192]
+    conv.fprop(x, to_taps(wt), 3, 3, 1, 1, 1, out=out)
+    want = ref_conv(x.contiguous(), wt, 1, 1, 1)
+    close(out, want, "slice")
+    assert out_full[..., :128].abs().max() == 0 and out_full[..., 192:].abs().max() == 0
+    conv.fprop(x, to_taps(wt), 3, 3, 1, 1, 1, out=out, accumulate=True)
+    close(out, 2 * want, "accumulate")
