@@ -12,27 +12,43 @@ _lib = None
 c_void_p, c_int, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
 c_i64 = ctypes.c_int64
 
+ROOT = os.path.dirname(HERE)
+HEADER = os.path.join(ROOT, "include", "aadg_b200.h")
+
+
+def _ctype(decl):
+    """C parameter / return type -> ctypes type (pointers are passed as integers / None)."""
+    d = decl.replace("const", " ").strip()
+    if "*" in d:
+        return ctypes.c_char_p if d.replace(" ", "") == "char*" else c_void_p
+    d = " ".join(d.split())
+    return {"int": c_int, "float": c_float, "size_t": c_size_t, "long long": ctypes.c_longlong,
+            "unsigned long long": ctypes.c_ulonglong, "void": None}[d]
+
+
+def _parse_header(path=HEADER):
+    """{name: (restype, [argtypes])} for every aadg_* prototype in include/aadg_b200.h."""
+    import re
+    text = re.sub(r"/\*.*?\*/", " ", open(path).read(), flags=re.S)
+    text = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith("#"))
+    sigs = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(aadg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, params = m.group(1), m.group(2), m.group(3)
+        args = []
+        for prm in params.split(","):
+            prm = prm.strip()
+            if prm in ("void", ""):
+                continue
+            prm = re.sub(r"\[.*\]", "*", prm)
+            # drop the parameter name (last identifier) unless the declaration is a bare type
+            mm = re.match(r"(.*?[\*\s])([A-Za-z_]\w*)$", prm)
+            args.append(_ctype(mm.group(1) if mm else prm))
+        sigs[name] = (_ctype(ret), args)
+    return sigs
+
+
 # name -> (restype, argtypes); every symbol include/aadg_b200.h declares
-SIGNATURES = {
-    "aadg_version": (c_int, []),
-    "aadg_last_error": (ctypes.c_char_p, []),
-    "aadg_u8_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "aadg_u8_apply_policy": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                      c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "aadg_u8_policy_normalize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                          c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "aadg_sinkhorn_small_max_points": (c_int, []),
-    "aadg_sinkhorn_small_batched": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "aadg_sinkhorn_rewards_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "aadg_sinkhorn_diversity_rewards": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                                 c_void_p, c_void_p, c_size_t, c_void_p]),
-    "aadg_sinkhorn_large_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "aadg_sinkhorn_large": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
-                                     c_void_p, c_size_t, c_void_p]),
-    "aadg_conv_fprop_bf16": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 6 + [c_void_p] + [c_int] * 5 + [c_void_p]),
-    "aadg_conv_dgrad_bf16": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 6 + [c_void_p] + [c_int] * 5 + [c_void_p]),
-    "aadg_conv_wgrad_bf16": (c_int, [c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 9 + [c_void_p, c_void_p]),
-}
+SIGNATURES = _parse_header()
 
 
 def lib():
@@ -51,7 +67,12 @@ def lib():
     return _lib
 
 
+CALLS = 0   # C-ABI compute calls made so far (every one launches at least one kernel of this library)
+
+
 def check(rc):
+    global CALLS
+    CALLS += 1
     if rc != 0:
         raise RuntimeError("libaadg_b200: error %d: %s" % (rc, lib().aadg_last_error().decode()))
 

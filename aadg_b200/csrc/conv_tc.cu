@@ -471,6 +471,22 @@ int aadg_conv_dgrad_bf16(const void* dy, int n, int ho, int wo, int cout, int ld
   int rc = check_geom(g);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate && stride > 1) {
+    // parity classes that no filter tap reaches (e.g. the odd pixels of a strided 1x1) get zero gradient
+    bool any_empty = false;
+    for (int py = 0; py < stride; ++py)
+      for (int px = 0; px < stride; ++px) {
+        int cnt = 0;
+        for (int i = 0; i < r; ++i)
+          for (int j = 0; j < s; ++j)
+            if ((py + pad - i * dil) % stride == 0 && (px + pad - j * dil) % stride == 0) ++cnt;
+        any_empty |= cnt == 0;
+      }
+    if (any_empty) {
+      AADG_REQUIRE(cin == lddx && dx_c_off == 0, "zero-fill of untouched pixels needs a dense dx tensor");
+      AADG_CUDA_TRY(cudaMemsetAsync(dx, 0, (size_t)n * h * w * lddx * 2, st));
+    }
+  }
   for (int py = 0; py < stride; ++py)
     for (int px = 0; px < stride; ++px) {
       const int hsub = (h - py + stride - 1) / stride, wsub = (w - px + stride - 1) / stride;
@@ -489,20 +505,7 @@ int aadg_conv_dgrad_bf16(const void* dy, int n, int ho, int wo, int cout, int ld
           ++taps.n;
         }
       }
-      if (taps.n == 0) {
-        // positions of this parity class receive no gradient: write zeros unless accumulating
-        if (!accumulate) {
-          AADG_REQUIRE(stride == 2 && cin == lddx && dx_c_off == 0,
-                       "zero-fill of untouched pixels needs a dense dx tensor");
-          // rows py, py+2, ...: every pixel px, px+2, ... -> strided 2-D memset
-          for (int img = 0; img < n; ++img)
-            for (int yy = py; yy < h; yy += stride) {
-              char* row = (char*)dx + (((size_t)img * h + yy) * w + px) * (size_t)lddx * 2;
-              AADG_CUDA_TRY(cudaMemset2DAsync(row, (size_t)stride * lddx * 2, 0, (size_t)cin * 2, wsub, st));
-            }
-        }
-        continue;
-      }
+      if (taps.n == 0) continue;   // untouched pixels were zeroed above
       rc = launch_igemm(dy, n, ho, wo, cout, lddy, 1, wgt_t, r * s, cin, taps, wsub, hsub, dx, h, w, lddx, dx_c_off,
                         stride, py, px, accumulate, st);
       if (rc) return rc;

@@ -1,0 +1,692 @@
+// HBM-bound layers of the segmentation net (bf16 NHWC, 8 channels = 16 bytes per thread access):
+// batch-norm statistics / apply / backward (with fused ReLU, residual add and dropout), max-pool,
+// bilinear up-sampling (align_corners=True), global average pool / broadcast, depthwise 3x3
+// (dilated) convolution forward / data / weight gradient, im2col for the 3-channel stem, Adam with
+// the bf16 weight re-layout.  They replace the cuDNN / ATen kernels behind smp.DeepLabV3Plus
+// (models/__init__.py:17-23; search_dg.py:132,170-172; scheduler.py:10-11).
+#include <cuda_bf16.h>
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace aadg {
+namespace nn {
+
+typedef __nv_bfloat16 bf16;
+
+struct V8 { float v[8]; };
+
+__device__ __forceinline__ V8 ld8(const bf16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  V8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
+  return r;
+}
+__device__ __forceinline__ void st8(bf16* p, const V8& a) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ V8 ld8f(const float* p) {
+  V8 r;
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// Philox4x32-10 -> 4 uniform words; key (seed lo, seed hi), counter (idx lo, idx hi, stream, 0)
+__device__ __forceinline__ uint4 philox(uint2 key, uint4 ctr) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// keep-mask of 8 consecutive elements starting at element index e (p = 0.5): bit i of the result
+__device__ __forceinline__ unsigned int dropout_bits8(unsigned long long seed, unsigned long long e) {
+  const uint4 r = philox(make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)),
+                         make_uint4((unsigned int)(e >> 3), (unsigned int)(e >> 35), 0x5eedu, 0u));
+  return r.x & 0xffu;
+}
+
+// ---- batch-norm ------------------------------------------------------------------------------------
+// grid-stride over pixels; thread (tx, ty): tx = 8-channel group, ty = pixel lane
+template <int NACC, class F>
+__device__ __forceinline__ void channel_reduce(int P, int C, float* out0, float* out1, F&& f) {
+  // f(pixel, group, acc0[8], acc1[8]) accumulates; results atomically added to out0/out1[C]
+  const int G = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float a0[8] = {}, a1[8] = {};
+  if (tx < G)
+    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y)
+      f((int)p, tx, a0, a1);
+  __shared__ float s0[2048], s1[2048];
+  for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) { s0[i] = 0.f; s1[i] = 0.f; }
+  __syncthreads();
+  if (tx < G) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s0[tx * 8 + i], a0[i]);
+      if (NACC > 1) atomicAdd(&s1[tx * 8 + i], a1[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) {
+    atomicAdd(&out0[i], s0[i]);
+    if (NACC > 1) atomicAdd(&out1[i], s1[i]);
+  }
+}
+
+__global__ void bn_stats_kernel(const bf16* x, int P, int C, int ld, float* sum, float* sumsq) {
+  channel_reduce<2>(P, C, sum, sumsq, [&](int p, int g, float* a0, float* a1) {
+    const V8 v = ld8(x + (size_t)p * ld + g * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0[i] += v.v[i]; a1[i] = fmaf(v.v[i], v.v[i], a1[i]); }
+  });
+}
+
+// mean / invstd, fused scale-shift for the apply pass, running statistics (momentum 0.1, unbiased var)
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                                   int C, float count, float eps, float momentum, float* mean, float* invstd,
+                                   float* scale, float* shift, float* run_mean, float* run_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = sum[c] / count;
+  const float var = fmaxf(sumsq[c] / count - m * m, 0.f);
+  const float is = rsqrtf(var + eps);
+  mean[c] = m; invstd[c] = is;
+  const float sc = gamma[c] * is;
+  scale[c] = sc; shift[c] = beta[c] - m * sc;
+  if (run_mean) {
+    run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * var * (count / fmaxf(count - 1.f, 1.f));
+  }
+}
+
+// y = act(x*scale + shift (+ res)) (* dropout) ; flags: 1 = relu, 2 = dropout(0.5)
+__global__ void bn_apply_kernel(const bf16* x, int ldx, const float* scale, const float* shift, const bf16* res,
+                                int ldr, bf16* y, int ldy, long long P, int C, int flags,
+                                unsigned long long seed) {
+  const int G = C >> 3;
+  const long long total = P * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / G;
+    const int g = (int)(e - p * G);
+    V8 v = ld8(x + p * ldx + g * 8);
+    const V8 sc = ld8f(scale + g * 8), sh = ld8f(shift + g * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.v[i] = fmaf(v.v[i], sc.v[i], sh.v[i]);
+    if (res) {
+      const V8 r = ld8(res + p * ldr + g * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] += r.v[i];
+    }
+    if (flags & 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(v.v[i], 0.f);
+    }
+    if (flags & 2) {
+      const unsigned int keep = dropout_bits8(seed, (unsigned long long)e * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] = (keep >> i) & 1 ? v.v[i] * 2.f : 0.f;
+    }
+    st8(y + p * ldy + g * 8, v);
+  }
+}
+
+// g = dy * relu'(y) * dropout ; dbeta = sum g ; dgamma = sum g * xhat
+__global__ void bn_bwd_reduce_kernel(const bf16* dy, int lddy, const bf16* x, int ldx, const bf16* y, int ldy,
+                                     const float* mean, const float* invstd, int P, int C, int flags,
+                                     unsigned long long seed, float* dgamma, float* dbeta) {
+  const int G = C >> 3;
+  channel_reduce<2>(P, C, dgamma, dbeta, [&](int p, int g, float* a0, float* a1) {
+    V8 d = ld8(dy + (size_t)p * lddy + g * 8);
+    const V8 xv = ld8(x + (size_t)p * ldx + g * 8);
+    if (flags & 1) {
+      const V8 yv = ld8(y + (size_t)p * ldy + g * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
+    }
+    if (flags & 2) {
+      const unsigned int keep = dropout_bits8(seed, ((unsigned long long)p * G + g) * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.v[i] = (keep >> i) & 1 ? d.v[i] * 2.f : 0.f;
+    }
+    const V8 m = ld8f(mean + g * 8), is = ld8f(invstd + g * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0[i] = fmaf(d.v[i], (xv.v[i] - m.v[i]) * is.v[i], a0[i]); a1[i] += d.v[i]; }
+  });
+}
+
+// dx = gamma*invstd * (g - dbeta/P - xhat*dgamma/P) ; optional dres = g (gradient of the residual input)
+__global__ void bn_bwd_apply_kernel(const bf16* dy, int lddy, const bf16* x, int ldx, const bf16* y, int ldy,
+                                    const float* mean, const float* invstd, const float* gamma,
+                                    const float* dgamma, const float* dbeta, long long P, int C, int flags,
+                                    unsigned long long seed, bf16* dx, int lddx, bf16* dres, int lddr,
+                                    int dres_accumulate) {
+  const int G = C >> 3;
+  const long long total = P * G;
+  const float invP = 1.f / (float)P;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / G;
+    const int g = (int)(e - p * G);
+    V8 d = ld8(dy + p * lddy + g * 8);
+    const V8 xv = ld8(x + p * ldx + g * 8);
+    if (flags & 1) {
+      const V8 yv = ld8(y + p * ldy + g * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
+    }
+    if (flags & 2) {
+      const unsigned int keep = dropout_bits8(seed, (unsigned long long)e * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.v[i] = (keep >> i) & 1 ? d.v[i] * 2.f : 0.f;
+    }
+    if (dres) {
+      V8 r = d;
+      if (dres_accumulate) {
+        const V8 o = ld8(dres + p * lddr + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] += o.v[i];
+      }
+      st8(dres + p * lddr + g * 8, r);
+    }
+    const V8 m = ld8f(mean + g * 8), is = ld8f(invstd + g * 8), ga = ld8f(gamma + g * 8);
+    const V8 dg = ld8f(dgamma + g * 8), db = ld8f(dbeta + g * 8);
+    V8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (xv.v[i] - m.v[i]) * is.v[i];
+      o.v[i] = ga.v[i] * is.v[i] * (d.v[i] - db.v[i] * invP - xh * dg.v[i] * invP);
+    }
+    st8(dx + p * lddx + g * 8, o);
+  }
+}
+
+// a (+)= b, bf16 NHWC with strides (gradient fan-in of skip connections)
+__global__ void add_kernel(bf16* a, int lda, const bf16* b, int ldb, long long P, int C) {
+  const int G = C >> 3;
+  const long long total = P * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / G;
+    const int g = (int)(e - p * G);
+    V8 x = ld8(a + p * lda + g * 8);
+    const V8 yv = ld8(b + p * ldb + g * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x.v[i] += yv.v[i];
+    st8(a + p * lda + g * 8, x);
+  }
+}
+
+// ---- max-pool 3x3 stride 2 pad 1 -------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const bf16* x, int N, int H, int W, int C, bf16* y, unsigned char* arg, int Ho, int Wo) {
+  const int G = C >> 3;
+  const long long total = (long long)N * Ho * Wo * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % G);
+    long long p = e / G;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    V8 best; unsigned char bi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best.v[i] = -INFINITY; bi[i] = 0; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy * 2 - 1 + r;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = ox * 2 - 1 + s;
+        if (ix < 0 || ix >= W) continue;
+        const V8 v = ld8(x + (((size_t)n * H + iy) * W + ix) * C + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (v.v[i] > best.v[i]) { best.v[i] = v.v[i]; bi[i] = (unsigned char)(r * 3 + s); }
+      }
+    }
+    const size_t o = (((size_t)n * Ho + oy) * Wo + ox) * C + g * 8;
+    st8(y + o, best);
+    uint2 packed;
+    packed.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    packed.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(arg + o) = packed;
+  }
+}
+// gather form: input pixel (iy,ix) collects dy of every window whose arg-max it is
+__global__ void maxpool_bwd_kernel(const bf16* dy, const unsigned char* arg, int N, int H, int W, int C, int Ho,
+                                   int Wo, bf16* dx) {
+  const int G = C >> 3;
+  const long long total = (long long)N * H * W * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % G);
+    long long p = e / G;
+    const int ix = (int)(p % W); p /= W;
+    const int iy = (int)(p % H);
+    const int n = (int)(p / H);
+    V8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+    for (int oy = (iy) / 2; oy <= (iy + 1) / 2; ++oy) {
+      if (oy >= Ho) continue;
+      const int r = iy - (oy * 2 - 1);
+      if (r < 0 || r > 2) continue;
+      for (int ox = (ix) / 2; ox <= (ix + 1) / 2; ++ox) {
+        if (ox >= Wo) continue;
+        const int s = ix - (ox * 2 - 1);
+        if (s < 0 || s > 2) continue;
+        const size_t o = (((size_t)n * Ho + oy) * Wo + ox) * C + g * 8;
+        const uint2 packed = *reinterpret_cast<const uint2*>(arg + o);
+        const V8 d = ld8(dy + o);
+        const int code = r * 3 + s;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int a = ((i < 4 ? packed.x : packed.y) >> ((i & 3) * 8)) & 0xff;
+          if (a == code) acc.v[i] += d.v[i];
+        }
+      }
+    }
+    st8(dx + (((size_t)n * H + iy) * W + ix) * C + g * 8, acc);
+  }
+}
+
+// ---- bilinear resize, align_corners = True (nn.UpsamplingBilinear2d) -----------------------------------------
+__device__ __forceinline__ void src_index(int o, float scale, int in, int& i0, int& i1, float& lam) {
+  const float s = scale * (float)o;
+  i0 = (int)s;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = min(i0 + 1, in - 1);
+  lam = s - (float)i0;
+}
+__global__ void upsample_fwd_kernel(const bf16* x, int N, int H, int W, int C, int ldx, bf16* y, int Ho, int Wo, int ldy) {
+  const int G = C >> 3;
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)N * Ho * Wo * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % G);
+    long long p = e / G;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    int y0, y1, x0, x1; float ly, lx;
+    src_index(oy, sy, H, y0, y1, ly);
+    src_index(ox, sx, W, x0, x1, lx);
+    const bf16* b = x + (size_t)n * H * W * ldx + g * 8;
+    const V8 v00 = ld8(b + ((size_t)y0 * W + x0) * ldx), v01 = ld8(b + ((size_t)y0 * W + x1) * ldx);
+    const V8 v10 = ld8(b + ((size_t)y1 * W + x0) * ldx), v11 = ld8(b + ((size_t)y1 * W + x1) * ldx);
+    V8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o.v[i] = (1.f - ly) * ((1.f - lx) * v00.v[i] + lx * v01.v[i]) + ly * ((1.f - lx) * v10.v[i] + lx * v11.v[i]);
+    st8(y + (((size_t)n * Ho + oy) * Wo + ox) * ldy + g * 8, o);
+  }
+}
+// gather form of the transpose: input pixel collects from every output pixel that samples it
+__global__ void upsample_bwd_kernel(const bf16* dy, int N, int Ho, int Wo, int C, int lddy, bf16* dx, int H, int W, int lddx) {
+  const int G = C >> 3;
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const long long total = (long long)N * H * W * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % G);
+    long long p = e / G;
+    const int ix = (int)(p % W); p /= W;
+    const int iy = (int)(p % H);
+    const int n = (int)(p / H);
+    // candidate outputs: scale*o in (i-1, i+1)
+    const int oy_lo = sy > 0.f ? max(0, (int)floorf((float)(iy - 1) / sy)) : 0;
+    const int oy_hi = sy > 0.f ? min(Ho - 1, (int)ceilf((float)(iy + 1) / sy)) : Ho - 1;
+    const int ox_lo = sx > 0.f ? max(0, (int)floorf((float)(ix - 1) / sx)) : 0;
+    const int ox_hi = sx > 0.f ? min(Wo - 1, (int)ceilf((float)(ix + 1) / sx)) : Wo - 1;
+    V8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1; float ly;
+      src_index(oy, sy, H, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        int x0, x1; float lx;
+        src_index(ox, sx, W, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx == 0.f) continue;
+        const V8 d = ld8(dy + (((size_t)n * Ho + oy) * Wo + ox) * lddy + g * 8);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wgt, d.v[i], acc.v[i]);
+      }
+    }
+    st8(dx + (((size_t)n * H + iy) * W + ix) * lddx + g * 8, acc);
+  }
+}
+
+// ---- global average pool / broadcast --------------------------------------------------------------------
+// out[n][c] (fp32) = mean over pixels ; grid (N, ceil(G/32)), block (32 groups, 8 pixel lanes)
+__global__ void gap_kernel(const bf16* x, int HW, int C, int ld, float* out, float scale) {
+  const int n = blockIdx.x, g = blockIdx.y * 32 + threadIdx.x, G = C >> 3;
+  __shared__ float sm[8][32][8];
+  float a[8] = {};
+  if (g < G)
+    for (int p = threadIdx.y; p < HW; p += 8) {
+      const V8 v = ld8(x + ((size_t)n * HW + p) * ld + g * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += v.v[i];
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[threadIdx.y][threadIdx.x][i] = a[i];
+  __syncthreads();
+  if (threadIdx.y == 0 && g < G) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x][i];
+      out[(size_t)n * C + g * 8 + i] = t * scale;
+    }
+  }
+}
+// y[n, p, :] = v[n, :]  (bilinear resize of a 1x1 map); v bf16 [N, C]
+__global__ void broadcast_kernel(const bf16* v, int C, bf16* y, int HW, int ldy, long long total_pix) {
+  const int G = C >> 3;
+  const long long total = total_pix * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / G;
+    const int g = (int)(e - p * G);
+    const long long n = p / HW;
+    *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = *reinterpret_cast<const uint4*>(v + n * C + g * 8);
+  }
+}
+// fp32 [N, C] -> bf16 [N, C] (optionally scaled)
+__global__ void f32_to_bf16_kernel(const float* x, bf16* y, long long n, float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i] * scale);
+}
+
+// ---- depthwise 3x3 (dilated, stride 1, "same" padding) ---------------------------------------------------
+// y[n,oy,ox,c] = sum_t w[t][c] * x[n, oy + (r-1)*dil*sign, ox + (s-1)*dil*sign, c]; sign = -1 gives the data gradient
+__global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const float* w, int dil, int sign,
+                             bf16* y, int ldy) {
+  const int G = C >> 3;
+  const long long total = (long long)N * H * W * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % G);
+    long long p = e / G;
+    const int ox = (int)(p % W); p /= W;
+    const int oy = (int)(p % H);
+    const int n = (int)(p / H);
+    V8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy + (r - 1) * dil * sign;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = ox + (s - 1) * dil * sign;
+        if (ix < 0 || ix >= W) continue;
+        const V8 v = ld8(x + (((size_t)n * H + iy) * W + ix) * ldx + g * 8);
+        const V8 wv = ld8f(w + (size_t)(r * 3 + s) * C + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wv.v[i], v.v[i], acc.v[i]);
+      }
+    }
+    st8(y + (((size_t)n * H + oy) * W + ox) * ldy + g * 8, acc);
+  }
+}
+// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]; grid (blocks, 9): one tap per blockIdx.y
+__global__ void dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const bf16* dy, int lddy,
+                                   int dil, float* dw) {
+  const int t = blockIdx.y, r = t / 3, s = t % 3;
+  const int P = N * H * W;
+  float* dummy = nullptr;
+  channel_reduce<1>(P, C, dw + (size_t)t * C, dummy, [&](int p, int g, float* a0, float* a1) {
+    const int ox = p % W, oy = (p / W) % H, n = p / (W * H);
+    const int iy = oy + (r - 1) * dil, ix = ox + (s - 1) * dil;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) return;
+    const V8 d = ld8(dy + (size_t)p * lddy + g * 8);
+    const V8 v = ld8(x + (((size_t)n * H + iy) * W + ix) * ldx + g * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = fmaf(d.v[i], v.v[i], a0[i]);
+  });
+}
+
+// ---- stem im2col: fp32 NCHW [-1,1] image -> bf16 [N*Ho*Wo][KP] patches, k = (r*S + s)*3 + c --------------------
+__global__ void im2col_stem_kernel(const float* img, int N, int H, int W, int R, int S, int stride, int pad, int Ho,
+                                   int Wo, int KP, bf16* col) {
+  const long long total = (long long)N * Ho * Wo * (KP / 8);
+  const int K = R * S * 3;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int kg = (int)(e % (KP / 8));
+    long long p = e / (KP / 8);
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    V8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kg * 8 + i;
+      float v = 0.f;
+      if (k < K) {
+        const int c = k % 3, rs = k / 3, s = rs % S, r = rs / S;
+        const int iy = oy * stride - pad + r, ix = ox * stride - pad + s;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(((size_t)n * 3 + c) * H + iy) * W + ix];
+      }
+      o.v[i] = v;
+    }
+    st8(col + (((size_t)n * Ho + oy) * Wo + ox) * KP + kg * 8, o);
+  }
+}
+
+// ---- Adam (torch.optim.Adam defaults, scheduler.py:10-11) over a flat parameter buffer ------------------------
+__global__ void adam_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                            float eps, float bc1, float bc2_sqrt, float wd) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+// fp32 master weights [taps][Cout][Cin] -> bf16 copy and bf16 transposed copy [taps][Cin][Cout]
+struct WeightDesc { long long off_master, off_bf16, off_bf16_t; int taps, cout, cin, pad_; };
+__global__ void weight_prep_kernel(const float* master, bf16* wb, bf16* wbt, const WeightDesc* descs) {
+  const WeightDesc d = descs[blockIdx.y];
+  const long long n = (long long)d.taps * d.cout * d.cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = master[d.off_master + i];
+    const bf16 b = __float2bfloat16_rn(v);
+    wb[d.off_bf16 + i] = b;
+    if (d.off_bf16_t >= 0) {
+      const int ci = (int)(i % d.cin);
+      const long long q = i / d.cin;
+      const int co = (int)(q % d.cout);
+      const long long t = q / d.cout;
+      wbt[d.off_bf16_t + (t * d.cin + ci) * d.cout + co] = b;
+    }
+  }
+}
+
+static inline int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  return (int)std::max<long long>(1, std::min<long long>(g, 148 * 16));
+}
+static inline dim3 reduce_block(int C) {
+  int tx = 1;
+  while (tx < (C >> 3)) tx <<= 1;
+  tx = std::min(tx, 256);
+  return dim3(tx, 256 / tx);
+}
+
+}  // namespace nn
+}  // namespace aadg
+
+using namespace aadg;
+using namespace aadg::nn;
+
+#define NN_REQ_C(C) AADG_REQUIRE((C) > 0 && (C) % 8 == 0 && (C) <= 2048, "channels %d must be a multiple of 8 and <= 2048", (C))
+
+extern "C" {
+
+int aadg_bn_stats(const void* x, long long pixels, int c, int ld, float* sum, float* sumsq, void* stream) {
+  NN_REQ_C(c);
+  AADG_REQUIRE(pixels > 0 && pixels < (1ll << 31), "bad pixel count");
+  const dim3 blk = reduce_block(c);
+  const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 8);
+  bn_stats_kernel<<<std::max(blocks, 1), blk, 0, (cudaStream_t)stream>>>((const bf16*)x, (int)pixels, c, ld, sum, sumsq);
+  return check_launch("bn_stats");
+}
+
+int aadg_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int c, float count,
+                     float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
+                     float* run_mean, float* run_var, void* stream) {
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, gamma, beta, c, count, eps, momentum,
+                                                                        mean, invstd, scale, shift, run_mean, run_var);
+  return check_launch("bn_finalize");
+}
+
+int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr, void* y,
+                  int ldy, long long pixels, int c, int flags, unsigned long long seed, void* stream) {
+  NN_REQ_C(c);
+  bn_apply_kernel<<<grid_for(pixels * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, ldx, scale, shift, (const bf16*)res, ldr, (bf16*)y, ldy, pixels, c, flags, seed);
+  return check_launch("bn_apply");
+}
+
+int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
+                     const float* invstd, const float* gamma, long long pixels, int c, int flags,
+                     unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,
+                     int dres_accumulate, void* stream) {
+  NN_REQ_C(c);
+  AADG_REQUIRE(pixels > 0 && pixels < (1ll << 31), "bad pixel count");
+  cudaStream_t st = (cudaStream_t)stream;
+  AADG_CUDA_TRY(cudaMemsetAsync(dgamma, 0, sizeof(float) * c, st));
+  AADG_CUDA_TRY(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
+  const dim3 blk = reduce_block(c);
+  const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 8);
+  bn_bwd_reduce_kernel<<<std::max(blocks, 1), blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y,
+                                                           ldy, mean, invstd, (int)pixels, c, flags, seed, dgamma, dbeta);
+  bn_bwd_apply_kernel<<<grid_for(pixels * (c / 8)), 256, 0, st>>>(
+      (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y, ldy, mean, invstd, gamma, dgamma, dbeta, pixels, c,
+      flags, seed, (bf16*)dx, lddx, (bf16*)dres, lddr, dres_accumulate);
+  return check_launch("bn_backward");
+}
+
+int aadg_add_bf16(void* a, int lda, const void* b, int ldb, long long pixels, int c, void* stream) {
+  NN_REQ_C(c);
+  add_kernel<<<grid_for(pixels * (c / 8)), 256, 0, (cudaStream_t)stream>>>((bf16*)a, lda, (const bf16*)b, ldb, pixels, c);
+  return check_launch("add");
+}
+
+int aadg_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, void* y, void* argmax, void* stream) {
+  NN_REQ_C(c);
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, n, h, w, c, (bf16*)y, (unsigned char*)argmax, ho, wo);
+  return check_launch("maxpool fwd");
+}
+int aadg_maxpool3x3s2_bwd(const void* dy, const void* argmax, int n, int h, int w, int c, void* dx, void* stream) {
+  NN_REQ_C(c);
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const unsigned char*)argmax, n, h, w, c, ho, wo, (bf16*)dx);
+  return check_launch("maxpool bwd");
+}
+
+int aadg_upsample_bilinear_fwd(const void* x, int n, int h, int w, int c, int ldx, void* y, int ho, int wo, int ldy,
+                               void* stream) {
+  NN_REQ_C(c);
+  upsample_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, n, h, w, c, ldx, (bf16*)y, ho, wo, ldy);
+  return check_launch("upsample fwd");
+}
+int aadg_upsample_bilinear_bwd(const void* dy, int n, int ho, int wo, int c, int lddy, void* dx, int h, int w, int lddx,
+                               void* stream) {
+  NN_REQ_C(c);
+  upsample_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, n, ho, wo, c, lddy, (bf16*)dx, h, w, lddx);
+  return check_launch("upsample bwd");
+}
+
+/* out fp32 [n,c] = scale * sum over the hw pixels of x bf16 [n,hw,ld] */
+int aadg_global_sum(const void* x, int n, int hw, int c, int ld, float* out, float scale, void* stream) {
+  NN_REQ_C(c);
+  dim3 grid(n, (c / 8 + 31) / 32), blk(32, 8);
+  gap_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>((const bf16*)x, hw, c, ld, out, scale);
+  return check_launch("global_sum");
+}
+int aadg_broadcast_pixels(const void* v, int n, int c, void* y, int hw, int ldy, void* stream) {
+  NN_REQ_C(c);
+  broadcast_kernel<<<grid_for((long long)n * hw * (c / 8)), 256, 0, (cudaStream_t)stream>>>((const bf16*)v, c, (bf16*)y, hw, ldy,
+                                                                                          (long long)n * hw);
+  return check_launch("broadcast");
+}
+int aadg_f32_to_bf16(const float* x, void* y, long long count, float scale, void* stream) {
+  f32_to_bf16_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, count, scale);
+  return check_launch("f32_to_bf16");
+}
+
+/* depthwise 3x3, stride 1, padding = dilation. direction 0: forward, 1: data gradient. w fp32 [9][c] */
+int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int direction, void* y,
+                   int ldy, void* stream) {
+  NN_REQ_C(c);
+  dw3x3_kernel<<<grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, n, h, w, c, ldx, wgt, dil, direction ? -1 : 1, (bf16*)y, ldy);
+  return check_launch("dwconv3x3");
+}
+int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil, float* dw,
+                         void* stream) {
+  NN_REQ_C(c);
+  const long long pixels = (long long)n * h * w;
+  AADG_REQUIRE(pixels < (1ll << 31), "too many pixels");
+  const dim3 blk = reduce_block(c);
+  const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 2);
+  dim3 grid(std::max(blocks, 1), 9);
+  dw3x3_wgrad_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, lddy, dil, dw);
+  return check_launch("dwconv3x3 wgrad");
+}
+
+/* img fp32 [n,3,h,w] -> col bf16 [n*ho*wo][kp], k = (r*S+s)*3 + c, zero padded to kp (multiple of 8) */
+int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int kp, void* col,
+                     void* stream) {
+  AADG_REQUIRE(kp % 8 == 0 && kp >= r * s * 3, "kp must be a multiple of 8 and >= R*S*3");
+  const int ho = (h + 2 * pad - r) / stride + 1, wo = (w + 2 * pad - s) / stride + 1;
+  im2col_stem_kernel<<<grid_for((long long)n * ho * wo * (kp / 8)), 256, 0, (cudaStream_t)stream>>>(
+      img, n, h, w, r, s, stride, pad, ho, wo, kp, (bf16*)col);
+  return check_launch("im2col");
+}
+
+int aadg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+  AADG_REQUIRE(step >= 1, "step counts from 1");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, count, lr, beta1,
+                                                                beta2, eps, bc1, bc2, weight_decay);
+  return check_launch("adam");
+}
+
+/* descs (device) int64x3 + int32x4 per weight: see WeightDesc */
+int aadg_weight_prep(const float* master, void* w_bf16, void* w_bf16_t, const void* descs, int n_descs, void* stream) {
+  if (n_descs <= 0) return AADG_OK;
+  dim3 grid(64, n_descs);
+  weight_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(master, (bf16*)w_bf16, (bf16*)w_bf16_t,
+                                                            (const WeightDesc*)descs);
+  return check_launch("weight_prep");
+}
+
+}  // extern "C"

@@ -1,0 +1,608 @@
+"""DeepLabV3+ over a ResNet encoder, forward AND backward, on the CUDA layers of libaadg_b200.so.
+
+Keeps the constructor and call shape the reference uses (models/__init__.py:17-23, models/heads.py:14-25):
+
+    model = DeepLabV3Plus(encoder_name="resnet50", encoder_weights=None, in_channels=3, classes=2,
+                          aux_params=dict(pooling="avg"))
+    logits, pooled = model(x)          # x float32 [N,3,H,W] in [-1,1]
+
+and the state_dict key names of segmentation_models_pytorch 0.2.0 (encoder.*, decoder.aspp.*, ...), but
+runs on its own engine: bf16 NHWC activations, tcgen05 implicit-GEMM convolutions, fused batch-norm /
+ReLU / residual / dropout kernels, one fused up-sample + sigmoid + BCE (+ Dice counts) loss kernel, an
+explicit backward pass (no autograd graph) and a fused Adam over one flat parameter buffer.
+Architecture: SURVEY.md App. A.3 (smp DeepLabV3Plus, output stride 16, ASPP rates 12/24/36, separable).
+"""
+import math
+
+import numpy as np
+import torch
+
+from ..ops import conv as C
+from ..ops import nn as K
+
+BF16 = torch.bfloat16
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameters: one flat fp32 buffer (+ grads, Adam moments), bf16 copies of the conv weights
+# ---------------------------------------------------------------------------------------------------
+class Param:
+    __slots__ = ("name", "shape", "kind", "offset", "numel", "init", "bf_off", "bft_off", "store")
+
+    def __init__(self, name, shape, kind, init):
+        self.name, self.shape, self.kind, self.init = name, tuple(shape), kind, init
+        self.numel = int(np.prod(shape))
+        self.offset = self.bf_off = self.bft_off = -1
+        self.store = None
+
+    @property
+    def data(self):
+        return self.store.params[self.offset:self.offset + self.numel].view(self.shape)
+
+    @property
+    def grad(self):
+        return self.store.grads[self.offset:self.offset + self.numel].view(self.shape)
+
+    @property
+    def bf16(self):
+        return self.store.wb[self.bf_off:self.bf_off + self.numel].view(self.shape)
+
+    @property
+    def bf16_t(self):
+        t, co, ci = self.shape
+        return self.store.wbt[self.bft_off:self.bft_off + self.numel].view(t, ci, co)
+
+
+class ParamStore:
+    """kinds: 'conv' (bf16 copy + transposed copy), 'conv_nt' (bf16 copy only), 'f32' (used as is)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.items = []
+        self.params = None
+
+    def add(self, name, shape, kind, init):
+        assert self.params is None
+        p = Param(name, shape, kind, init)
+        p.store = self
+        self.items.append(p)
+        return p
+
+    def finalize(self):
+        off = bf = bft = 0
+        for p in self.items:
+            p.offset = off
+            off += (p.numel + 3) // 4 * 4
+            if p.kind in ("conv", "conv_nt"):
+                p.bf_off = bf
+                bf += (p.numel + 7) // 8 * 8
+            if p.kind == "conv":
+                p.bft_off = bft
+                bft += (p.numel + 7) // 8 * 8
+        dev = self.device
+        self.params = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.wb = torch.zeros(max(bf, 8), dtype=BF16, device=dev)
+        self.wbt = torch.zeros(max(bft, 8), dtype=BF16, device=dev)
+        descs = []
+        for p in self.items:
+            if p.kind in ("conv", "conv_nt"):
+                t, co, ci = p.shape
+                descs.append(np.array([p.offset, p.bf_off, p.bft_off if p.kind == "conv" else -1], np.int64).tobytes()
+                             + np.array([t, co, ci, 0], np.int32).tobytes())
+        self.n_descs = len(descs)
+        self.descs = torch.frombuffer(bytearray(b"".join(descs)), dtype=torch.uint8).to(dev)
+        for p in self.items:
+            p.data.copy_(p.init(p.shape).to(dev))
+            p.init = None
+        self.step = 0
+        self.refresh()
+
+    def refresh(self):
+        """bf16 (and transposed) copies of the convolution weights from the fp32 masters."""
+        K.weight_prep(self.params, self.wb, self.wbt, self.descs, self.n_descs)
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.step += 1
+        K.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, lr, betas[0], betas[1], eps,
+                    weight_decay, self.step)
+        self.refresh()
+
+
+def kaiming_fan_out(shape_torch):
+    """torchvision ResNet init: kaiming_normal_(mode='fan_out', nonlinearity='relu') on [Cout,Cin,R,S]."""
+    co, ci, r, s = shape_torch
+    return torch.randn(shape_torch) * math.sqrt(2.0 / (co * r * s))
+
+
+def kaiming_uniform_default(shape_torch):
+    """nn.Conv2d default init (kaiming_uniform_(a=sqrt(5))) used by smp's decoder convs."""
+    co, ci, r, s = shape_torch
+    bound = 1.0 / math.sqrt(ci * r * s)
+    return (torch.rand(shape_torch) * 2 - 1) * bound
+
+
+def to_taps(w):
+    """torch [Cout,Cin,R,S] -> [R*S,Cout,Cin]"""
+    co, ci, r, s = w.shape
+    return w.permute(2, 3, 0, 1).reshape(r * s, co, ci).contiguous()
+
+
+def from_taps(w, r, s):
+    t, co, ci = w.shape
+    return w.reshape(r, s, co, ci).permute(2, 3, 0, 1).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+# layers
+# ---------------------------------------------------------------------------------------------------
+class BatchNorm:
+    def __init__(self, store, name, c):
+        self.c, self.name = c, name
+        self.gamma = store.add(name + ".weight", (c,), "f32", lambda s: torch.ones(s))
+        self.beta = store.add(name + ".bias", (c,), "f32", lambda s: torch.zeros(s))
+        dev = store.device
+        self.running_mean = torch.zeros(c, device=dev)
+        self.running_var = torch.ones(c, device=dev)
+        self.num_batches_tracked = 0
+        self.buf = torch.zeros(6, c, device=dev)    # sum, sumsq, mean, invstd, scale, shift
+
+    def forward(self, x, y, training, res=None, relu=True, dropout_seed=None):
+        s = self.buf
+        if training:
+            s[:2].zero_()
+            K.bn_stats(x, s[0], s[1])
+            count = x.numel() // x.shape[-1]
+            K.bn_finalize(s[0], s[1], self.gamma.data, self.beta.data, count, BN_EPS, BN_MOMENTUM, s[2], s[3], s[4],
+                          s[5], self.running_mean, self.running_var)
+            self.num_batches_tracked += 1
+        else:
+            torch.rsqrt(self.running_var + BN_EPS, out=s[3])
+            s[2].copy_(self.running_mean)
+            torch.mul(self.gamma.data, s[3], out=s[4])
+            torch.sub(self.beta.data, s[2] * s[4], out=s[5])
+        K.bn_apply(x, s[4], s[5], y, res=res, relu=relu, dropout_seed=dropout_seed)
+        self.saved = (s[2].clone(), s[3].clone()) if training else None
+
+    def backward(self, dy, x, y, dx, relu=True, dropout_seed=None, dres=None, dres_accumulate=False):
+        mean, invstd = self.saved
+        K.bn_backward(dy, x, y, mean, invstd, self.gamma.data, self.gamma.grad, self.beta.grad, dx, relu=relu,
+                      dropout_seed=dropout_seed, dres=dres, dres_accumulate=dres_accumulate)
+        self.saved = None
+
+
+class ConvBN:
+    """Conv2d(bias=False) -> BatchNorm2d -> [+ residual] -> [ReLU] -> [Dropout(0.5)]"""
+
+    def __init__(self, store, conv_name, bn_name, cin, cout, k=1, stride=1, pad=0, dil=1, relu=True, init=None,
+                 need_dgrad=True):
+        self.cin, self.cout, self.k, self.stride, self.pad, self.dil, self.relu = cin, cout, k, stride, pad, dil, relu
+        init = init or kaiming_fan_out
+        self.w = store.add(conv_name + ".weight", (k * k, cout, cin), "conv" if need_dgrad else "conv_nt",
+                           lambda s: to_taps(init((cout, cin, k, k))))
+        self.bn = BatchNorm(store, bn_name, cout)
+        self.need_dgrad = need_dgrad
+
+    def out_hw(self, h, w):
+        return C.out_size(h, w, self.k, self.k, self.stride, self.pad, self.dil)
+
+    def forward(self, x, training, out=None, res=None, dropout_seed=None):
+        n, h, w, _ = x.shape
+        ho, wo = self.out_hw(h, w)
+        pre = C.fprop(x, self.w.bf16, self.k, self.k, self.stride, self.pad, self.dil)
+        if out is None:
+            out = torch.empty((n, ho, wo, self.cout), dtype=BF16, device=x.device)
+        self.bn.forward(pre, out, training, res=res, relu=self.relu, dropout_seed=dropout_seed)
+        self.ctx = (x, pre, out, dropout_seed) if training else None
+        return out
+
+    def backward(self, dy, dx=None, accumulate=False, want_dres=False, dres=None, dres_accumulate=False):
+        """returns dx (or None when the input needs no gradient); with want_dres also the residual gradient."""
+        x, pre, y, seed = self.ctx
+        self.ctx = None
+        dpre = torch.empty_like(pre)
+        if want_dres and dres is None:
+            dres = torch.empty(y.shape, dtype=BF16, device=y.device)
+        self.bn.backward(dy, pre, y, dpre, relu=self.relu, dropout_seed=seed, dres=dres if want_dres else None,
+                         dres_accumulate=dres_accumulate)
+        C.wgrad(x, dpre, self.k, self.k, self.stride, self.pad, self.dil, out=self.w.grad)
+        if self.need_dgrad:
+            dx = C.dgrad(dpre, self.w.bf16_t, self.k, self.k, self.stride, self.pad, self.dil, x.shape[1:3], out=dx,
+                         accumulate=accumulate)
+        else:
+            dx = None
+        return (dx, dres) if want_dres else dx
+
+
+class Depthwise3x3:
+    def __init__(self, store, name, c, dil):
+        self.c, self.dil = c, dil
+        self.w = store.add(name + ".weight", (9, c), "f32",
+                           lambda s: kaiming_uniform_default((c, 1, 3, 3)).reshape(c, 9).t().contiguous())
+
+    def forward(self, x, training):
+        y = torch.empty(x.shape, dtype=BF16, device=x.device)
+        K.dwconv3x3(x, self.w.data, self.dil, y)
+        self.ctx = x if training else None
+        return y
+
+    def backward(self, dy):
+        x = self.ctx
+        self.ctx = None
+        K.dwconv3x3_wgrad(x, dy, self.dil, self.w.grad)
+        dx = torch.empty(x.shape, dtype=BF16, device=x.device)
+        K.dwconv3x3(dy, self.w.data, self.dil, dx, backward_data=True)
+        return dx
+
+
+class Bottleneck:
+    expansion = 4
+
+    def __init__(self, store, name, cin, planes, stride, dil, downsample):
+        self.c1 = ConvBN(store, name + ".conv1", name + ".bn1", cin, planes, 1)
+        self.c2 = ConvBN(store, name + ".conv2", name + ".bn2", planes, planes, 3, stride, dil, dil)
+        self.c3 = ConvBN(store, name + ".conv3", name + ".bn3", planes, planes * 4, 1)
+        self.ds = ConvBN(store, name + ".downsample.0", name + ".downsample.1", cin, planes * 4, 1, stride,
+                         relu=False) if downsample else None
+
+    def forward(self, x, training):
+        idt = self.ds.forward(x, training) if self.ds else x
+        return self.c3.forward(self.c2.forward(self.c1.forward(x, training), training), training, res=idt)
+
+    def backward(self, dy):
+        d2, dres = self.c3.backward(dy, want_dres=True)
+        d1 = self.c2.backward(d2)
+        if self.ds:
+            dx = self.ds.backward(dres)
+            return self.c1.backward(d1, dx=dx, accumulate=True)
+        return self.c1.backward(d1, dx=dres, accumulate=True)
+
+
+class BasicBlock:
+    expansion = 1
+
+    def __init__(self, store, name, cin, planes, stride, dil, downsample):
+        self.c1 = ConvBN(store, name + ".conv1", name + ".bn1", cin, planes, 3, stride, dil, dil)
+        self.c2 = ConvBN(store, name + ".conv2", name + ".bn2", planes, planes, 3, 1, dil, dil)
+        self.ds = ConvBN(store, name + ".downsample.0", name + ".downsample.1", cin, planes, 1, stride,
+                         relu=False) if downsample else None
+
+    def forward(self, x, training):
+        idt = self.ds.forward(x, training) if self.ds else x
+        return self.c2.forward(self.c1.forward(x, training), training, res=idt)
+
+    def backward(self, dy):
+        d1, dres = self.c2.backward(dy, want_dres=True)
+        if self.ds:
+            dx = self.ds.backward(dres)
+            return self.c1.backward(d1, dx=dx, accumulate=True)
+        return self.c1.backward(d1, dx=dres, accumulate=True)
+
+
+RESNETS = {
+    "resnet18": (BasicBlock, [2, 2, 2, 2]),
+    "resnet34": (BasicBlock, [3, 4, 6, 3]),
+    "resnet50": (Bottleneck, [3, 4, 6, 3]),
+}
+STEM_KP = 192   # 7*7*3 = 147 patch values, zero padded to a multiple of 64
+
+
+class ResNetEncoder:
+    """torchvision ResNet without the classifier; stage 5 dilated (stride 1, dilation 2) for output stride 16
+    (smp `make_dilated(stage_list=[5], dilation_list=[2])`)."""
+
+    def __init__(self, store, name, in_channels=3):
+        assert in_channels == 3
+        block, layers = RESNETS[name]
+
+        def stem_init(shape):
+            w = kaiming_fan_out((64, 3, 7, 7)).permute(0, 2, 3, 1).reshape(64, 147)   # k = (r*7+s)*3 + c
+            return torch.cat([w, torch.zeros(64, STEM_KP - 147)], 1).reshape(1, 64, STEM_KP)
+        self.stem_w = store.add("encoder.conv1.weight", (1, 64, STEM_KP), "conv_nt", stem_init)
+        self.stem_bn = BatchNorm(store, "encoder.bn1", 64)
+        self.blocks = []
+        cin = 64
+        self.out_channels = [3, 64]
+        for li, (planes, n) in enumerate(zip([64, 128, 256, 512], layers)):
+            stride = 1 if li == 0 else 2
+            dil = 1
+            if li == 3:
+                stride, dil = 1, 2
+            stage = []
+            for b in range(n):
+                s = stride if b == 0 else 1
+                ds = b == 0 and (stride != 1 or li == 3 or cin != planes * block.expansion)
+                stage.append(block(store, "encoder.layer%d.%d" % (li + 1, b), cin, planes, s, dil, ds))
+                cin = planes * block.expansion
+            self.blocks.append(stage)
+            self.out_channels.append(cin)
+
+    def forward(self, img, training):
+        col = K.im2col_stem(img, 7, 7, 2, 3, STEM_KP)
+        pre = C.fprop(col, self.stem_w.bf16, 1, 1)
+        f1 = torch.empty_like(pre)
+        self.stem_bn.forward(pre, f1, training)
+        pooled, arg = K.maxpool_fwd(f1)
+        feats = [f1]
+        x = pooled
+        for stage in self.blocks:
+            for blk in stage:
+                x = blk.forward(x, training)
+            feats.append(x)
+        self.ctx = (col, pre, f1, arg) if training else None
+        return feats            # strides 2, 4, 8, 16, 16
+
+    def backward(self, d_last, d_stride4):
+        """d_last: gradient of the last feature map; d_stride4: gradient of the stride-4 map (decoder skip)."""
+        col, pre, f1, arg = self.ctx
+        self.ctx = None
+        d = d_last
+        for li in (3, 2, 1, 0):
+            if li == 0 and d_stride4 is not None:
+                K.add_(d, d_stride4)
+            for blk in reversed(self.blocks[li]):
+                d = blk.backward(d)
+        d = K.maxpool_bwd(d, arg, f1.shape)
+        dpre = torch.empty_like(pre)
+        self.stem_bn.backward(d, pre, f1, dpre)
+        C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad)
+
+
+class SeparableConvBN:
+    """smp SeparableConv2d(depthwise 3x3 + pointwise 1x1, bias=False) -> BN -> ReLU"""
+
+    def __init__(self, store, dw_name, pw_name, bn_name, cin, cout, dil):
+        self.dw = Depthwise3x3(store, dw_name, cin, dil)
+        self.pw = ConvBN(store, pw_name, bn_name, cin, cout, 1, init=kaiming_uniform_default)
+
+    def forward(self, x, training, out=None):
+        return self.pw.forward(self.dw.forward(x, training), training, out=out)
+
+    def backward(self, dy):
+        return self.dw.backward(self.pw.backward(dy))
+
+
+class DeepLabV3PlusDecoder:
+    def __init__(self, store, enc_channels, out_channels=256, rates=(12, 24, 36)):
+        cenc, chigh = enc_channels[-1], enc_channels[-4]
+        oc = out_channels
+        u = kaiming_uniform_default
+        a = "decoder.aspp.0."
+        self.b0 = ConvBN(store, a + "convs.0.0", a + "convs.0.1", cenc, oc, 1, init=u)
+        self.br = [SeparableConvBN(store, a + "convs.%d.0.0" % (i + 1), a + "convs.%d.0.1" % (i + 1),
+                                   a + "convs.%d.1" % (i + 1), cenc, oc, r) for i, r in enumerate(rates)]
+        self.bp = ConvBN(store, a + "convs.4.1", a + "convs.4.2", cenc, oc, 1, init=u)
+        self.project = ConvBN(store, a + "project.0", a + "project.1", 5 * oc, oc, 1, init=u)
+        self.sep = SeparableConvBN(store, "decoder.aspp.1.0", "decoder.aspp.1.1", "decoder.aspp.2", oc, oc, 1)
+        self.block1 = ConvBN(store, "decoder.block1.0", "decoder.block1.1", chigh, 48, 1, init=u)
+        self.block2 = SeparableConvBN(store, "decoder.block2.0.0", "decoder.block2.0.1", "decoder.block2.1", 48 + oc,
+                                      oc, 1)
+        self.oc = oc
+
+    def forward(self, feats, training, dropout_seed):
+        x, high = feats[-1], feats[-4]
+        n, h, w, cenc = x.shape
+        oc = self.oc
+        cat = torch.empty((n, h, w, 5 * oc), dtype=BF16, device=x.device)
+        self.b0.forward(x, training, out=cat[..., 0:oc])
+        for i, br in enumerate(self.br):
+            br.forward(x, training, out=cat[..., (i + 1) * oc:(i + 2) * oc])
+        pooled = K.f32_to_bf16(K.global_sum(x, 1.0 / (h * w))).view(n, 1, 1, cenc)
+        pv = self.bp.forward(pooled, training)
+        K.broadcast_pixels(pv, cat[..., 4 * oc:5 * oc])
+        pj = self.project.forward(cat, training, dropout_seed=dropout_seed if training else None)
+        a = self.sep.forward(pj, training)
+        hh, hw = high.shape[1:3]
+        cat2 = torch.empty((n, hh, hw, oc + 48), dtype=BF16, device=x.device)
+        K.upsample_fwd(a, cat2[..., 0:oc])
+        self.block1.forward(high, training, out=cat2[..., oc:oc + 48])
+        out = self.block2.forward(cat2, training)
+        self.ctx = (x.shape, a.shape, cat.shape, cat2.shape) if training else None
+        return out
+
+    def backward(self, dy):
+        xs, ash, cats, cat2s = self.ctx
+        self.ctx = None
+        n, h, w, cenc = xs
+        oc = self.oc
+        dev = dy.device
+        dcat2 = self.block2.backward(dy)                                  # [n, hh, hw, oc+48]
+        d_high = self.block1.backward(dcat2[..., oc:oc + 48])
+        da = torch.empty(ash, dtype=BF16, device=dev)
+        K.upsample_bwd(dcat2[..., 0:oc], da)
+        dpj = self.sep.backward(da)
+        dcat = self.project.backward(dpj)                                 # [n, h, w, 5*oc]
+        dx = self.b0.backward(dcat[..., 0:oc])
+        for i, br in enumerate(self.br):
+            K.add_(dx, br.backward(dcat[..., (i + 1) * oc:(i + 2) * oc]))
+        dpv = K.f32_to_bf16(K.global_sum(dcat[..., 4 * oc:5 * oc], 1.0)).view(n, 1, 1, oc)
+        dpooled = self.bp.backward(dpv)                                   # [n,1,1,cenc]
+        tmp = torch.empty(xs, dtype=BF16, device=dev)
+        K.broadcast_pixels((dpooled.float() / (h * w)).to(BF16), tmp)
+        K.add_(dx, tmp)
+        return dx, d_high
+
+
+class SegNet:
+    """encoder + decoder + segmentation head (Conv2d(256, classes, 1) -> UpsamplingBilinear2d(4)) and the
+    patched classification head (AdaptiveAvgPool2d(1) + flatten of the last encoder map, models/heads.py:14-25)."""
+
+    def __init__(self, encoder_name="resnet50", classes=2, device="cuda", seed=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("aadg_b200.nn needs a CUDA device: there is no CPU path")
+        self.device = torch.device(device)
+        gen_state = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        self.store = ParamStore(self.device)
+        self.encoder = ResNetEncoder(self.store, encoder_name)
+        self.decoder = DeepLabV3PlusDecoder(self.store, self.encoder.out_channels)
+        self.classes = classes
+        self.head_w = self.store.add("segmentation_head.0.weight", (classes, 256), "f32",
+                                     lambda s: kaiming_uniform_default((classes, 256, 1, 1)).reshape(classes, 256))
+        bound = 1.0 / math.sqrt(256)
+        self.head_b = self.store.add("segmentation_head.0.bias", (classes,), "f32",
+                                     lambda s: (torch.rand(s) * 2 - 1) * bound)
+        self.store.finalize()
+        torch.random.set_rng_state(gen_state)
+        self.training = True
+        self.dropout_seed = 0x5EED0000 + seed
+        self.dropout_enabled = True      # Dropout(0.5) of the ASPP projection (train mode)
+        self.steps = 0
+
+    # ---- torch.nn.Module-like surface ---------------------------------------------------------------
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def cuda(self, *a, **k):
+        return self
+
+    def parameters(self):
+        return [p.data for p in self.store.items]
+
+    def named_params(self):
+        return {p.name: p for p in self.store.items}
+
+    def _bns(self):
+        out = []
+
+        def walk(o):
+            if isinstance(o, BatchNorm):
+                out.append(o)
+            elif isinstance(o, (list, tuple)):
+                for i in o:
+                    walk(i)
+            elif hasattr(o, "__dict__") and not isinstance(o, (ParamStore, Param, torch.Tensor)):
+                for v in vars(o).values():
+                    walk(v)
+        walk(self.encoder)
+        walk(self.decoder)
+        return out
+
+    def state_dict(self):
+        """smp 0.2.0 key names and torch weight layouts."""
+        sd = {}
+        for p in self.store.items:
+            d = p.data.detach().clone()
+            if p.name == "encoder.conv1.weight":
+                d = d[0, :, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+            elif p.kind in ("conv", "conv_nt"):
+                k = int(round(math.sqrt(p.shape[0])))
+                d = from_taps(d, k, k)
+            elif p.name.startswith("segmentation_head.0.weight"):
+                d = d.reshape(self.classes, 256, 1, 1)
+            elif len(p.shape) == 2 and p.shape[0] == 9:
+                d = d.t().reshape(p.shape[1], 1, 3, 3).contiguous()
+            sd[p.name] = d
+        for bn in self._bns():
+            sd[bn.name + ".running_mean"] = bn.running_mean.clone()
+            sd[bn.name + ".running_var"] = bn.running_var.clone()
+            sd[bn.name + ".num_batches_tracked"] = torch.tensor(bn.num_batches_tracked)
+        return sd
+
+    def load_state_dict(self, sd, strict=True):
+        named = self.named_params()
+        missing = [k for k in named if k not in sd]
+        if strict and missing:
+            raise KeyError("missing keys: %s" % missing[:5])
+        for name, p in named.items():
+            if name not in sd:
+                continue
+            w = sd[name].detach().to(self.device, torch.float32)
+            if name == "encoder.conv1.weight":
+                w = torch.cat([w.permute(0, 2, 3, 1).reshape(64, 147),
+                               torch.zeros(64, STEM_KP - 147, device=self.device)], 1).reshape(1, 64, STEM_KP)
+            elif p.kind in ("conv", "conv_nt"):
+                w = to_taps(w)
+            elif name == "segmentation_head.0.weight":
+                w = w.reshape(self.classes, 256)
+            elif len(p.shape) == 2 and p.shape[0] == 9:
+                w = w.reshape(p.shape[1], 9).t().contiguous()
+            p.data.copy_(w.reshape(p.shape))
+        for bn in self._bns():
+            if bn.name + ".running_mean" in sd:
+                bn.running_mean.copy_(sd[bn.name + ".running_mean"])
+                bn.running_var.copy_(sd[bn.name + ".running_var"])
+        self.store.refresh()
+
+    # ---- forward / backward ---------------------------------------------------------------------------
+    def features(self, x):
+        """encoder + decoder; returns (decoder map bf16 [N,H/4,W/4,256], pooled encoder feature fp32 [N,C])."""
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
+            raise ValueError("input must be CUDA float32 [N,3,H,W]")
+        feats = self.encoder.forward(x.contiguous(), self.training)
+        last = feats[-1]
+        pooled = K.global_sum(last, 1.0 / (last.shape[1] * last.shape[2]))
+        seed = (self.dropout_seed + self.steps) if (self.training and self.dropout_enabled) else None
+        dec = self.decoder.forward(feats, self.training, seed)
+        return dec, pooled
+
+    def __call__(self, x):
+        """smp call shape: (logits float32 [N,classes,H,W], pooled feature float32 [N,C_enc])."""
+        dec, pooled = self.features(x)
+        z = K.seg_head_fwd(dec, self.head_w.data, self.head_b.data)
+        n, _, hh, ww = x.shape
+        logits = torch.empty((n, self.classes, hh, ww), dtype=torch.float32, device=x.device)
+        dummy_t = torch.zeros_like(logits)
+        K.seg_loss_fwd(z, dummy_t, 0.5, torch.zeros(1, dtype=torch.float64, device=x.device),
+                       torch.zeros((n, self.classes, 3), dtype=torch.int32, device=x.device), logits)
+        self.ctx = (dec, z) if self.training else None
+        return logits, pooled
+
+    forward = __call__
+
+    def loss_step(self, x, target, thr=0.5, want_logits=False):
+        """Forward + BCELoss(sigmoid(logits), target) (mean) + Dice counts, then the whole backward.
+        Gradients are left in store.grads (call store.zero_grad() before, store.adam_step() after).
+        Returns dict(loss [1] fp32 tensor, counts int32 [N,classes,3], pooled fp32 [N,C], logits or None)."""
+        assert self.training
+        n, _, hh, ww = x.shape
+        dec, pooled = self.features(x)
+        z = K.seg_head_fwd(dec, self.head_w.data, self.head_b.data)
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=x.device)
+        counts = torch.zeros((n, self.classes, 3), dtype=torch.int32, device=x.device)
+        logits = torch.empty((n, self.classes, hh, ww), dtype=torch.float32, device=x.device) if want_logits else None
+        K.seg_loss_fwd(z, target, thr, loss_sum, counts, logits)
+        numel = float(n * self.classes * hh * ww)
+        dz = K.seg_loss_bwd(z, target, 1.0 / numel)
+        ddec = torch.empty(dec.shape, dtype=BF16, device=x.device)
+        K.seg_head_bwd(dz, dec, self.head_w.data, ddec, self.head_w.grad, self.head_b.grad)
+        d_last, d_high = self.decoder.backward(ddec)
+        self.encoder.backward(d_last, d_high)
+        self.steps += 1
+        return dict(loss=(loss_sum / numel).float(), counts=counts, pooled=pooled, logits=logits)
+
+
+def dice_from_counts(counts):
+    """torchmetrics F1(num_classes=2, average=None, mdmc_average='samplewise')[1] per class:
+    mean over samples of 2TP/(2TP+FP+FN), 0 on 0/0.  counts int [N,K,3] -> [K]."""
+    c = counts.to(torch.float64)
+    den = 2 * c[..., 0] + c[..., 1] + c[..., 2]
+    f1 = torch.where(den > 0, 2 * c[..., 0] / den.clamp(min=1), torch.zeros_like(den))
+    return f1.mean(0)
+
+
+def DeepLabV3Plus(encoder_name="resnet50", encoder_depth=5, encoder_weights=None, encoder_output_stride=16,
+                  decoder_channels=256, decoder_atrous_rates=(12, 24, 36), in_channels=3, classes=1, activation=None,
+                  upsampling=4, aux_params=None, device="cuda", seed=0):
+    """smp.DeepLabV3Plus constructor shape (models/__init__.py:17-23).  `encoder_weights` must be None
+    (no network for ImageNet checkpoints: load_state_dict() accepts smp-named weights instead)."""
+    if encoder_name not in RESNETS:
+        raise NotImplementedError("encoder %r: resnet18/34/50 are implemented" % encoder_name)
+    if encoder_weights not in (None, "none"):
+        raise NotImplementedError("pretrained encoder weights cannot be downloaded here; use load_state_dict()")
+    if (encoder_depth, encoder_output_stride, decoder_channels, tuple(decoder_atrous_rates), in_channels, upsampling,
+            activation) != (5, 16, 256, (12, 24, 36), 3, 4, None):
+        raise NotImplementedError("only the reference's DeepLabV3+ configuration is implemented")
+    if aux_params is not None and aux_params.get("pooling", "avg") != "avg":
+        raise NotImplementedError("aux head: average pooling only (models/heads.py)")
+    return SegNet(encoder_name, classes, device, seed)

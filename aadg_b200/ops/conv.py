@@ -8,6 +8,26 @@ import torch
 from .. import _lib
 
 
+# bench.py sets TIMING = [] to bracket every launch with CUDA events: (kind, algorithmic flops, start, end)
+TIMING = None
+
+
+class _timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            self.e1.record()
+            TIMING.append((self.kind, self.flops, self.e0, self.e1))
+
+
 def _nhwc(t, name):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4):
         raise RuntimeError("%s must be a CUDA bf16 [N,H,W,C] tensor (no CPU path)" % name)
@@ -32,7 +52,7 @@ def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False):
         out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
     _, oh, ow, oc, ldy = _nhwc(out, "out")
     assert (oh, ow, oc) == (ho, wo, cout)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("fprop", 2.0 * n * ho * wo * cout * cin * r * s):
         _lib.check(_lib.lib().aadg_conv_fprop_bf16(x.data_ptr(), n, h, w, cin, ldx, wgt.data_ptr(), cout, r, s, stride,
                                                    pad, dil, out.data_ptr(), ho, wo, ldy, 0, int(accumulate),
                                                    _lib.stream_ptr()))
@@ -49,7 +69,7 @@ def dgrad(dy, wgt_t, r, s, stride, pad, dil, in_hw, out=None, accumulate=False):
         out = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=dy.device)
     _, xh, xw, xc, lddx = _nhwc(out, "out")
     assert (xh, xw, xc) == (h, w, cin)
-    with torch.cuda.device(dy.device):
+    with torch.cuda.device(dy.device), _timed("dgrad", 2.0 * n * ho * wo * cout * cin * r * s):
         _lib.check(_lib.lib().aadg_conv_dgrad_bf16(dy.data_ptr(), n, ho, wo, cout, lddy, wgt_t.data_ptr(), cin, r, s,
                                                    stride, pad, dil, out.data_ptr(), h, w, lddx, 0, int(accumulate),
                                                    _lib.stream_ptr()))
@@ -63,7 +83,7 @@ def wgrad(x, dy, r, s, stride, pad, dil, out=None):
     if out is None:
         out = torch.zeros((r * s, cout, cin), dtype=torch.float32, device=x.device)
     assert out.shape == (r * s, cout, cin) and out.dtype == torch.float32 and out.is_contiguous()
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed("wgrad", 2.0 * n * ho * wo * cout * cin * r * s):
         _lib.check(_lib.lib().aadg_conv_wgrad_bf16(x.data_ptr(), n, h, w, cin, ldx, dy.data_ptr(), ho, wo, cout, lddy,
                                                    r, s, stride, pad, dil, out.data_ptr(), _lib.stream_ptr()))
     return out

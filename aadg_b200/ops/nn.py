@@ -1,0 +1,151 @@
+"""Thin torch-facing calls into the layer kernels (csrc/nn_elem.cu, csrc/nn_loss.cu).  All tensors
+are CUDA; activations bf16 `[N,H,W,C]` views whose channel stride may exceed C.  No CPU path."""
+import torch
+
+from .. import _lib
+
+BF16 = torch.bfloat16
+
+
+def _ld(t):
+    assert t.is_cuda and t.dtype == BF16 and t.stride(-1) == 1, "bf16 CUDA channel-last tensor expected"
+    return t.stride(-2)
+
+
+def _pix(t):
+    n = 1
+    for s in t.shape[:-1]:
+        n *= s
+    return n
+
+
+def _call(name, *args):
+    _lib.check(getattr(_lib.lib(), name)(*args, _lib.stream_ptr()))
+
+
+def p(t):
+    return None if t is None else t.data_ptr()
+
+
+def bn_stats(x, sum_, sumsq):
+    _call("aadg_bn_stats", p(x), _pix(x), x.shape[-1], _ld(x), p(sum_), p(sumsq))
+
+
+def bn_finalize(sum_, sumsq, gamma, beta, count, eps, momentum, mean, invstd, scale, shift, run_mean, run_var):
+    _call("aadg_bn_finalize", p(sum_), p(sumsq), p(gamma), p(beta), gamma.numel(), float(count), eps, momentum,
+          p(mean), p(invstd), p(scale), p(shift), p(run_mean), p(run_var))
+
+
+def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None):
+    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0)
+    _call("aadg_bn_apply", p(x), _ld(x), p(scale), p(shift), p(res), _ld(res) if res is not None else 0, p(y), _ld(y),
+          _pix(x), x.shape[-1], flags, int(dropout_seed or 0))
+
+
+def bn_backward(dy, x, y, mean, invstd, gamma, dgamma, dbeta, dx, relu=True, dropout_seed=None, dres=None,
+                dres_accumulate=False):
+    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0)
+    _call("aadg_bn_backward", p(dy), _ld(dy), p(x), _ld(x), p(y), _ld(y) if y is not None else 0, p(mean), p(invstd),
+          p(gamma), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
+          p(dres), _ld(dres) if dres is not None else 0, int(dres_accumulate))
+
+
+def add_(a, b):
+    _call("aadg_add_bf16", p(a), _ld(a), p(b), _ld(b), _pix(a), a.shape[-1])
+
+
+def maxpool_fwd(x):
+    n, h, w, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    arg = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device)
+    _call("aadg_maxpool3x3s2_fwd", p(x), n, h, w, c, p(y), p(arg))
+    return y, arg
+
+
+def maxpool_bwd(dy, arg, in_shape):
+    n, h, w, c = in_shape
+    dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
+    _call("aadg_maxpool3x3s2_bwd", p(dy), p(arg), n, h, w, c, p(dx))
+    return dx
+
+
+def upsample_fwd(x, y):
+    n, h, w, c = x.shape
+    _call("aadg_upsample_bilinear_fwd", p(x), n, h, w, c, _ld(x), p(y), y.shape[1], y.shape[2], _ld(y))
+
+
+def upsample_bwd(dy, dx):
+    n, h, w, c = dx.shape
+    _call("aadg_upsample_bilinear_bwd", p(dy), n, dy.shape[1], dy.shape[2], c, _ld(dy), p(dx), h, w, _ld(dx))
+
+
+def global_sum(x, scale):
+    n, h, w, c = x.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    _call("aadg_global_sum", p(x), n, h * w, c, _ld(x), p(out), float(scale))
+    return out
+
+
+def broadcast_pixels(v, y):
+    n, h, w, c = y.shape
+    _call("aadg_broadcast_pixels", p(v), n, c, p(y), h * w, _ld(y))
+
+
+def f32_to_bf16(x, scale=1.0):
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    _call("aadg_f32_to_bf16", p(x), p(y), x.numel(), float(scale))
+    return y
+
+
+def dwconv3x3(x, w, dil, y, backward_data=False):
+    n, h, wd, c = x.shape
+    _call("aadg_dwconv3x3", p(x), n, h, wd, c, _ld(x), p(w), dil, int(backward_data), p(y), _ld(y))
+
+
+def dwconv3x3_wgrad(x, dy, dil, dw):
+    n, h, wd, c = x.shape
+    _call("aadg_dwconv3x3_wgrad", p(x), n, h, wd, c, _ld(x), p(dy), _ld(dy), dil, p(dw))
+
+
+def im2col_stem(img, r, s, stride, pad, kp):
+    img = img.contiguous()
+    n, _, h, w = img.shape
+    ho, wo = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
+    col = torch.empty((n, ho, wo, kp), dtype=BF16, device=img.device)
+    _call("aadg_im2col_stem", p(img), n, h, w, r, s, stride, pad, kp, p(col))
+    return col
+
+
+def adam_step(params, grads, m, v, lr, beta1, beta2, eps, wd, step):
+    _call("aadg_adam_step", p(params), p(grads), p(m), p(v), params.numel(), lr, beta1, beta2, eps, wd, step)
+
+
+def weight_prep(master, wb, wbt, descs, n):
+    _call("aadg_weight_prep", p(master), p(wb), p(wbt), p(descs), n)
+
+
+def seg_head_fwd(a, w, b):
+    n, h, wd, c = a.shape
+    k = w.shape[0]
+    z = torch.empty((n, h, wd, k), dtype=torch.float32, device=a.device)
+    _call("aadg_seg_head_fwd", p(a), n * h * wd, c, _ld(a), p(w), p(b), k, p(z))
+    return z
+
+
+def seg_loss_fwd(z, target, thr, loss_sum, counts, logits_out=None):
+    n, h, w, k = z.shape
+    _call("aadg_seg_loss_fwd", p(z), n, h, w, k, p(target), target.shape[2], target.shape[3], float(thr),
+          p(loss_sum), p(counts), p(logits_out))
+
+
+def seg_loss_bwd(z, target, grad_scale):
+    n, h, w, k = z.shape
+    dz = torch.empty_like(z)
+    _call("aadg_seg_loss_bwd", p(z), n, h, w, k, p(target), target.shape[2], target.shape[3], float(grad_scale), p(dz))
+    return dz
+
+
+def seg_head_bwd(dz, a, w, da, dw, db):
+    n, h, wd, c = a.shape
+    _call("aadg_seg_head_bwd", p(dz), p(a), n * h * wd, c, _ld(a), p(w), w.shape[0], p(da), _ld(da), p(dw), p(db))

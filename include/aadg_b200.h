@@ -152,6 +152,69 @@ int aadg_conv_dgrad_bf16(const void* dy, int n, int ho, int wo, int cout, int ld
 int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo,
                          int cout, int lddy, int r, int s, int stride, int pad, int dil, float* dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound layers of the segmentation net (bf16 NHWC, channel strides `ld*` in elements, channel
+ * counts multiples of 8, <= 2048) — the cuDNN/ATen batch-norm, ReLU, pooling, up-sampling and
+ * optimiser kernels behind smp.DeepLabV3Plus / torch.optim.Adam (models/__init__.py:17-23,
+ * search_dg.py:132,170-172, scheduler.py:10-11).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* sum[c] += sum_p x[p][c]; sumsq[c] += sum_p x[p][c]^2 (fp32; zero them first) */
+int aadg_bn_stats(const void* x, long long pixels, int c, int ld, float* sum, float* sumsq, void* stream);
+/* mean, 1/sqrt(var+eps), scale = gamma*invstd, shift = beta - mean*scale, running stats (may be NULL) */
+int aadg_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int c, float count,
+                     float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
+                     float* run_mean, float* run_var, void* stream);
+/* y = act(x*scale + shift (+ res)) ; flags bit0 = ReLU, bit1 = Dropout(0.5) keyed by (seed, element) */
+int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr, void* y,
+                  int ldy, long long pixels, int c, int flags, unsigned long long seed, void* stream);
+/* backward of aadg_bn_apply(training statistics): dgamma, dbeta (overwritten), dx, optional dres (+=) */
+int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
+                     const float* invstd, const float* gamma, long long pixels, int c, int flags,
+                     unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,
+                     int dres_accumulate, void* stream);
+int aadg_add_bf16(void* a, int lda, const void* b, int ldb, long long pixels, int c, void* stream);
+/* MaxPool2d(3, stride 2, padding 1): argmax uint8 [n,ho,wo,c] */
+int aadg_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, void* y, void* argmax, void* stream);
+int aadg_maxpool3x3s2_bwd(const void* dy, const void* argmax, int n, int h, int w, int c, void* dx, void* stream);
+/* UpsamplingBilinear2d (align_corners=True) and its transpose */
+int aadg_upsample_bilinear_fwd(const void* x, int n, int h, int w, int c, int ldx, void* y, int ho, int wo, int ldy,
+                               void* stream);
+int aadg_upsample_bilinear_bwd(const void* dy, int n, int ho, int wo, int c, int lddy, void* dx, int h, int w, int lddx,
+                               void* stream);
+/* out fp32 [n,c] = scale * sum over the hw pixels of x bf16 [n,hw,ld] (AdaptiveAvgPool2d(1) with scale = 1/hw) */
+int aadg_global_sum(const void* x, int n, int hw, int c, int ld, float* out, float scale, void* stream);
+/* y[n, p, 0:c] = v[n, 0:c]  (bilinear resize of a 1x1 map) */
+int aadg_broadcast_pixels(const void* v, int n, int c, void* y, int hw, int ldy, void* stream);
+int aadg_f32_to_bf16(const float* x, void* y, long long count, float scale, void* stream);
+/* depthwise 3x3, stride 1, padding = dilation; w fp32 [9][c]; direction 0 forward, 1 data gradient */
+int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int direction, void* y,
+                   int ldy, void* stream);
+int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil, float* dw,
+                         void* stream);
+/* img fp32 [n,3,h,w] -> col bf16 [n*ho*wo][kp], k = (r*S+s)*3 + c, zero padded to kp */
+int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int kp, void* col,
+                     void* stream);
+/* torch.optim.Adam step `step` (1-based) over flat fp32 buffers */
+int aadg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+/* fp32 master weights [taps][cout][cin] -> bf16 copy (+ transposed [taps][cin][cout] copy); descs (device):
+ * per weight { int64 off_master, off_bf16, off_bf16_t (-1: none); int32 taps, cout, cin, 0 } */
+int aadg_weight_prep(const float* master, void* w_bf16, void* w_bf16_t, const void* descs, int n_descs, void* stream);
+
+/* Segmentation head + loss (search_dg.py:140-142,164-165; losses.py:21-23; smp SegmentationHead):
+ * logits z fp32 [pixels][classes] at decoder resolution; classes <= 2 */
+int aadg_seg_head_fwd(const void* a, long long pixels, int c, int lda, const float* w, const float* bias, int classes,
+                      float* z, void* stream);
+/* upsample(align_corners=True) -> sigmoid -> BCELoss sum (double, +=) and TP/FP/FN counts int32
+ * [n][classes][3] (+=) at threshold thr; logits_out fp32 [n,classes,H,W] or NULL; target fp32 [n,classes,H,W] */
+int aadg_seg_loss_fwd(const float* z, int n, int h, int w, int classes, const float* target, int H, int W, float thr,
+                      double* loss_sum, int* counts, float* logits_out, void* stream);
+int aadg_seg_loss_bwd(const float* z, int n, int h, int w, int classes, const float* target, int H, int W,
+                      float grad_scale, float* dz, void* stream);
+int aadg_seg_head_bwd(const float* dz, const void* a, long long pixels, int c, int lda, const float* w, int classes,
+                      void* da, int ldda, float* dw, float* db, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,127 @@
+"""CPU: host-side logic — controller call shapes and bit-exact policy indexing, config defaults, PPO,
+decision-table generators, and the N>1 exchange (world_size 2, gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from aadg_b200.data import decisions as D
+from aadg_b200.data.policy import parse_policies, DGMultiPolicy
+from aadg_b200.host.config import get_config, optic_search_config
+from aadg_b200.host.controller import Controller
+from aadg_b200.host.discriminator import MomentumFeatureDiscriminator
+from aadg_b200.host.losses import CrossEntropy, search_loss
+from aadg_b200.synth import random_policies
+
+
+def test_config_defaults_match_reference_paths():
+    cfg = get_config()
+    assert (cfg.CONTROLLER.L, cfg.CONTROLLER.M, cfg.CONTROLLER.T, cfg.CONTROLLER.C, cfg.CONTROLLER.NUM_MAGS) == (2, 6, 2, 2.5, 10)
+    assert cfg.TRAIN.BATCH_SIZE == 8 and cfg.DATASET.DG.TRAIN == [1, 2, 3]
+    o = optic_search_config()
+    assert o.TRAIN.LR == 0.001 and o.MODEL.BACKBONE == "resnet50" and o.DATASET.NAME == "optic"
+
+
+def test_controller_shapes_and_evaluate_consistency():
+    torch.manual_seed(0)
+    c = Controller(get_config())
+    policies, op_p, mag_p, logp, ent = c(6)
+    assert policies.shape == (6, 20) and policies.dtype == torch.int64
+    assert op_p.shape == (10,) and mag_p.shape == (10,) and logp.shape == (6,) and ent.shape == (6,)
+    assert int(policies[:, 0::2].max()) < 10 and int(policies[:, 1::2].max()) < 10 and int(policies.min()) >= 0
+    assert torch.allclose(c.evaluate(policies, 6), logp, atol=1e-5)
+    parsed = parse_policies(policies.numpy(), get_config())
+    assert len(parsed) == 6 and len(parsed[0]) == 5 and len(parsed[0][0]) == 2
+    assert parsed[2][3][1][1] == policies[2, 3 * 4 + 3].item() / 9
+
+
+def test_ppo_updates_controller():
+    torch.manual_seed(1)
+    cfg = get_config()
+    c = Controller(cfg)
+    crit = search_loss(cfg)
+    opt = torch.optim.Adam(c.parameters(), lr=0.00035)
+    crit.register_optimizer(opt)
+    policies, _, _, logp, ent = c(6)
+    before = [p.detach().clone() for p in c.parameters()]
+    loss, score, e = crit(c, policies, logp, ent, torch.linspace(-1, 1, 6))
+    assert torch.isfinite(loss) and any(not torch.equal(a, b) for a, b in zip(before, c.parameters()))
+
+
+def test_discriminator_and_soft_ce():
+    torch.manual_seed(2)
+    d = MomentumFeatureDiscriminator(3, 64)
+    d.synchronize_parameters()
+    x = torch.randn(12, 64)
+    out, fe = d(x, momentum=True, return_feature=True)
+    assert out.shape == (12, 3) and fe.shape == (12, 128) and not fe.requires_grad
+    assert torch.allclose(d(x), out, atol=1e-6)
+    for p in d.dis.parameters():
+        p.data.add_(1.0)
+    d.momentum_update()
+    assert not torch.allclose(d(x), d(x, momentum=True))
+    t = torch.softmax(torch.randn(12, 3), 1)
+    ce = CrossEntropy()(out, t)
+    assert torch.allclose(ce, (-(t * torch.log_softmax(out, 1)).sum(1)).mean())
+
+
+def test_philox_rows_deterministic_and_in_range():
+    parsed = parse_policies(random_policies(seed=5), get_config())
+    a, _ = D.philox_rows(parsed, 4, 64, 48, 32, (1, 1.5), seed=9, epoch=2, step=3)
+    b, _ = D.philox_rows(parsed, 4, 64, 48, 32, (1, 1.5), seed=9, epoch=2, step=3)
+    c, _ = D.philox_rows(parsed, 4, 64, 48, 32, (1, 1.5), seed=9, epoch=2, step=4)
+    assert a.tobytes() == b.tobytes() and a.tobytes() != c.tobytes()
+    assert len(a) == 24 and (a["src"] == np.repeat(np.arange(4), 6)).all()
+    assert ((a["scale_w"] >= 64) & (a["scale_w"] <= 96)).all()
+    assert ((a["crop_x"] >= 0) & (a["crop_x"] <= a["scale_w"] + 2 * a["pad"] - 32)).all()
+    pol = DGMultiPolicy(parsed, crop=32)
+    r1, _ = pol.rows_for(2, 64, 48)
+    r2, _ = pol.rows_for(2, 64, 48)
+    assert r1.tobytes() != r2.tobytes()          # the step counter advances the stream
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _exchange_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from aadg_b200.host.search import gather_rows, average_, shard_sources
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)
+    feat = torch.randn(6, 8) + rank
+    dc = torch.full((6, 3), float(rank))
+    all_f, all_dc = gather_rows(feat, dc)
+    grads = torch.full((5,), float(rank + 1))
+    average_(grads)
+    q.put((rank, all_f.numpy(), all_dc.numpy(), grads.numpy(), shard_sources(24, rank, world)))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_exchange_gloo():
+    """rank-major feature all-gather gives every rank the same clouds; gradients are averaged;
+    source images are dealt in contiguous blocks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, f0, d0, g0, s0), (r1, f1, d1, g1, s1) = res
+    assert np.array_equal(f0, f1) and np.array_equal(d0, d1) and f0.shape == (12, 8)
+    assert (d0[:6] == 0).all() and (d0[6:] == 1).all()
+    assert np.allclose(g0, 1.5) and np.allclose(g1, 1.5)
+    assert s0 == list(range(12)) and s1 == list(range(12, 24))
