@@ -19,6 +19,7 @@
 //     across CTAs, fp32 `red.add` into dW.
 #include "tc_common.cuh"
 
+#include <stdlib.h>
 #include <algorithm>
 #include <mutex>
 
@@ -213,6 +214,162 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---- persistent variant: tile loop per CTA, two TMEM accumulators, TMA-store epilogue -----------------------
+// One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the MMA issuer fills accumulator
+// (t & 1) while the epilogue warps drain the other one: TMEM -> registers -> bf16 -> 128B-swizzled staging
+// tile in shared memory -> one TMA tensor store (or reduce-add) per 64-channel half, so the output leaves
+// the SM as full 128-byte lines and the epilogue overlaps the next tile's main loop.
+struct IgemmPArgs {
+  int lg_tw, lg_th;
+  int tiles_x, tiles_y, tiles_n, cout_tiles;
+  int in_step, k_blocks;
+  int accumulate;
+  Taps taps;
+};
+template <int BN, int STAGES>
+constexpr int igemm_p_smem_bytes() { return STAGES * (A_BYTES + BN * 128) + 2 * 128 * BN * 2 + 1024 + 256; }
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(IG_THREADS, 1) igemm_p_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmC,
+                                                                const IgemmPArgs a) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int OUT_BYTES = 128 * BN * 2;           // one staged output tile: BN/64 halves of [128][128 B]
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_out = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = (uint64_t*)(stage_out + 2 * OUT_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_map(&tmA); prefetch_map(&tmB); prefetch_map(&tmC); }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int lg_tn = 7 - a.lg_tw - a.lg_th;
+  const int n_tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.cout_tiles;
+  const int total_k = a.taps.n * a.k_blocks;
+
+  auto decode = [&](int t, int& sx0, int& sy0, int& img0, int& n0) {
+    n0 = (t % a.cout_tiles) * BN; t /= a.cout_tiles;
+    sx0 = (t % a.tiles_x) << a.lg_tw; t /= a.tiles_x;
+    sy0 = (t % a.tiles_y) << a.lg_th; t /= a.tiles_y;
+    img0 = t << lg_tn;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int sx0, sy0, img0, n0;
+        decode(t, sx0, sy0, img0, n0);
+        for (int tap = 0; tap < a.taps.n; ++tap) {
+          const int ix = sx0 * a.in_step + a.taps.dx[tap], iy = sy0 * a.in_step + a.taps.dy[tap];
+          const int wi = a.taps.w[tap];
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            tma_load_4d(sa, &tmA, &full[stage], kb * 64, ix, iy, img0);
+            tma_load_3d(sa + A_BYTES, &tmB, &full[stage], kb * 64, n0, wi);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0, phase = 0, it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int k = 0; k < total_k; ++k) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = make_sdesc(sa, 16, 1024);
+          const uint64_t bdesc = make_sdesc(sa + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(acc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const bool leader = threadIdx.x == 64;     // first epilogue thread issues the TMA stores
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int sx0, sy0, img0, n0;
+      decode(t, sx0, sy0, img0, n0);
+      uint8_t* so = stage_out + buf * OUT_BYTES;
+      // the staging buffer was last used two tiles ago: its TMA store must have finished reading it
+      if (leader) tma_store_wait_read<1>();
+      named_bar_sync(1, 128);
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < BN / 64; ++h) {
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + h * 64;
+        tmem_ld32(taddr, r);
+        tmem_ld32(taddr + 32, r + 32);
+        tmem_ld_wait();
+        uint8_t* row = so + h * (128 * 128) + m * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
+          v.y = pack_bf16x2(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
+          v.z = pack_bf16x2(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
+          v.w = pack_bf16x2(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+          *reinterpret_cast<uint4*>(row + ((j ^ (m & 7)) << 4)) = v;
+        }
+      }
+      // accumulator drained: hand it back to the MMA issuer (one arrival per epilogue warp)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (leader) {
+#pragma unroll
+        for (int h = 0; h < BN / 64; ++h) {
+          if (a.accumulate) tma_reduce_add_4d(&tmC, so + h * (128 * 128), n0 + h * 64, sx0, sy0, img0);
+          else tma_store_4d(&tmC, so + h * (128 * 128), n0 + h * 64, sx0, sy0, img0);
+        }
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // ---- wgrad --------------------------------------------------------------------------------------------
 struct WgradArgs {
   int lg_tw, lg_th;            // log2 extents of the 64-pixel K tile in x, y
@@ -346,6 +503,35 @@ struct ConvGeom {
   int R, S, stride, pad, dil;
 };
 
+static int tuning_stages() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AADG_CONV_STAGES");
+    v = e ? atoi(e) : 2;
+    if (v < 2 || v > 4) v = 2;
+  }
+  return v;
+}
+
+static int tuning_persistent() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AADG_CONV_PERSISTENT");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static int num_sms() {
+  static int v = 0;
+  if (!v) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+  }
+  return v;
+}
+
 template <int BN, int STAGES>
 static int launch_igemm_t(const CUtensorMap& mA, const CUtensorMap& mB, const IgemmArgs& args, int cout_tiles,
                           cudaStream_t st) {
@@ -406,7 +592,44 @@ static int launch_igemm(const void* in, int Nimg, int Hin, int Win, int Cin, int
     if (rc) return rc;
   }
   const int cout_tiles = (Cn + bn - 1) / bn;
-  if (bn == 64) return launch_igemm_t<64, 4>(mA, mB, a, cout_tiles, st);
+  if (o_step == 1 && o_y0 == 0 && o_x0 == 0 && Wsub == Wout && Hsub == Hout && tuning_persistent()) {
+    // persistent kernel with TMA-store epilogue: output = channel slice [c_off, c_off + Cn) of the NHWC tensor
+    CUtensorMap mC;
+    const long long dims[4] = {Cn, Wout, Hout, Nimg};
+    const long long strides[3] = {ldc, (long long)Wout * ldc, (long long)Hout * Wout * ldc};
+    const int box[4] = {64, 1 << a.lg_tw, 1 << a.lg_th, 1 << lg_tn};
+    int rc = make_map_bf16(&mC, (const __nv_bfloat16*)out + c_off, 4, dims, strides, box, nullptr);
+    if (rc) return rc;
+    IgemmPArgs pa{};
+    pa.lg_tw = a.lg_tw; pa.lg_th = a.lg_th;
+    pa.tiles_x = a.tiles_x; pa.tiles_y = a.tiles_y; pa.tiles_n = a.tiles_n; pa.cout_tiles = cout_tiles;
+    pa.in_step = in_step; pa.k_blocks = a.k_blocks; pa.accumulate = accumulate;
+    pa.taps = taps;
+    const int n_tiles = pa.tiles_x * pa.tiles_y * pa.tiles_n * cout_tiles;
+    const int grid = std::min(n_tiles, num_sms());
+    if (bn == 64) {
+      constexpr int smem = igemm_p_smem_bytes<64, 6>();
+      static bool set64 = false;
+      if (!set64) { AADG_CUDA_TRY(cudaFuncSetAttribute(igemm_p_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
+      igemm_p_kernel<64, 6><<<grid, IG_THREADS, smem, st>>>(mA, mB, mC, pa);
+    } else {
+      constexpr int smem = igemm_p_smem_bytes<128, 4>();
+      static bool set128 = false;
+      if (!set128) { AADG_CUDA_TRY(cudaFuncSetAttribute(igemm_p_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set128 = true; }
+      igemm_p_kernel<128, 4><<<grid, IG_THREADS, smem, st>>>(mA, mB, mC, pa);
+    }
+    return check_launch("igemm persistent kernel");
+  }
+  // fewer stages = less shared memory = more CTAs per SM: the per-CTA latencies (TMEM allocation, first TMA
+  // round trip, epilogue) of one CTA overlap the main loop of its neighbours
+  const int stages = tuning_stages();
+  if (bn == 64) {
+    if (stages == 2) return launch_igemm_t<64, 2>(mA, mB, a, cout_tiles, st);
+    if (stages == 3) return launch_igemm_t<64, 3>(mA, mB, a, cout_tiles, st);
+    return launch_igemm_t<64, 4>(mA, mB, a, cout_tiles, st);
+  }
+  if (stages == 2) return launch_igemm_t<128, 2>(mA, mB, a, cout_tiles, st);
+  if (stages == 3) return launch_igemm_t<128, 3>(mA, mB, a, cout_tiles, st);
   return launch_igemm_t<128, 4>(mA, mB, a, cout_tiles, st);
 }
 
@@ -563,7 +786,14 @@ int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, c
     if (rc) return rc;
   }
   dim3 grid((cout + 127) / 128, (cin + bn - 1) / bn, r * s * ksplit);
-  if (bn == 64) return launch_wgrad_t<64, 4>(mDY, mX, a, grid, (cudaStream_t)stream);
+  const int stages = tuning_stages();
+  if (bn == 64) {
+    if (stages == 2) return launch_wgrad_t<64, 2>(mDY, mX, a, grid, (cudaStream_t)stream);
+    if (stages == 3) return launch_wgrad_t<64, 3>(mDY, mX, a, grid, (cudaStream_t)stream);
+    return launch_wgrad_t<64, 4>(mDY, mX, a, grid, (cudaStream_t)stream);
+  }
+  if (stages == 2) return launch_wgrad_t<128, 2>(mDY, mX, a, grid, (cudaStream_t)stream);
+  if (stages == 3) return launch_wgrad_t<128, 3>(mDY, mX, a, grid, (cudaStream_t)stream);
   return launch_wgrad_t<128, 4>(mDY, mX, a, grid, (cudaStream_t)stream);
 }
 

@@ -56,6 +56,16 @@ __device__ __forceinline__ unsigned int dropout_bits8(unsigned long long seed, u
   return r.x & 0xffu;
 }
 
+// grid-stride walk over (pixel p, 8-channel group g) without a division per iteration
+#define AADG_FOR_PIXEL_GROUPS(P, G, p, g)                                                      \
+  const long long _tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;                     \
+  const long long _stride = (long long)gridDim.x * blockDim.x;                                 \
+  const int _sg = (int)(_stride % (G));                                                        \
+  const long long _sp = _stride / (G);                                                         \
+  long long p = _tid / (G);                                                                    \
+  int g = (int)(_tid % (G));                                                                   \
+  for (; p < (P); p += _sp, g += _sg, (g >= (G) ? (g -= (G), ++p) : 0))
+
 // ---- batch-norm ------------------------------------------------------------------------------------
 // grid-stride over pixels; thread (tx, ty): tx = 8-channel group, ty = pixel lane
 template <int NACC, class F>
@@ -64,9 +74,18 @@ __device__ __forceinline__ void channel_reduce(int P, int C, float* out0, float*
   const int G = C >> 3;
   const int tx = threadIdx.x, ty = threadIdx.y;
   float a0[8] = {}, a1[8] = {};
-  if (tx < G)
-    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y)
+  if (tx < G) {
+    const long long step = (long long)gridDim.x * blockDim.y;
+    long long p = (long long)blockIdx.x * blockDim.y + ty;
+    float b0[8] = {}, b1[8] = {};          // second accumulator set: two independent load streams in flight
+    for (; p + step < P; p += 2 * step) {
       f((int)p, tx, a0, a1);
+      f((int)(p + step), tx, b0, b1);
+    }
+    if (p < P) f((int)p, tx, a0, a1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0[i] += b0[i]; a1[i] += b1[i]; }
+  }
   __shared__ float s0[2048], s1[2048];
   for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) { s0[i] = 0.f; s1[i] = 0.f; }
   __syncthreads();
@@ -115,10 +134,8 @@ __global__ void bn_apply_kernel(const bf16* x, int ldx, const float* scale, cons
                                 int ldr, bf16* y, int ldy, long long P, int C, int flags,
                                 unsigned long long seed) {
   const int G = C >> 3;
-  const long long total = P * G;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long p = e / G;
-    const int g = (int)(e - p * G);
+  AADG_FOR_PIXEL_GROUPS(P, G, p, g) {
+    const long long e = p * G + g;
     V8 v = ld8(x + p * ldx + g * 8);
     const V8 sc = ld8f(scale + g * 8), sh = ld8f(shift + g * 8);
 #pragma unroll
@@ -143,13 +160,19 @@ __global__ void bn_apply_kernel(const bf16* x, int ldx, const float* scale, cons
 
 // g = dy * relu'(y) * dropout ; dbeta = sum g ; dgamma = sum g * xhat
 __global__ void bn_bwd_reduce_kernel(const bf16* dy, int lddy, const bf16* x, int ldx, const bf16* y, int ldy,
-                                     const float* mean, const float* invstd, int P, int C, int flags,
-                                     unsigned long long seed, float* dgamma, float* dbeta) {
+                                     const float* mean, const float* invstd, const float* gamma,
+                                     const float* beta, int P, int C, int flags, unsigned long long seed,
+                                     float* dgamma, float* dbeta) {
   const int G = C >> 3;
   channel_reduce<2>(P, C, dgamma, dbeta, [&](int p, int g, float* a0, float* a1) {
     V8 d = ld8(dy + (size_t)p * lddy + g * 8);
     const V8 xv = ld8(x + (size_t)p * ldx + g * 8);
-    if (flags & 1) {
+    if (flags & 4) {
+      // no residual: relu(x*scale + shift) > 0 recomputed exactly as forward evaluated it (`beta` = saved shift)
+      const V8 is = ld8f(invstd + g * 8), ga = ld8f(gamma + g * 8), sh = ld8f(beta + g * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.v[i] = fmaf(xv.v[i], ga.v[i] * is.v[i], sh.v[i]) > 0.f ? d.v[i] : 0.f;
+    } else if (flags & 1) {
       const V8 yv = ld8(y + (size_t)p * ldy + g * 8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
@@ -167,19 +190,22 @@ __global__ void bn_bwd_reduce_kernel(const bf16* dy, int lddy, const bf16* x, in
 
 // dx = gamma*invstd * (g - dbeta/P - xhat*dgamma/P) ; optional dres = g (gradient of the residual input)
 __global__ void bn_bwd_apply_kernel(const bf16* dy, int lddy, const bf16* x, int ldx, const bf16* y, int ldy,
-                                    const float* mean, const float* invstd, const float* gamma,
+                                    const float* mean, const float* invstd, const float* gamma, const float* beta,
                                     const float* dgamma, const float* dbeta, long long P, int C, int flags,
                                     unsigned long long seed, bf16* dx, int lddx, bf16* dres, int lddr,
                                     int dres_accumulate) {
   const int G = C >> 3;
-  const long long total = P * G;
   const float invP = 1.f / (float)P;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long p = e / G;
-    const int g = (int)(e - p * G);
+  AADG_FOR_PIXEL_GROUPS(P, G, p, g) {
+    const long long e = p * G + g;
     V8 d = ld8(dy + p * lddy + g * 8);
     const V8 xv = ld8(x + p * ldx + g * 8);
-    if (flags & 1) {
+    const V8 m = ld8f(mean + g * 8), is = ld8f(invstd + g * 8), ga = ld8f(gamma + g * 8);
+    if (flags & 4) {
+      const V8 sh = ld8f(beta + g * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.v[i] = fmaf(xv.v[i], ga.v[i] * is.v[i], sh.v[i]) > 0.f ? d.v[i] : 0.f;
+    } else if (flags & 1) {
       const V8 yv = ld8(y + p * ldy + g * 8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
@@ -198,7 +224,6 @@ __global__ void bn_bwd_apply_kernel(const bf16* dy, int lddy, const bf16* x, int
       }
       st8(dres + p * lddr + g * 8, r);
     }
-    const V8 m = ld8f(mean + g * 8), is = ld8f(invstd + g * 8), ga = ld8f(gamma + g * 8);
     const V8 dg = ld8f(dgamma + g * 8), db = ld8f(dbeta + g * 8);
     V8 o;
 #pragma unroll
@@ -213,10 +238,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* dy, int lddy, const bf16* x, int
 // a (+)= b, bf16 NHWC with strides (gradient fan-in of skip connections)
 __global__ void add_kernel(bf16* a, int lda, const bf16* b, int ldb, long long P, int C) {
   const int G = C >> 3;
-  const long long total = P * G;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long p = e / G;
-    const int g = (int)(e - p * G);
+  AADG_FOR_PIXEL_GROUPS(P, G, p, g) {
     V8 x = ld8(a + p * lda + g * 8);
     const V8 yv = ld8(b + p * ldb + g * 8);
 #pragma unroll
@@ -417,13 +439,11 @@ __global__ void f32_to_bf16_kernel(const float* x, bf16* y, long long n, float s
 __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const float* w, int dil, int sign,
                              bf16* y, int ldy) {
   const int G = C >> 3;
-  const long long total = (long long)N * H * W * G;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(e % G);
-    long long p = e / G;
-    const int ox = (int)(p % W); p /= W;
-    const int oy = (int)(p % H);
-    const int n = (int)(p / H);
+  const int oy = blockIdx.y, n = blockIdx.z;
+  const bf16* xn = x + (size_t)n * H * W * ldx;
+  bf16* yrow = y + ((size_t)n * H + oy) * W * ldy;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < W * G; e += gridDim.x * blockDim.x) {
+    const int ox = e / G, g = e - ox * G;
     V8 acc;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
@@ -432,59 +452,90 @@ __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
       const int iy = oy + (r - 1) * dil * sign;
       if (iy < 0 || iy >= H) continue;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ix = ox + (s - 1) * dil * sign;
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int ix = ox + (s2 - 1) * dil * sign;
         if (ix < 0 || ix >= W) continue;
-        const V8 v = ld8(x + (((size_t)n * H + iy) * W + ix) * ldx + g * 8);
-        const V8 wv = ld8f(w + (size_t)(r * 3 + s) * C + g * 8);
+        const V8 v = ld8(xn + ((size_t)iy * W + ix) * ldx + g * 8);
+        const V8 wv = ld8f(w + (size_t)(r * 3 + s2) * C + g * 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wv.v[i], v.v[i], acc.v[i]);
       }
     }
-    st8(y + (((size_t)n * H + oy) * W + ox) * ldy + g * 8, acc);
+    st8(yrow + (size_t)ox * ldy + g * 8, acc);
   }
 }
-// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]; grid (blocks, 9): one tap per blockIdx.y
+// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]: one pass over dy, the nine shifted x reads hit L1/L2;
+// 72 register accumulators per thread, block reduction in dynamic shared memory [9][C]
 __global__ void dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const bf16* dy, int lddy,
                                    int dil, float* dw) {
-  const int t = blockIdx.y, r = t / 3, s = t % 3;
-  const int P = N * H * W;
-  float* dummy = nullptr;
-  channel_reduce<1>(P, C, dw + (size_t)t * C, dummy, [&](int p, int g, float* a0, float* a1) {
-    const int ox = p % W, oy = (p / W) % H, n = p / (W * H);
-    const int iy = oy + (r - 1) * dil, ix = ox + (s - 1) * dil;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) return;
-    const V8 d = ld8(dy + (size_t)p * lddy + g * 8);
-    const V8 v = ld8(x + (((size_t)n * H + iy) * W + ix) * ldx + g * 8);
+  extern __shared__ float s_dw[];
+  const int G = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long P = (long long)N * H * W;
+  float acc[9][8] = {};
+  if (tx < G)
+    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y) {
+      const int ox = (int)(p % W), oy = (int)((p / W) % H);
+      const long long nb = p - (long long)oy * W - ox;      // pixel index of (n, 0, 0)
+      const V8 d = ld8(dy + (size_t)p * lddy + tx * 8);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a0[i] = fmaf(d.v[i], v.v[i], a0[i]);
-  });
+      for (int r = 0; r < 3; ++r) {
+        const int iy = oy + (r - 1) * dil;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const int ix = ox + (s2 - 1) * dil;
+          if (ix < 0 || ix >= W) continue;
+          const V8 v = ld8(x + (size_t)(nb + (long long)iy * W + ix) * ldx + tx * 8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[r * 3 + s2][i] = fmaf(d.v[i], v.v[i], acc[r * 3 + s2][i]);
+        }
+      }
+    }
+  for (int i = ty * blockDim.x + tx; i < 9 * C; i += blockDim.x * blockDim.y) s_dw[i] = 0.f;
+  __syncthreads();
+  if (tx < G) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * C + tx * 8 + i], acc[t][i]);
+  }
+  __syncthreads();
+  for (int i = ty * blockDim.x + tx; i < 9 * C; i += blockDim.x * blockDim.y) atomicAdd(&dw[i], s_dw[i]);
 }
 
 // ---- stem im2col: fp32 NCHW [-1,1] image -> bf16 [N*Ho*Wo][KP] patches, k = (r*S + s)*3 + c --------------------
+// one CTA per (image, output row): the R input rows it needs are staged as bf16 in shared memory
+// [R][3][W + 2*pad] (zero padded), then every thread emits 16-byte groups of 8 patch values
 __global__ void im2col_stem_kernel(const float* img, int N, int H, int W, int R, int S, int stride, int pad, int Ho,
                                    int Wo, int KP, bf16* col) {
-  const long long total = (long long)N * Ho * Wo * (KP / 8);
-  const int K = R * S * 3;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int kg = (int)(e % (KP / 8));
-    long long p = e / (KP / 8);
-    const int ox = (int)(p % Wo); p /= Wo;
-    const int oy = (int)(p % Ho);
-    const int n = (int)(p / Ho);
-    V8 o;
+  extern __shared__ bf16 s_rows[];
+  const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  const int WP = W + 2 * pad;
+  for (int e = threadIdx.x; e < R * 3 * WP; e += blockDim.x) {
+    const int xp = e % WP, c = (e / WP) % 3, r = e / (3 * WP);
+    const int iy = oy * stride - pad + r, ix = xp - pad;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(((size_t)n * 3 + c) * H + iy) * W + ix];
+    s_rows[e] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int K = R * S * 3, KG = KP / 8;
+  bf16* orow = col + ((size_t)n * Ho + oy) * Wo * KP;
+  for (int e = threadIdx.x; e < Wo * KG; e += blockDim.x) {
+    const int kg = e % KG, ox = e / KG;
+    __align__(16) bf16 o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int k = kg * 8 + i;
-      float v = 0.f;
+      bf16 v = __float2bfloat16_rn(0.f);
       if (k < K) {
-        const int c = k % 3, rs = k / 3, s = rs % S, r = rs / S;
-        const int iy = oy * stride - pad + r, ix = ox * stride - pad + s;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(((size_t)n * 3 + c) * H + iy) * W + ix];
+        const int c = k % 3, rs = k / 3, s2 = rs % S, r = rs / S;
+        v = s_rows[(r * 3 + c) * WP + ox * stride + s2];
       }
-      o.v[i] = v;
+      o[i] = v;
     }
-    st8(col + (((size_t)n * Ho + oy) * Wo + ox) * KP + kg * 8, o);
+    *reinterpret_cast<uint4*>(orow + (size_t)ox * KP + kg * 8) = *reinterpret_cast<const uint4*>(o);
   }
 }
 
@@ -568,7 +619,7 @@ int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift
 }
 
 int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
-                     const float* invstd, const float* gamma, long long pixels, int c, int flags,
+                     const float* invstd, const float* gamma, const float* shift, long long pixels, int c, int flags,
                      unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,
                      int dres_accumulate, void* stream) {
   NN_REQ_C(c);
@@ -578,10 +629,13 @@ int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const voi
   AADG_CUDA_TRY(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
   const dim3 blk = reduce_block(c);
   const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 8);
+  AADG_REQUIRE(!(flags & 1) || (flags & 4) || y, "ReLU mask needs y (or flag 4 to recompute it from x)");
+  AADG_REQUIRE(!(flags & 4) || shift, "flag 4 needs the forward shift vector");
   bn_bwd_reduce_kernel<<<std::max(blocks, 1), blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y,
-                                                           ldy, mean, invstd, (int)pixels, c, flags, seed, dgamma, dbeta);
+                                                           ldy, mean, invstd, gamma, shift, (int)pixels, c, flags, seed,
+                                                           dgamma, dbeta);
   bn_bwd_apply_kernel<<<grid_for(pixels * (c / 8)), 256, 0, st>>>(
-      (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y, ldy, mean, invstd, gamma, dgamma, dbeta, pixels, c,
+      (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y, ldy, mean, invstd, gamma, shift, dgamma, dbeta, pixels, c,
       flags, seed, (bf16*)dx, lddx, (bf16*)dres, lddr, dres_accumulate);
   return check_launch("bn_backward");
 }
@@ -644,8 +698,10 @@ int aadg_f32_to_bf16(const float* x, void* y, long long count, float scale, void
 int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int direction, void* y,
                    int ldy, void* stream) {
   NN_REQ_C(c);
-  dw3x3_kernel<<<grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, n, h, w, c, ldx, wgt, dil, direction ? -1 : 1, (bf16*)y, ldy);
+  AADG_REQUIRE(h <= 65535 && n <= 65535, "image too tall / batch too large for the depthwise grid");
+  dim3 grid(std::max(1, std::min((w * (c / 8) + 255) / 256, 64)), h, n);
+  dw3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, wgt, dil, direction ? -1 : 1,
+                                                       (bf16*)y, ldy);
   return check_launch("dwconv3x3");
 }
 int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil, float* dw,
@@ -655,8 +711,14 @@ int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, con
   AADG_REQUIRE(pixels < (1ll << 31), "too many pixels");
   const dim3 blk = reduce_block(c);
   const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 2);
-  dim3 grid(std::max(blocks, 1), 9);
-  dw3x3_wgrad_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, lddy, dil, dw);
+  const size_t smem = (size_t)9 * c * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(dw3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 2048 * 4));
+    attr_set = true;
+  }
+  dw3x3_wgrad_kernel<<<std::max(blocks, 1), blk, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx,
+                                                                              (const bf16*)dy, lddy, dil, dw);
   return check_launch("dwconv3x3 wgrad");
 }
 
@@ -665,8 +727,14 @@ int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int st
                      void* stream) {
   AADG_REQUIRE(kp % 8 == 0 && kp >= r * s * 3, "kp must be a multiple of 8 and >= R*S*3");
   const int ho = (h + 2 * pad - r) / stride + 1, wo = (w + 2 * pad - s) / stride + 1;
-  im2col_stem_kernel<<<grid_for((long long)n * ho * wo * (kp / 8)), 256, 0, (cudaStream_t)stream>>>(
-      img, n, h, w, r, s, stride, pad, ho, wo, kp, (bf16*)col);
+  const size_t smem = (size_t)r * 3 * (w + 2 * pad) * sizeof(bf16);
+  AADG_REQUIRE(smem <= 200 * 1024, "image too wide for the staged im2col (%zu bytes of shared memory)", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(im2col_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  im2col_stem_kernel<<<n * ho, 256, smem, (cudaStream_t)stream>>>(img, n, h, w, r, s, stride, pad, ho, wo, kp, (bf16*)col);
   return check_launch("im2col");
 }
 

@@ -168,12 +168,13 @@ class BatchNorm:
             torch.mul(self.gamma.data, s[3], out=s[4])
             torch.sub(self.beta.data, s[2] * s[4], out=s[5])
         K.bn_apply(x, s[4], s[5], y, res=res, relu=relu, dropout_seed=dropout_seed)
-        self.saved = (s[2].clone(), s[3].clone()) if training else None
+        self.saved = s[2:6].clone() if training else None       # mean, invstd, scale, shift
 
     def backward(self, dy, x, y, dx, relu=True, dropout_seed=None, dres=None, dres_accumulate=False):
-        mean, invstd = self.saved
-        K.bn_backward(dy, x, y, mean, invstd, self.gamma.data, self.gamma.grad, self.beta.grad, dx, relu=relu,
-                      dropout_seed=dropout_seed, dres=dres, dres_accumulate=dres_accumulate)
+        """y=None: no residual was added in forward, the ReLU mask is recomputed from x (saves reading y)."""
+        sv = self.saved
+        K.bn_backward(dy, x, y, sv[0], sv[1], self.gamma.data, self.gamma.grad, self.beta.grad, dx, relu=relu,
+                      dropout_seed=dropout_seed, dres=dres, dres_accumulate=dres_accumulate, shift=sv[3])
         self.saved = None
 
 
@@ -199,7 +200,8 @@ class ConvBN:
         if out is None:
             out = torch.empty((n, ho, wo, self.cout), dtype=BF16, device=x.device)
         self.bn.forward(pre, out, training, res=res, relu=self.relu, dropout_seed=dropout_seed)
-        self.ctx = (x, pre, out, dropout_seed) if training else None
+        # the output is only needed by backward for the ReLU mask of a residual sum
+        self.ctx = (x, pre, out if res is not None else None, dropout_seed) if training else None
         return out
 
     def backward(self, dy, dx=None, accumulate=False, want_dres=False, dres=None, dres_accumulate=False):
@@ -208,7 +210,7 @@ class ConvBN:
         self.ctx = None
         dpre = torch.empty_like(pre)
         if want_dres and dres is None:
-            dres = torch.empty(y.shape, dtype=BF16, device=y.device)
+            dres = torch.empty(pre.shape, dtype=BF16, device=pre.device)
         self.bn.backward(dy, pre, y, dpre, relu=self.relu, dropout_seed=seed, dres=dres if want_dres else None,
                          dres_accumulate=dres_accumulate)
         C.wgrad(x, dpre, self.k, self.k, self.stride, self.pad, self.dil, out=self.w.grad)

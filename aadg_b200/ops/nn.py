@@ -43,10 +43,11 @@ def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None):
 
 
 def bn_backward(dy, x, y, mean, invstd, gamma, dgamma, dbeta, dx, relu=True, dropout_seed=None, dres=None,
-                dres_accumulate=False):
-    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0)
+                dres_accumulate=False, shift=None):
+    """y=None with relu=True recomputes the ReLU mask from x and the forward `shift` (no residual case)."""
+    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (4 if (relu and y is None) else 0)
     _call("aadg_bn_backward", p(dy), _ld(dy), p(x), _ld(x), p(y), _ld(y) if y is not None else 0, p(mean), p(invstd),
-          p(gamma), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
+          p(gamma), p(shift), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
           p(dres), _ld(dres) if dres is not None else 0, int(dres_accumulate))
 
 

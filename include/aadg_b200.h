@@ -92,6 +92,20 @@ int aadg_u8_policy_normalize(const uint8_t* src_images, const uint8_t* src_masks
                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Float tensor augmentation bank — replaces the 19 operations of data/operations.py:142-399 /
+ * data/functional.py:110-271 (+ data/kernels.py:9-13), forward values:
+ *     out = clamp(mask_b * op(x, mag_b) + (1 - mask_b) * x, 0, 1)          (operations.py:73-100)
+ * x, out float32 [batch,3,h,w] in [0,1] (out != x); mag, mask float32 [batch] on the device (NULL: mag 0,
+ * mask 1); perm int32 [batch] (SamplePairing only).  op = index in data/operations.py __all__:
+ * ShearX 0, ShearY 1, TranslateX 2, TranslateY 3, HorizontalFlip 4, VerticalFlip 5, Rotate 6, Invert 7,
+ * Solarize 8, Posterize 9, Gray 10, Contrast 11, AutoContrast 12, Saturate 13, Brightness 14, Hue 15,
+ * SamplePairing 16, Equalize 17, Sharpness 18.
+ * ---------------------------------------------------------------------------------------------- */
+size_t aadg_f32_workspace_bytes(int batch);
+int aadg_f32_op(int op, const float* x, int batch, int h, int w, const float* mag, const float* mask,
+                const int32_t* perm, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Sinkhorn diversity reward — replaces geomloss.SamplesLoss("sinkhorn", cost=<cosine KeOps formula>,
  * backend="online") constructed at search_dg.py:116 / search_dg_2d.py:116 and called at
  * search_dg.py:158-160 / search_dg_2d.py:159-161 (p=2, blur=.05, scaling=.5, debiased, uniform
@@ -168,9 +182,11 @@ int aadg_bn_finalize(const float* sum, const float* sumsq, const float* gamma, c
 /* y = act(x*scale + shift (+ res)) ; flags bit0 = ReLU, bit1 = Dropout(0.5) keyed by (seed, element) */
 int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr, void* y,
                   int ldy, long long pixels, int c, int flags, unsigned long long seed, void* stream);
-/* backward of aadg_bn_apply(training statistics): dgamma, dbeta (overwritten), dx, optional dres (+=) */
+/* backward of aadg_bn_apply(training statistics): dgamma, dbeta (overwritten), dx, optional dres (+=).
+ * flags bit2 (4): no residual was added, recompute the ReLU mask from x and the forward pass's `shift`
+ * vector (y and ldy unused) */
 int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
-                     const float* invstd, const float* gamma, long long pixels, int c, int flags,
+                     const float* invstd, const float* gamma, const float* shift, long long pixels, int c, int flags,
                      unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,
                      int dres_accumulate, void* stream);
 int aadg_add_bf16(void* a, int lda, const void* b, int ldb, long long pixels, int c, void* stream);
