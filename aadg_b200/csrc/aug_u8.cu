@@ -29,6 +29,7 @@ namespace u8 {
 constexpr int TW = 128;          // tile width in pixels
 constexpr int TH = 8;            // tile height in pixels
 constexpr int NT = 256;          // threads per CTA: 32 threads x 4 pixels per tile row
+constexpr int TILES_PER_CTA = 8;  // consecutive tiles walked by one CTA (amortises the table set-up)
 constexpr int RS = 432;           // shared-memory bytes per staged row: (TW+2)*3 + 2x15 alignment slack, 16-B multiple
 static_assert(RS % 16 == 0 && RS >= (TW + 2) * 3 + 30, "row stride must keep 16-byte alignment for bulk copies");
 
@@ -176,17 +177,31 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
   const PassItem it = a.items[blockIdx.y];
   const int W = a.W, H = a.H;
   const int tiles_x = (W + TW - 1) / TW;
-  const int x0 = (blockIdx.x % tiles_x) * TW;
-  const int y0 = (blockIdx.x / tiles_x) * TH;
+  const int n_tiles = tiles_x * ((H + TH - 1) / TH);
   const int tid = threadIdx.x;
 
   if (tid < (int)(sizeof(DevRow) / 4)) ((int*)&s_row)[tid] = ((const int*)&a.rows[it.row])[tid];
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  // per-CTA set-up, amortised over TILES_PER_CTA tiles: tables, normalisation map, histograms
+  {
+    const uint4* g = (const uint4*)(a.luts + (size_t)it.row * AADG_MAX_OPS * 768);
+    uint4* s = (uint4*)s_luts;
+    for (int i = tid; i < AADG_MAX_OPS * 768 / 16; i += NT) s[i] = g[i];
+    if (MODE == MODE_F32) s_norm[tid] = __fsub_rn(__fdiv_rn((float)tid, 127.5f), 1.0f);
+    if (MODE == MODE_STATS)
+      for (int i = tid; i < (NT / 32) * 768; i += NT) s_hist[i] = 0;
+  }
   __syncthreads();
   const DevRow& row = s_row;
   const uint8_t* base = it.base < 0 ? a.src + (size_t)row.src * H * W * 3
                                     : a.scratch + (size_t)it.base * H * W * 3;
   const int halo = it.sharp >= 0 ? 1 : 0;
+  unsigned int lsum = 0;
+  uint32_t bar_phase = 0;
+  const int t_end = min(n_tiles, (int)(blockIdx.x + 1) * TILES_PER_CTA);
+  for (int t = blockIdx.x * TILES_PER_CTA; t < t_end; ++t) {
+  const int x0 = (t % tiles_x) * TW;
+  const int y0 = (t / tiles_x) * TH;
   const int ya = max(y0 - halo, 0), yb = min(y0 + TH + halo, H);   // staged image rows [ya,yb)
   const int bx0 = max((x0 - halo) * 3, 0), bx1 = min((x0 + TW + halo) * 3, W * 3);
   int sbase;   // byte column of the image row that sits at tile row offset 0
@@ -212,16 +227,7 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
   } else {
     sbase = bx0;
   }
-  // tables and the normalisation map while the copies fly
-  {
-    const uint4* g = (const uint4*)(a.luts + (size_t)it.row * AADG_MAX_OPS * 768);
-    uint4* s = (uint4*)s_luts;
-    for (int i = tid; i < AADG_MAX_OPS * 768 / 16; i += NT) s[i] = g[i];
-    if (MODE == MODE_F32) s_norm[tid] = __fsub_rn(__fdiv_rn((float)tid, 127.5f), 1.0f);
-    if (MODE == MODE_STATS)
-      for (int i = tid; i < (NT / 32) * 768; i += NT) s_hist[i] = 0;
-  }
-  __syncthreads();
+  if (it.gather || !a.aligned) __syncthreads();    // generic byte copies / nothing staged yet
 
   const int pre_end = it.sharp >= 0 ? it.sharp : it.s1;   // steps [s0,pre_end) before the stencil
   if (it.gather) {
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
     }
     __syncthreads();
   } else {
-    if (a.aligned) mbar_wait(&bar, 0);
+    if (a.aligned) { mbar_wait(&bar, bar_phase); bar_phase ^= 1; }
     if (it.sharp >= 0 && pre_end > it.s0) {
       // pointwise prefix applied in place on tile + halo before the stencil reads neighbours
       const int nx = (bx1 - bx0) / 3;
@@ -286,24 +292,12 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
 
   if (MODE == MODE_STATS) {
     unsigned int* hh = s_hist + (tid >> 5) * 768;
-    unsigned int lsum = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (row_ok && xq + i < W) {
         atomicAdd(&hh[vr[i]], 1u); atomicAdd(&hh[256 + vg[i]], 1u); atomicAdd(&hh[512 + vb[i]], 1u);
         lsum += luma_u8(vr[i], vg[i], vb[i]);
       }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-    __syncthreads();
-    Stat* st = a.stats + it.out;
-    for (int i = tid; i < 768; i += NT) {
-      unsigned int v = 0;
-#pragma unroll
-      for (int w = 0; w < NT / 32; ++w) v += s_hist[w * 768 + i];
-      if (v) atomicAdd(&st->hist[0][0] + i, v);
-    }
-    if ((tid & 31) == 0 && lsum) atomicAdd(&st->luma_sum, (unsigned long long)lsum);
   } else if (MODE == MODE_U8) {
     if (row_ok) {
       uint8_t* o = a.out_u8 + ((size_t)it.out * H + y) * W * 3 + (size_t)xq * 3;
@@ -333,6 +327,22 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
           if (xq + i < W) { o[i] = s_norm[vr[i]]; o[plane + i] = s_norm[vg[i]]; o[2 * plane + i] = s_norm[vb[i]]; }
       }
     }
+  }
+  fence_proxy_async();  // generic accesses to the tile are ordered before the next iteration's bulk copies
+  __syncthreads();      // the staged tile is reused by the next iteration
+  }  // tile loop
+
+  if (MODE == MODE_STATS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    Stat* st = a.stats + it.out;
+    for (int i = tid; i < 768; i += NT) {
+      unsigned int v = 0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) v += s_hist[w * 768 + i];
+      if (v) atomicAdd(&st->hist[0][0] + i, v);
+    }
+    if ((tid & 31) == 0 && lsum) atomicAdd(&st->luma_sum, (unsigned long long)lsum);
   }
 }
 
@@ -670,7 +680,7 @@ static int launch_pass(const PassArgs& base, const PassItem* d_items, int n, cud
   for (int done = 0; done < n; done += 65535) {
     PassArgs a = base;
     a.items = d_items + done;
-    dim3 grid(tiles, std::min(n - done, 65535));
+    dim3 grid((tiles + TILES_PER_CTA - 1) / TILES_PER_CTA, std::min(n - done, 65535));
     pass_kernel<MODE><<<grid, NT, 0, st>>>(a);
   }
   return check_launch("aug_u8 pass kernel");

@@ -414,7 +414,10 @@ __global__ void __launch_bounds__(IG_THREADS) wgrad_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int co0 = blockIdx.x * 128, ci0 = blockIdx.y * BN;
-  const int tap = blockIdx.z / a.ksplit, split = blockIdx.z % a.ksplit;
+  // taps of one pixel range are adjacent in launch order: the dY / X slices of that range stay in L2 while all
+  // R*S taps consume them (tap-major order re-read both tensors from HBM once per tap)
+  const int n_taps = a.taps.n;
+  const int tap = blockIdx.z % n_taps, split = blockIdx.z / n_taps;
   const int n_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
   const int my_tiles = split < n_tiles ? (n_tiles - split + a.ksplit - 1) / a.ksplit : 0;
   const int lg_tn = 6 - a.lg_tw - a.lg_th;

@@ -74,18 +74,9 @@ __device__ __forceinline__ void channel_reduce(int P, int C, float* out0, float*
   const int G = C >> 3;
   const int tx = threadIdx.x, ty = threadIdx.y;
   float a0[8] = {}, a1[8] = {};
-  if (tx < G) {
-    const long long step = (long long)gridDim.x * blockDim.y;
-    long long p = (long long)blockIdx.x * blockDim.y + ty;
-    float b0[8] = {}, b1[8] = {};          // second accumulator set: two independent load streams in flight
-    for (; p + step < P; p += 2 * step) {
+  if (tx < G)
+    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y)
       f((int)p, tx, a0, a1);
-      f((int)(p + step), tx, b0, b1);
-    }
-    if (p < P) f((int)p, tx, a0, a1);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a0[i] += b0[i]; a1[i] += b1[i]; }
-  }
   __shared__ float s0[2048], s1[2048];
   for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) { s0[i] = 0.f; s1[i] = 0.f; }
   __syncthreads();
@@ -103,7 +94,7 @@ __device__ __forceinline__ void channel_reduce(int P, int C, float* out0, float*
   }
 }
 
-__global__ void bn_stats_kernel(const bf16* x, int P, int C, int ld, float* sum, float* sumsq) {
+__global__ void __launch_bounds__(256, 4) bn_stats_kernel(const bf16* x, int P, int C, int ld, float* sum, float* sumsq) {
   channel_reduce<2>(P, C, sum, sumsq, [&](int p, int g, float* a0, float* a1) {
     const V8 v = ld8(x + (size_t)p * ld + g * 8);
 #pragma unroll
@@ -159,7 +150,7 @@ __global__ void bn_apply_kernel(const bf16* x, int ldx, const float* scale, cons
 }
 
 // g = dy * relu'(y) * dropout ; dbeta = sum g ; dgamma = sum g * xhat
-__global__ void bn_bwd_reduce_kernel(const bf16* dy, int lddy, const bf16* x, int ldx, const bf16* y, int ldy,
+__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const bf16* dy, int lddy, const bf16* x, int ldx, const bf16* y, int ldy,
                                      const float* mean, const float* invstd, const float* gamma,
                                      const float* beta, int P, int C, int flags, unsigned long long seed,
                                      float* dgamma, float* dbeta) {
@@ -393,6 +384,45 @@ __global__ void upsample_bwd_kernel(const bf16* dy, int N, int Ho, int Wo, int C
   }
 }
 
+// ---- nearest x2 up-sampling (smp Unet DecoderBlock: F.interpolate(scale_factor=2, mode="nearest")) ---------
+__global__ void nearest2x_fwd_kernel(const bf16* x, int N, int H, int W, int C, int ldx, bf16* y, int ldy) {
+  const int G = C >> 3;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int oy = blockIdx.y, n = blockIdx.z;
+  const bf16* xrow = x + ((size_t)n * H + (oy >> 1)) * W * ldx;
+  bf16* yrow = y + ((size_t)n * Ho + oy) * Wo * ldy;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Wo * G; e += gridDim.x * blockDim.x) {
+    const int ox = e / G, g = e - ox * G;
+    *reinterpret_cast<uint4*>(yrow + (size_t)ox * ldy + g * 8) =
+        *reinterpret_cast<const uint4*>(xrow + (size_t)(ox >> 1) * ldx + g * 8);
+  }
+}
+// dx[iy,ix] = sum of the 2x2 block of dy it was copied to
+__global__ void nearest2x_bwd_kernel(const bf16* dy, int N, int H, int W, int C, int lddy, bf16* dx, int lddx) {
+  const int G = C >> 3;
+  const int Wo = 2 * W;
+  const int iy = blockIdx.y, n = blockIdx.z;
+  const bf16* d0 = dy + ((size_t)n * 2 * H + 2 * iy) * Wo * lddy;
+  const bf16* d1 = d0 + (size_t)Wo * lddy;
+  bf16* xrow = dx + ((size_t)n * H + iy) * W * lddx;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < W * G; e += gridDim.x * blockDim.x) {
+    const int ix = e / G, g = e - ix * G;
+    const V8 a = ld8(d0 + (size_t)(2 * ix) * lddy + g * 8), b = ld8(d0 + (size_t)(2 * ix + 1) * lddy + g * 8);
+    const V8 c = ld8(d1 + (size_t)(2 * ix) * lddy + g * 8), d = ld8(d1 + (size_t)(2 * ix + 1) * lddy + g * 8);
+    V8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = (a.v[i] + b.v[i]) + (c.v[i] + d.v[i]);
+    st8(xrow + (size_t)ix * lddx + g * 8, o);
+  }
+}
+// channel-slice copy (skip connection into a concat buffer)
+__global__ void copy_kernel(const bf16* x, int ldx, bf16* y, int ldy, long long P, int C) {
+  const int G = C >> 3;
+  AADG_FOR_PIXEL_GROUPS(P, G, p, g) {
+    *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = *reinterpret_cast<const uint4*>(x + p * ldx + g * 8);
+  }
+}
+
 // ---- global average pool / broadcast --------------------------------------------------------------------
 // out[n][c] (fp32) = mean over pixels ; grid (N, ceil(G/32)), block (32 groups, 8 pixel lanes)
 __global__ void gap_kernel(const bf16* x, int HW, int C, int ld, float* out, float scale) {
@@ -436,7 +466,8 @@ __global__ void f32_to_bf16_kernel(const float* x, bf16* y, long long n, float s
 
 // ---- depthwise 3x3 (dilated, stride 1, "same" padding) ---------------------------------------------------
 // y[n,oy,ox,c] = sum_t w[t][c] * x[n, oy + (r-1)*dil*sign, ox + (s-1)*dil*sign, c]; sign = -1 gives the data gradient
-__global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const float* w, int dil, int sign,
+// generic (dilated) form: one output pixel x 8 channels per thread (filter taps come from L1)
+__global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const float* s_w, int dil, int sign,
                              bf16* y, int ldy) {
   const int G = C >> 3;
   const int oy = blockIdx.y, n = blockIdx.z;
@@ -456,7 +487,7 @@ __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
         const int ix = ox + (s2 - 1) * dil * sign;
         if (ix < 0 || ix >= W) continue;
         const V8 v = ld8(xn + ((size_t)iy * W + ix) * ldx + g * 8);
-        const V8 wv = ld8f(w + (size_t)(r * 3 + s2) * C + g * 8);
+        const V8 wv = ld8f(s_w + (r * 3 + s2) * C + g * 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wv.v[i], v.v[i], acc.v[i]);
       }
@@ -464,44 +495,90 @@ __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
     st8(yrow + (size_t)ox * ldy + g * 8, acc);
   }
 }
-// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]: one pass over dy, the nine shifted x reads hit L1/L2;
-// 72 register accumulators per thread, block reduction in dynamic shared memory [9][C]
-__global__ void dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const bf16* dy, int lddy,
-                                   int dil, float* dw) {
-  extern __shared__ float s_dw[];
+// dilation 1: four consecutive output pixels per thread share a 3 x 6 window (18 loads instead of 36)
+__global__ void dw3x3_d1_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const float* s_w, int sign,
+                                bf16* y, int ldy) {
   const int G = C >> 3;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const long long P = (long long)N * H * W;
-  float acc[9][8] = {};
-  if (tx < G)
-    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y) {
-      const int ox = (int)(p % W), oy = (int)((p / W) % H);
-      const long long nb = p - (long long)oy * W - ox;      // pixel index of (n, 0, 0)
-      const V8 d = ld8(dy + (size_t)p * lddy + tx * 8);
+  const int oy = blockIdx.y, n = blockIdx.z;
+  const int W4 = (W + 3) >> 2;
+  const bf16* xn = x + (size_t)n * H * W * ldx;
+  bf16* yrow = y + ((size_t)n * H + oy) * W * ldy;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < W4 * G; e += gridDim.x * blockDim.x) {
+    const int q = e / G, g = e - q * G;
+    const int ox0 = q * 4;
+    float acc[4][8] = {};
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int iy = oy + (r - 1) * dil;
-        if (iy < 0 || iy >= H) continue;
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy + (r - 1);      // forward geometry; the data gradient flips the filter instead
+      if (iy < 0 || iy >= H) continue;
+      V8 col[6];
 #pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) {
-          const int ix = ox + (s2 - 1) * dil;
-          if (ix < 0 || ix >= W) continue;
-          const V8 v = ld8(x + (size_t)(nb + (long long)iy * W + ix) * ldx + tx * 8);
+      for (int j = 0; j < 6; ++j) {
+        const int ix = ox0 - 1 + j;
+        if (ix >= 0 && ix < W) col[j] = ld8(xn + ((size_t)iy * W + ix) * ldx + g * 8);
+        else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[r * 3 + s2][i] = fmaf(d.v[i], v.v[i], acc[r * 3 + s2][i]);
+          for (int i = 0; i < 8; ++i) col[j].v[i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int tap = sign > 0 ? r * 3 + s2 : (2 - r) * 3 + (2 - s2);
+        const V8 wv = ld8f(s_w + tap * C + g * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const V8& v = col[k + s2];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(wv.v[i], v.v[i], acc[k][i]);
         }
       }
     }
-  for (int i = ty * blockDim.x + tx; i < 9 * C; i += blockDim.x * blockDim.y) s_dw[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ox0 + k < W) {
+        V8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = acc[k][i];
+        st8(yrow + (size_t)(ox0 + k) * ldy + g * 8, o);
+      }
+  }
+}
+// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]; blockIdx.y = filter row r (3 taps, 24 register accumulators),
+// the three launches' dy reads overlap in L2; block reduction in shared memory [3][C], then atomics
+__global__ void __launch_bounds__(256, 3) dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
+                                                             const bf16* dy, int lddy, int dil, float* dw) {
+  extern __shared__ float s_dw[];
+  const int G = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int r = blockIdx.y;
+  const long long P = (long long)N * H * W;
+  float acc[3][8] = {};
+  if (tx < G)
+    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y) {
+      const int ox = (int)(p % W), oy = (int)((p / W) % H);
+      const int iy = oy + (r - 1) * dil;
+      if (iy < 0 || iy >= H) continue;
+      const V8 d = ld8(dy + (size_t)p * lddy + tx * 8);
+      const bf16* xr = x + (size_t)(p + (long long)(iy - oy) * W) * ldx + tx * 8;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int ix = ox + (s2 - 1) * dil;
+        if (ix < 0 || ix >= W) continue;
+        const V8 v = ld8(xr + (long long)(ix - ox) * ldx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[s2][i] = fmaf(d.v[i], v.v[i], acc[s2][i]);
+      }
+    }
+  for (int i = ty * blockDim.x + tx; i < 3 * C; i += blockDim.x * blockDim.y) s_dw[i] = 0.f;
   __syncthreads();
   if (tx < G) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+    for (int t = 0; t < 3; ++t)
 #pragma unroll
       for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * C + tx * 8 + i], acc[t][i]);
   }
   __syncthreads();
-  for (int i = ty * blockDim.x + tx; i < 9 * C; i += blockDim.x * blockDim.y) atomicAdd(&dw[i], s_dw[i]);
+  for (int i = ty * blockDim.x + tx; i < 3 * C; i += blockDim.x * blockDim.y) atomicAdd(&dw[(size_t)r * 3 * C + i], s_dw[i]);
 }
 
 // ---- stem im2col: fp32 NCHW [-1,1] image -> bf16 [N*Ho*Wo][KP] patches, k = (r*S + s)*3 + c --------------------
@@ -519,21 +596,25 @@ __global__ void im2col_stem_kernel(const float* img, int N, int H, int W, int R,
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = img[(((size_t)n * 3 + c) * H + iy) * W + ix];
     s_rows[e] = __float2bfloat16_rn(v);
   }
-  __syncthreads();
+  // patch index k -> offset inside the staged rows (computed once per CTA: no divisions in the copy loop)
+  __shared__ short koff[512];
   const int K = R * S * 3, KG = KP / 8;
+  for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+    int off = -1;
+    if (k < K) { const int c = k % 3, rs = k / 3, s2 = rs % S, r = rs / S; off = (r * 3 + c) * WP + s2; }
+    koff[k] = (short)off;
+  }
+  __syncthreads();
   bf16* orow = col + ((size_t)n * Ho + oy) * Wo * KP;
+  const bf16 zero = __float2bfloat16_rn(0.f);
   for (int e = threadIdx.x; e < Wo * KG; e += blockDim.x) {
-    const int kg = e % KG, ox = e / KG;
+    const int ox = e / KG, kg = e - ox * KG;
+    const int xs = ox * stride;
     __align__(16) bf16 o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = kg * 8 + i;
-      bf16 v = __float2bfloat16_rn(0.f);
-      if (k < K) {
-        const int c = k % 3, rs = k / 3, s2 = rs % S, r = rs / S;
-        v = s_rows[(r * 3 + c) * WP + ox * stride + s2];
-      }
-      o[i] = v;
+      const int off = koff[kg * 8 + i];
+      o[i] = off >= 0 ? s_rows[off + xs] : zero;
     }
     *reinterpret_cast<uint4*>(orow + (size_t)ox * KP + kg * 8) = *reinterpret_cast<const uint4*>(o);
   }
@@ -661,6 +742,27 @@ int aadg_maxpool3x3s2_bwd(const void* dy, const void* argmax, int n, int h, int 
   return check_launch("maxpool bwd");
 }
 
+/* nearest x2 up-sampling: y bf16 [n,2h,2w,ldy] (channel slice) <- x bf16 [n,h,w,ldx]; and its transpose */
+int aadg_upsample_nearest2x_fwd(const void* x, int n, int h, int w, int c, int ldx, void* y, int ldy, void* stream) {
+  NN_REQ_C(c);
+  AADG_REQUIRE(2 * h <= 65535 && n <= 65535, "tensor too large for the grid");
+  dim3 grid(std::max(1, std::min((2 * w * (c / 8) + 255) / 256, 64)), 2 * h, n);
+  nearest2x_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, (bf16*)y, ldy);
+  return check_launch("nearest2x fwd");
+}
+int aadg_upsample_nearest2x_bwd(const void* dy, int n, int h, int w, int c, int lddy, void* dx, int lddx, void* stream) {
+  NN_REQ_C(c);
+  AADG_REQUIRE(h <= 65535 && n <= 65535, "tensor too large for the grid");
+  dim3 grid(std::max(1, std::min((w * (c / 8) + 255) / 256, 64)), h, n);
+  nearest2x_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, n, h, w, c, lddy, (bf16*)dx, lddx);
+  return check_launch("nearest2x bwd");
+}
+int aadg_copy_bf16(const void* x, int ldx, void* y, int ldy, long long pixels, int c, void* stream) {
+  NN_REQ_C(c);
+  copy_kernel<<<grid_for(pixels * (c / 8)), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, pixels, c);
+  return check_launch("copy");
+}
+
 int aadg_upsample_bilinear_fwd(const void* x, int n, int h, int w, int c, int ldx, void* y, int ho, int wo, int ldy,
                                void* stream) {
   NN_REQ_C(c);
@@ -699,9 +801,16 @@ int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const flo
                    int ldy, void* stream) {
   NN_REQ_C(c);
   AADG_REQUIRE(h <= 65535 && n <= 65535, "image too tall / batch too large for the depthwise grid");
-  dim3 grid(std::max(1, std::min((w * (c / 8) + 255) / 256, 64)), h, n);
-  dw3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, wgt, dil, direction ? -1 : 1,
-                                                       (bf16*)y, ldy);
+  const size_t smem = 0;
+  if (dil == 1) {
+    dim3 grid(std::max(1, std::min((((w + 3) / 4) * (c / 8) + 127) / 128, 64)), h, n);
+    dw3x3_d1_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, wgt, direction ? -1 : 1,
+                                                              (bf16*)y, ldy);
+  } else {
+    dim3 grid(std::max(1, std::min((w * (c / 8) + 255) / 256, 64)), h, n);
+    dw3x3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, wgt, dil,
+                                                           direction ? -1 : 1, (bf16*)y, ldy);
+  }
   return check_launch("dwconv3x3");
 }
 int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil, float* dw,
@@ -710,22 +819,19 @@ int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, con
   const long long pixels = (long long)n * h * w;
   AADG_REQUIRE(pixels < (1ll << 31), "too many pixels");
   const dim3 blk = reduce_block(c);
-  const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 2);
-  const size_t smem = (size_t)9 * c * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    AADG_CUDA_TRY(cudaFuncSetAttribute(dw3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 2048 * 4));
-    attr_set = true;
-  }
-  dw3x3_wgrad_kernel<<<std::max(blocks, 1), blk, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx,
-                                                                              (const bf16*)dy, lddy, dil, dw);
+  const int blocks = (int)std::min<long long>((pixels + blk.y * 16 - 1) / (blk.y * 16), 148 * 6);
+  const size_t smem = (size_t)3 * c * sizeof(float);
+  dim3 grid(std::max(blocks, 1), 3);
+  dw3x3_wgrad_kernel<<<grid, blk, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, lddy,
+                                                               dil, dw);
   return check_launch("dwconv3x3 wgrad");
 }
 
 /* img fp32 [n,3,h,w] -> col bf16 [n*ho*wo][kp], k = (r*S+s)*3 + c, zero padded to kp (multiple of 8) */
 int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int kp, void* col,
                      void* stream) {
-  AADG_REQUIRE(kp % 8 == 0 && kp >= r * s * 3, "kp must be a multiple of 8 and >= R*S*3");
+  AADG_REQUIRE(kp % 8 == 0 && kp >= r * s * 3 && kp <= 512, "kp must be a multiple of 8, >= R*S*3 and <= 512");
+  AADG_REQUIRE((size_t)r * 3 * (w + 2 * pad) < 32768, "image too wide for 16-bit patch offsets");
   const int ho = (h + 2 * pad - r) / stride + 1, wo = (w + 2 * pad - s) / stride + 1;
   const size_t smem = (size_t)r * 3 * (w + 2 * pad) * sizeof(bf16);
   AADG_REQUIRE(smem <= 200 * 1024, "image too wide for the staged im2col (%zu bytes of shared memory)", smem);

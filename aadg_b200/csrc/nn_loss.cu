@@ -193,6 +193,104 @@ __global__ void head_bwd_kernel(const float* dz, const bf16* a, long long P, int
   }
 }
 
+// ---- 3x3 head (smp Unet SegmentationHead: Conv2d(16, classes, 3, padding=1)) --------------------------------
+// z[n,y,x,k] = b[k] + sum_{r,s,c} w[k][r*3+s][c] * a[n,y+r-1,x+s-1,c] ; C <= 64, one thread per pixel
+__global__ void head3x3_fwd_kernel(const bf16* a, int N, int H, int W, int C, int lda, const float* w, const float* b,
+                                   int K, float* z) {
+  extern __shared__ float sw[];          // [K][9][C]
+  for (int i = threadIdx.x; i < K * 9 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long P = (long long)N * H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    float acc[MAXK] = {};
+    for (int r = 0; r < 3; ++r) {
+      const int iy = y + r - 1;
+      if (iy < 0 || iy >= H) continue;
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int ix = x + s2 - 1;
+        if (ix < 0 || ix >= W) continue;
+        const bf16* ap = a + (p + (long long)(r - 1) * W + (s2 - 1)) * lda;
+        for (int c = 0; c < C; c += 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(ap + c);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h2[i]);
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k)
+              if (k < K) {
+                const float* wk = sw + (k * 9 + r * 3 + s2) * C + c + 2 * i;
+                acc[k] = fmaf(f.x, wk[0], fmaf(f.y, wk[1], acc[k]));
+              }
+          }
+        }
+      }
+    }
+    for (int k = 0; k < K; ++k) z[p * K + k] = acc[k] + b[k];
+  }
+}
+// da[p][c] = sum_{r,s,k} dz[p - (r-1,s-1)][k] * w[k][r*3+s][c]
+__global__ void head3x3_dgrad_kernel(const float* dz, int N, int H, int W, int C, const float* w, int K, bf16* da,
+                                     int ldda) {
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < K * 9 * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long P = (long long)N * H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    float acc[64];
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int r = 0; r < 3; ++r) {
+      const int oy = y - (r - 1);
+      if (oy < 0 || oy >= H) continue;
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int ox = x - (s2 - 1);
+        if (ox < 0 || ox >= W) continue;
+        const float* dp = dz + (p - (long long)(r - 1) * W - (s2 - 1)) * K;
+        for (int k = 0; k < K; ++k) {
+          const float d = dp[k];
+          const float* wk = sw + (k * 9 + r * 3 + s2) * C;
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(d, wk[c], acc[c]);
+        }
+      }
+    }
+    for (int c = 0; c < C; c += 2)
+      *reinterpret_cast<__nv_bfloat162*>(da + p * ldda + c) = __floats2bfloat162_rn(acc[c], acc[c + 1]);
+  }
+}
+// dw[k][tap][c] += sum_p dz[p][k] * a[p + tap][c] ; db[k] += sum_p dz[p][k] ; grid (blocks, 9 taps)
+__global__ void head3x3_wgrad_kernel(const float* dz, const bf16* a, int N, int H, int W, int C, int lda, int K,
+                                     float* dw, float* db) {
+  const int tap = blockIdx.y, r = tap / 3, s2 = tap % 3;
+  const long long P = (long long)N * H * W;
+  float acc[MAXK][64];
+  float accb[MAXK] = {};
+  for (int k = 0; k < MAXK; ++k) for (int c = 0; c < C; ++c) acc[k][c] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    float d[MAXK];
+    for (int k = 0; k < K; ++k) { d[k] = dz[p * K + k]; if (tap == 4) accb[k] += d[k]; }
+    const int iy = y + r - 1, ix = x + s2 - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const bf16* ap = a + (p + (long long)(r - 1) * W + (s2 - 1)) * lda;
+    for (int c = 0; c < C; c += 2) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ap + c));
+      for (int k = 0; k < K; ++k) { acc[k][c] = fmaf(d[k], f.x, acc[k][c]); acc[k][c + 1] = fmaf(d[k], f.y, acc[k][c + 1]); }
+    }
+  }
+  for (int k = 0; k < K; ++k) {
+    for (int c = 0; c < C; ++c) {
+      const float t = warp_sum(acc[k][c]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&dw[(k * 9 + tap) * C + c], t);
+    }
+    if (tap == 4) {
+      const float t = warp_sum(accb[k]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&db[k], t);
+    }
+  }
+}
+
 }  // namespace nnl
 }  // namespace aadg
 
@@ -243,6 +341,28 @@ int aadg_seg_head_bwd(const float* dz, const void* a, long long pixels, int c, i
   head_bwd_kernel<<<std::max(blocks, 1), blk, 0, (cudaStream_t)stream>>>(dz, (const bf16*)a, pixels, c, lda, w, classes,
                                                                         (bf16*)da, ldda, dw, db);
   return check_launch("seg_head_bwd");
+}
+
+/* 3x3 segmentation head (padding 1) at full resolution: z fp32 [n,h,w,classes]; w fp32 [classes][9][c], c <= 64 */
+int aadg_seg_head3x3_fwd(const void* a, int n, int h, int w, int c, int lda, const float* wgt, const float* bias,
+                         int classes, float* z, void* stream) {
+  AADG_REQUIRE(classes >= 1 && classes <= MAXK && c % 8 == 0 && c > 0 && c <= 64, "classes <= %d, channels <= 64", MAXK);
+  const long long P = (long long)n * h * w;
+  const int blocks = (int)std::min<long long>((P + 127) / 128, 148 * 16);
+  head3x3_fwd_kernel<<<blocks, 128, classes * 9 * c * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)a, n, h, w, c, lda, wgt, bias, classes, z);
+  return check_launch("head3x3 fwd");
+}
+int aadg_seg_head3x3_bwd(const float* dz, const void* a, int n, int h, int w, int c, int lda, const float* wgt,
+                         int classes, void* da, int ldda, float* dw, float* db, void* stream) {
+  AADG_REQUIRE(classes >= 1 && classes <= MAXK && c % 8 == 0 && c > 0 && c <= 64, "classes <= %d, channels <= 64", MAXK);
+  const long long P = (long long)n * h * w;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)std::min<long long>((P + 127) / 128, 148 * 16);
+  head3x3_dgrad_kernel<<<blocks, 128, classes * 9 * c * sizeof(float), st>>>(dz, n, h, w, c, wgt, classes, (bf16*)da, ldda);
+  dim3 grid((int)std::min<long long>((P + 127) / 128, 148 * 2), 9);
+  head3x3_wgrad_kernel<<<grid, 128, 0, st>>>(dz, (const bf16*)a, n, h, w, c, lda, classes, dw, db);
+  return check_launch("head3x3 bwd");
 }
 
 }  // extern "C"

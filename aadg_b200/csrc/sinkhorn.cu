@@ -570,10 +570,27 @@ size_t aadg_sinkhorn_large_workspace_bytes(int n, int m, int dim) {
 /* One divergence on big clouds.  Synchronises `stream` once (the diameter, like the reference's
  * .item()) unless diameter > 0 is supplied.  n_iterations_out (HOST, optional) receives the number
  * of epsilon steps (soft-min sweeps = n + 2). */
+static int sinkhorn_large_impl(const float* x, int n, const float* y, int m, int dim, float diameter, float* out,
+                               int* n_iterations_out, void* workspace, size_t workspace_bytes, void* stream,
+                               int cost_only);
+
 int aadg_sinkhorn_large(const float* x, int n, const float* y, int m, int dim, float diameter, float* out,
                         int* n_iterations_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return sinkhorn_large_impl(x, n, y, m, dim, diameter, out, n_iterations_out, workspace, workspace_bytes, stream, 0);
+}
+
+/* Only the set-up part of aadg_sinkhorn_large (norms, diameter, the four cost matrices): lets a benchmark
+ * separate the one-off cost build from the epsilon iterations. */
+int aadg_sinkhorn_large_setup(const float* x, int n, const float* y, int m, int dim, float diameter,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return sinkhorn_large_impl(x, n, y, m, dim, diameter, nullptr, nullptr, workspace, workspace_bytes, stream, 1);
+}
+
+static int sinkhorn_large_impl(const float* x, int n, const float* y, int m, int dim, float diameter, float* out,
+                               int* n_iterations_out, void* workspace, size_t workspace_bytes, void* stream,
+                               int cost_only) {
   AADG_REQUIRE(n > 0 && m > 0 && dim > 0 && dim <= 4096, "bad sizes n=%d m=%d dim=%d", n, m, dim);
-  AADG_REQUIRE(x && y && out, "null pointer");
+  AADG_REQUIRE(x && y && (out || cost_only), "null pointer");
   const LargeLayout L = large_layout(n, m);
   if (!workspace || workspace_bytes < L.total) {
     set_error("workspace too small: need %zu bytes, got %zu", L.total, workspace_bytes);
@@ -622,7 +639,7 @@ int aadg_sinkhorn_large(const float* x, int n, const float* y, int m, int dim, f
     cost_kernel<<<g3, 256, 0, st>>>(x, nx, n, y, ny, m, dim, cxy, L.ldm, cyx, L.ldn);
   }
   int rc = check_launch("sinkhorn cost kernels");
-  if (rc) return rc;
+  if (rc || cost_only) return rc;
   const float alog = logf(1.0f / (float)n), blog = logf(1.0f / (float)m);
   fill_kernel<<<(2 * n + 255) / 256, 256, 0, st>>>(hax, 2 * n, alog * LOG2E);
   fill_kernel<<<(2 * m + 255) / 256, 256, 0, st>>>(hby, 2 * m, blog * LOG2E);

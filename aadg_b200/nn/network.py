@@ -299,7 +299,7 @@ class ResNetEncoder:
     """torchvision ResNet without the classifier; stage 5 dilated (stride 1, dilation 2) for output stride 16
     (smp `make_dilated(stage_list=[5], dilation_list=[2])`)."""
 
-    def __init__(self, store, name, in_channels=3):
+    def __init__(self, store, name, in_channels=3, dilated=True):
         assert in_channels == 3
         block, layers = RESNETS[name]
 
@@ -314,12 +314,12 @@ class ResNetEncoder:
         for li, (planes, n) in enumerate(zip([64, 128, 256, 512], layers)):
             stride = 1 if li == 0 else 2
             dil = 1
-            if li == 3:
+            if li == 3 and dilated:
                 stride, dil = 1, 2
             stage = []
             for b in range(n):
                 s = stride if b == 0 else 1
-                ds = b == 0 and (stride != 1 or li == 3 or cin != planes * block.expansion)
+                ds = b == 0 and (li > 0 or cin != planes * block.expansion)
                 stage.append(block(store, "encoder.layer%d.%d" % (li + 1, b), cin, planes, s, dil, ds))
                 cin = planes * block.expansion
             self.blocks.append(stage)
@@ -340,17 +340,21 @@ class ResNetEncoder:
         self.ctx = (col, pre, f1, arg) if training else None
         return feats            # strides 2, 4, 8, 16, 16
 
-    def backward(self, d_last, d_stride4):
-        """d_last: gradient of the last feature map; d_stride4: gradient of the stride-4 map (decoder skip)."""
+    def backward(self, d_last, d_stride4=None, d_skips=None):
+        """d_last: gradient of the last feature map; d_stride4: gradient of the stride-4 map (DeepLab decoder
+        skip); d_skips: gradients of feats[0..3] as returned by forward (UNet skips, None entries allowed)."""
         col, pre, f1, arg = self.ctx
         self.ctx = None
+        skips = list(d_skips) if d_skips is not None else [None, d_stride4, None, None]
         d = d_last
         for li in (3, 2, 1, 0):
-            if li == 0 and d_stride4 is not None:
-                K.add_(d, d_stride4)
+            if li < 3 and skips[li + 1] is not None:
+                K.add_(d, skips[li + 1])          # extra gradient of stage li's output (= feats[li + 1])
             for blk in reversed(self.blocks[li]):
                 d = blk.backward(d)
         d = K.maxpool_bwd(d, arg, f1.shape)
+        if skips[0] is not None:
+            K.add_(d, skips[0])
         dpre = torch.empty_like(pre)
         self.stem_bn.backward(d, pre, f1, dpre)
         C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad)
@@ -431,23 +435,77 @@ class DeepLabV3PlusDecoder:
         return dx, d_high
 
 
+class UnetDecoder:
+    """smp 0.2.0 UnetDecoder(decoder_channels=(256,128,64,32,16), use_batchnorm=True, center=False): five
+    blocks of [nearest x2 up-sampling, concat skip, Conv3x3-BN-ReLU, Conv3x3-BN-ReLU]."""
+
+    def __init__(self, store, enc_channels, decoder_channels=(256, 128, 64, 32, 16)):
+        enc = list(enc_channels[1:])[::-1]                   # [f5, f4, f3, f2, f1] channels
+        in_ch = [enc[0]] + list(decoder_channels[:-1])
+        skip_ch = enc[1:] + [0]
+        self.blocks = []
+        for i, (ic, sc, oc) in enumerate(zip(in_ch, skip_ch, decoder_channels)):
+            n = "decoder.blocks.%d." % i
+            c1 = ConvBN(store, n + "conv1.0", n + "conv1.1", ic + sc, oc, 3, 1, 1, 1, init=kaiming_uniform_default)
+            c2 = ConvBN(store, n + "conv2.0", n + "conv2.1", oc, oc, 3, 1, 1, 1, init=kaiming_uniform_default)
+            self.blocks.append((c1, c2, ic, sc))
+        self.out_channels = decoder_channels[-1]
+
+    def forward(self, feats, training):
+        """feats = [f1, f2, f3, f4, f5] (strides 2..32)"""
+        x = feats[-1]
+        skips = feats[:-1][::-1] + [None]
+        for (c1, c2, ic, sc), skip in zip(self.blocks, skips):
+            n, h, w, _ = x.shape
+            cat = torch.empty((n, 2 * h, 2 * w, ic + sc), dtype=BF16, device=x.device)
+            K.nearest2x_fwd(x, cat[..., :ic])
+            if skip is not None:
+                K.copy_(skip, cat[..., ic:])
+            x = c2.forward(c1.forward(cat, training), training)
+        return x
+
+    def backward(self, dy):
+        """returns (gradient of f5, [gradients of f1..f4])"""
+        d = dy
+        d_skips = []
+        for (c1, c2, ic, sc) in reversed(self.blocks):
+            dcat = c1.backward(c2.backward(d))
+            n, h2, w2, _ = dcat.shape
+            if sc:
+                d_skips.append(dcat[..., ic:])
+            d = torch.empty((n, h2 // 2, w2 // 2, ic), dtype=BF16, device=dcat.device)
+            K.nearest2x_bwd(dcat[..., :ic], d)
+        # d_skips was collected for f1, f2, f3, f4 in that order (blocks reversed: last block has no skip)
+        return d, d_skips
+
+
 class SegNet:
     """encoder + decoder + segmentation head (Conv2d(256, classes, 1) -> UpsamplingBilinear2d(4)) and the
     patched classification head (AdaptiveAvgPool2d(1) + flatten of the last encoder map, models/heads.py:14-25)."""
 
-    def __init__(self, encoder_name="resnet50", classes=2, device="cuda", seed=0):
+    def __init__(self, encoder_name="resnet50", classes=2, device="cuda", seed=0, arch="deeplabv3plus"):
         if not torch.cuda.is_available():
             raise RuntimeError("aadg_b200.nn needs a CUDA device: there is no CPU path")
         self.device = torch.device(device)
         gen_state = torch.random.get_rng_state()
         torch.manual_seed(seed)
         self.store = ParamStore(self.device)
-        self.encoder = ResNetEncoder(self.store, encoder_name)
-        self.decoder = DeepLabV3PlusDecoder(self.store, self.encoder.out_channels)
+        self.arch = arch
         self.classes = classes
-        self.head_w = self.store.add("segmentation_head.0.weight", (classes, 256), "f32",
-                                     lambda s: kaiming_uniform_default((classes, 256, 1, 1)).reshape(classes, 256))
-        bound = 1.0 / math.sqrt(256)
+        if arch == "unet":
+            self.encoder = ResNetEncoder(self.store, encoder_name, dilated=False)
+            self.decoder = UnetDecoder(self.store, self.encoder.out_channels)
+            hc = self.decoder.out_channels
+            self.head_w = self.store.add(
+                "segmentation_head.0.weight", (classes, 9, hc), "f32",
+                lambda s: kaiming_uniform_default((classes, hc, 3, 3)).permute(0, 2, 3, 1).reshape(classes, 9, hc))
+            bound = 1.0 / math.sqrt(hc * 9)
+        else:
+            self.encoder = ResNetEncoder(self.store, encoder_name)
+            self.decoder = DeepLabV3PlusDecoder(self.store, self.encoder.out_channels)
+            self.head_w = self.store.add("segmentation_head.0.weight", (classes, 256), "f32",
+                                         lambda s: kaiming_uniform_default((classes, 256, 1, 1)).reshape(classes, 256))
+            bound = 1.0 / math.sqrt(256)
         self.head_b = self.store.add("segmentation_head.0.bias", (classes,), "f32",
                                      lambda s: (torch.rand(s) * 2 - 1) * bound)
         self.store.finalize()
@@ -501,7 +559,8 @@ class SegNet:
                 k = int(round(math.sqrt(p.shape[0])))
                 d = from_taps(d, k, k)
             elif p.name.startswith("segmentation_head.0.weight"):
-                d = d.reshape(self.classes, 256, 1, 1)
+                d = d.reshape(self.classes, 256, 1, 1) if self.arch != "unet" else \
+                    d.reshape(self.classes, 3, 3, -1).permute(0, 3, 1, 2).contiguous()
             elif len(p.shape) == 2 and p.shape[0] == 9:
                 d = d.t().reshape(p.shape[1], 1, 3, 3).contiguous()
             sd[p.name] = d
@@ -526,7 +585,8 @@ class SegNet:
             elif p.kind in ("conv", "conv_nt"):
                 w = to_taps(w)
             elif name == "segmentation_head.0.weight":
-                w = w.reshape(self.classes, 256)
+                w = w.reshape(self.classes, 256) if self.arch != "unet" else \
+                    w.permute(0, 2, 3, 1).reshape(self.classes, 9, -1)
             elif len(p.shape) == 2 and p.shape[0] == 9:
                 w = w.reshape(p.shape[1], 9).t().contiguous()
             p.data.copy_(w.reshape(p.shape))
@@ -544,14 +604,22 @@ class SegNet:
         feats = self.encoder.forward(x.contiguous(), self.training)
         last = feats[-1]
         pooled = K.global_sum(last, 1.0 / (last.shape[1] * last.shape[2]))
-        seed = (self.dropout_seed + self.steps) if (self.training and self.dropout_enabled) else None
-        dec = self.decoder.forward(feats, self.training, seed)
+        if self.arch == "unet":
+            dec = self.decoder.forward(feats, self.training)
+        else:
+            seed = (self.dropout_seed + self.steps) if (self.training and self.dropout_enabled) else None
+            dec = self.decoder.forward(feats, self.training, seed)
         return dec, pooled
+
+    def _head(self, dec):
+        if self.arch == "unet":
+            return K.seg_head3x3_fwd(dec, self.head_w.data, self.head_b.data)
+        return K.seg_head_fwd(dec, self.head_w.data, self.head_b.data)
 
     def __call__(self, x):
         """smp call shape: (logits float32 [N,classes,H,W], pooled feature float32 [N,C_enc])."""
         dec, pooled = self.features(x)
-        z = K.seg_head_fwd(dec, self.head_w.data, self.head_b.data)
+        z = self._head(dec)
         n, _, hh, ww = x.shape
         logits = torch.empty((n, self.classes, hh, ww), dtype=torch.float32, device=x.device)
         dummy_t = torch.zeros_like(logits)
@@ -569,7 +637,7 @@ class SegNet:
         assert self.training
         n, _, hh, ww = x.shape
         dec, pooled = self.features(x)
-        z = K.seg_head_fwd(dec, self.head_w.data, self.head_b.data)
+        z = self._head(dec)
         loss_sum = torch.zeros(1, dtype=torch.float64, device=x.device)
         counts = torch.zeros((n, self.classes, 3), dtype=torch.int32, device=x.device)
         logits = torch.empty((n, self.classes, hh, ww), dtype=torch.float32, device=x.device) if want_logits else None
@@ -577,9 +645,14 @@ class SegNet:
         numel = float(n * self.classes * hh * ww)
         dz = K.seg_loss_bwd(z, target, 1.0 / numel)
         ddec = torch.empty(dec.shape, dtype=BF16, device=x.device)
-        K.seg_head_bwd(dz, dec, self.head_w.data, ddec, self.head_w.grad, self.head_b.grad)
-        d_last, d_high = self.decoder.backward(ddec)
-        self.encoder.backward(d_last, d_high)
+        if self.arch == "unet":
+            K.seg_head3x3_bwd(dz, dec, self.head_w.data, ddec, self.head_w.grad, self.head_b.grad)
+            d_last, d_skips = self.decoder.backward(ddec)
+            self.encoder.backward(d_last, d_skips=d_skips)
+        else:
+            K.seg_head_bwd(dz, dec, self.head_w.data, ddec, self.head_w.grad, self.head_b.grad)
+            d_last, d_high = self.decoder.backward(ddec)
+            self.encoder.backward(d_last, d_high)
         self.steps += 1
         return dict(loss=(loss_sum / numel).float(), counts=counts, pooled=pooled, logits=logits)
 
@@ -608,3 +681,17 @@ def DeepLabV3Plus(encoder_name="resnet50", encoder_depth=5, encoder_weights=None
     if aux_params is not None and aux_params.get("pooling", "avg") != "avg":
         raise NotImplementedError("aux head: average pooling only (models/heads.py)")
     return SegNet(encoder_name, classes, device, seed)
+
+
+def Unet(encoder_name="resnet34", encoder_depth=5, encoder_weights=None, decoder_use_batchnorm=True,
+         decoder_channels=(256, 128, 64, 32, 16), decoder_attention_type=None, in_channels=3, classes=1,
+         activation=None, aux_params=None, device="cuda", seed=0):
+    """smp.Unet constructor shape (the north star's UNet / RVS configuration)."""
+    if encoder_name not in RESNETS:
+        raise NotImplementedError("encoder %r: resnet18/34/50 are implemented" % encoder_name)
+    if encoder_weights not in (None, "none"):
+        raise NotImplementedError("pretrained encoder weights cannot be downloaded here; use load_state_dict()")
+    if (encoder_depth, decoder_use_batchnorm, tuple(decoder_channels), decoder_attention_type, in_channels,
+            activation) != (5, True, (256, 128, 64, 32, 16), None, 3, None):
+        raise NotImplementedError("only smp's default Unet configuration is implemented")
+    return SegNet(encoder_name, classes, device, seed, arch="unet")

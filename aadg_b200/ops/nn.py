@@ -150,3 +150,30 @@ def seg_loss_bwd(z, target, grad_scale):
 def seg_head_bwd(dz, a, w, da, dw, db):
     n, h, wd, c = a.shape
     _call("aadg_seg_head_bwd", p(dz), p(a), n * h * wd, c, _ld(a), p(w), w.shape[0], p(da), _ld(da), p(dw), p(db))
+
+
+def nearest2x_fwd(x, y):
+    n, h, w, c = x.shape
+    _call("aadg_upsample_nearest2x_fwd", p(x), n, h, w, c, _ld(x), p(y), _ld(y))
+
+
+def nearest2x_bwd(dy, dx):
+    n, h, w, c = dx.shape
+    _call("aadg_upsample_nearest2x_bwd", p(dy), n, h, w, c, _ld(dy), p(dx), _ld(dx))
+
+
+def copy_(x, y):
+    _call("aadg_copy_bf16", p(x), _ld(x), p(y), _ld(y), _pix(x), x.shape[-1])
+
+
+def seg_head3x3_fwd(a, w, b):
+    n, h, wd, c = a.shape
+    k = w.shape[0]
+    z = torch.empty((n, h, wd, k), dtype=torch.float32, device=a.device)
+    _call("aadg_seg_head3x3_fwd", p(a), n, h, wd, c, _ld(a), p(w), p(b), k, p(z))
+    return z
+
+
+def seg_head3x3_bwd(dz, a, w, da, dw, db):
+    n, h, wd, c = a.shape
+    _call("aadg_seg_head3x3_bwd", p(dz), p(a), n, h, wd, c, _ld(a), p(w), w.shape[0], p(da), _ld(da), p(dw), p(db))

@@ -53,6 +53,17 @@ def divergence_large(x, y, diameter=None):
     return out[0], int(nit[0])
 
 
+def large_setup_only(x, y, diameter=None):
+    """benchmark helper: norms + diameter + cost matrices of divergence_large, nothing else."""
+    x, y = _check(x), _check(y)
+    L = _lib.lib()
+    n, m, d = x.shape[0], y.shape[0], x.shape[1]
+    ws = _lib.workspace(L.aadg_sinkhorn_large_workspace_bytes(n, m, d), x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.aadg_sinkhorn_large_setup(_lib.ptr(x), n, _lib.ptr(y), m, d, float(diameter) if diameter else 0.0,
+                                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+
+
 def divergence(x, y, diameter=None):
     x, y = _check(x), _check(y)
     if max(x.shape[0], y.shape[0]) <= small_max_points() and diameter is None:

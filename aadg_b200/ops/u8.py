@@ -67,6 +67,38 @@ def policy_normalize(src_images, src_masks, rows, dataset="optic", want_images=T
     return out_images, out_labels
 
 
+def scale_crop_normalize(images, masks, rows, crop, dataset="optic", image_by_row=True, want_labels=True):
+    """DGRandomScaleCrop + Normalize_dg + ToTensor for every row (data/transform.py:97-236): images uint8
+    [n,H,W,3] (post-policy, one per row) or the sources (image_by_row=False); masks = ORIGINAL masks [S,H,W].
+    Returns (float32 [n,3,crop,crop], float32 [n,C,crop,crop] or None)."""
+    images, masks, rows = _prep(images, masks, rows) if masks is None or masks.shape[0] == images.shape[0] \
+        else (images.contiguous(), masks.contiguous(), np.ascontiguousarray(rows, dtype=ROW_DTYPE))
+    _, h, w, _ = images.shape
+    n = len(rows)
+    dev = images.device
+    ds = DATASETS[dataset]
+    c = 2 if ds == 0 else 1
+    n_src = masks.shape[0] if masks is not None else images.shape[0]
+    out_i = torch.empty((n, 3, crop, crop), dtype=torch.float32, device=dev)
+    out_l = torch.empty((n, c, crop, crop), dtype=torch.float32, device=dev) if (want_labels and masks is not None) else None
+    mw = int(max([w] + [int(r["scale_w"]) for r in rows if r["do_scale"]]))
+    mh = int(max([h] + [int(r["scale_h"]) for r in rows if r["do_scale"]]))
+    L = _lib.lib()
+    ws = _lib.workspace(L.aadg_u8_scale_crop_workspace_bytes(max(n, 1), mw, mh), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.aadg_u8_scale_crop_normalize(_lib.ptr(images), int(image_by_row), _lib.ptr(masks), _lib.ptr(rows), n,
+                                                  n_src, h, w, crop, crop, ds, _lib.ptr(out_i), _lib.ptr(out_l),
+                                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    return out_i, out_l
+
+
+def policy_scale_crop_normalize(src_images, src_masks, rows, crop, dataset="optic"):
+    """The reference's whole train transform for the augmented copies: DGMultiPolicy -> DGRandomScaleCrop ->
+    Normalize_dg -> ToTensor -> collate (data/policy.py:51-61, data/transform.py:97-236,323-340)."""
+    post = apply_policy(src_images, src_masks, rows)
+    return scale_crop_normalize(post, src_masks, rows, crop, dataset, image_by_row=True)
+
+
 def apply_dg_multipolicy(policy, sample):
     """DGMultiPolicy.__call__ on a batch sample (reference data/policy.py:51-61): adds
     'aug_images' uint8 [S*M,H,W,3] and 'aug_labels' uint8 [S*M,H,W], row index s*M + j."""

@@ -91,6 +91,17 @@ int aadg_u8_policy_normalize(const uint8_t* src_images, const uint8_t* src_masks
                              int width, int dataset, float* out_images, float* out_labels,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* DGRandomScaleCrop + Normalize_dg + ToTensor (data/transform.py:97-236), bit-exact with Pillow's BILINEAR /
+ * NEAREST resize, ImageOps.expand zero padding and crop, driven by the row's do_scale, scale_w, scale_h, pad,
+ * crop_x, crop_y.  images uint8 [*,H,W,3]: image r is images[r] if image_by_row else images[rows[r].src];
+ * masks uint8 [n_src,H,W]: the ORIGINAL masks, indexed rows[r].src (data/transform.py:127-131), may be NULL;
+ * out_images float32 [n_rows,3,crop_h,crop_w]; out_labels float32 [n_rows,C,crop_h,crop_w]; either may be NULL. */
+size_t aadg_u8_scale_crop_workspace_bytes(int n_rows, int max_scale_w, int max_scale_h);
+int aadg_u8_scale_crop_normalize(const uint8_t* images, int image_by_row, const uint8_t* masks,
+                                 const aadg_aug_row_t* rows, int n_rows, int n_src, int height, int width,
+                                 int crop_w, int crop_h, int dataset, float* out_images, float* out_labels,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Float tensor augmentation bank — replaces the 19 operations of data/operations.py:142-399 /
  * data/functional.py:110-271 (+ data/kernels.py:9-13), forward values:
@@ -141,6 +152,10 @@ size_t aadg_sinkhorn_large_workspace_bytes(int n, int m, int dim);
  * NULL) receives the number of epsilon values (soft-min sweeps executed = that + 2). */
 int aadg_sinkhorn_large(const float* x, int n, const float* y, int m, int dim, float diameter, float* out,
                         int* n_iterations_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Only the set-up of aadg_sinkhorn_large (norms, diameter, cost matrices) — for benchmarks that report the
+ * epsilon iterations separately from the one-off cost build. */
+int aadg_sinkhorn_large_setup(const float* x, int n, const float* y, int m, int dim, float diameter,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Segmentation-net convolutions — replace the cuDNN convolutions behind `model(input)` and
@@ -198,6 +213,10 @@ int aadg_upsample_bilinear_fwd(const void* x, int n, int h, int w, int c, int ld
                                void* stream);
 int aadg_upsample_bilinear_bwd(const void* dy, int n, int ho, int wo, int c, int lddy, void* dx, int h, int w, int lddx,
                                void* stream);
+/* nearest x2 up-sampling into a channel slice (smp Unet DecoderBlock) and its transpose; plain slice copy */
+int aadg_upsample_nearest2x_fwd(const void* x, int n, int h, int w, int c, int ldx, void* y, int ldy, void* stream);
+int aadg_upsample_nearest2x_bwd(const void* dy, int n, int h, int w, int c, int lddy, void* dx, int lddx, void* stream);
+int aadg_copy_bf16(const void* x, int ldx, void* y, int ldy, long long pixels, int c, void* stream);
 /* out fp32 [n,c] = scale * sum over the hw pixels of x bf16 [n,hw,ld] (AdaptiveAvgPool2d(1) with scale = 1/hw) */
 int aadg_global_sum(const void* x, int n, int hw, int c, int ld, float* out, float scale, void* stream);
 /* y[n, p, 0:c] = v[n, 0:c]  (bilinear resize of a 1x1 map) */
@@ -230,6 +249,13 @@ int aadg_seg_loss_bwd(const float* z, int n, int h, int w, int classes, const fl
                       float grad_scale, float* dz, void* stream);
 int aadg_seg_head_bwd(const float* dz, const void* a, long long pixels, int c, int lda, const float* w, int classes,
                       void* da, int ldda, float* dw, float* db, void* stream);
+
+/* smp Unet SegmentationHead: Conv2d(c, classes, 3, padding=1) at full resolution, c <= 64, classes <= 2.
+ * w fp32 [classes][9][c]; z fp32 [n,h,w,classes]; backward: da bf16, dw (+=), db (+=) */
+int aadg_seg_head3x3_fwd(const void* a, int n, int h, int w, int c, int lda, const float* wgt, const float* bias,
+                         int classes, float* z, void* stream);
+int aadg_seg_head3x3_bwd(const float* dz, const void* a, int n, int h, int w, int c, int lda, const float* wgt,
+                         int classes, void* da, int ldda, float* dw, float* db, void* stream);
 
 #ifdef __cplusplus
 }

@@ -76,13 +76,13 @@ class Decoder(nn.Module):
 class ResNetEncoder(nn.Module):
     """smp ResNetEncoder: torchvision ResNet minus fc/avgpool; keys conv1, bn1, layer1..4."""
 
-    def __init__(self, name):
+    def __init__(self, name, dilated=True):
         super().__init__()
         net = getattr(torchvision.models, name)(weights=None)
         self.conv1, self.bn1, self.relu, self.maxpool = net.conv1, net.bn1, net.relu, net.maxpool
         self.layer1, self.layer2, self.layer3, self.layer4 = net.layer1, net.layer2, net.layer3, net.layer4
         # make_dilated(stage_list=[5], dilation_list=[2]) -> replace_strides_with_dilation(layer4, 2)
-        for m in self.layer4.modules():
+        for m in (self.layer4.modules() if dilated else []):
             if isinstance(m, nn.Conv2d):
                 m.stride = (1, 1)
                 m.dilation = (2, 2)
@@ -114,6 +114,55 @@ class DeepLabV3PlusTorch(nn.Module):
         feats = self.encoder(x)
         masks = self.segmentation_head(self.decoder(*feats))
         return masks, torch.flatten(self.pool(feats[-1]), 1)
+
+
+class Conv2dReLU(nn.Sequential):
+    def __init__(self, cin, cout):
+        super().__init__(nn.Conv2d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU())
+
+
+class UnetDecoderBlock(nn.Module):
+    def __init__(self, cin, cskip, cout):
+        super().__init__()
+        self.conv1 = Conv2dReLU(cin + cskip, cout)
+        self.conv2 = Conv2dReLU(cout, cout)
+
+    def forward(self, x, skip=None):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        if skip is not None:
+            x = torch.cat([x, skip], dim=1)
+        return self.conv2(self.conv1(x))
+
+
+class UnetDecoder(nn.Module):
+    def __init__(self, enc_channels, dec_channels=(256, 128, 64, 32, 16)):
+        super().__init__()
+        enc = list(enc_channels[1:])[::-1]
+        in_ch = [enc[0]] + list(dec_channels[:-1])
+        skip_ch = enc[1:] + [0]
+        self.blocks = nn.ModuleList([UnetDecoderBlock(i, s, o) for i, s, o in zip(in_ch, skip_ch, dec_channels)])
+
+    def forward(self, *features):
+        feats = features[1:][::-1]
+        x, skips = feats[0], feats[1:]
+        for i, blk in enumerate(self.blocks):
+            x = blk(x, skips[i] if i < len(skips) else None)
+        return x
+
+
+class UnetTorch(nn.Module):
+    """smp.Unet(encoder_name, classes) with the patched classification head (pool + flatten)."""
+
+    def __init__(self, encoder_name="resnet34", classes=1):
+        super().__init__()
+        self.encoder = ResNetEncoder(encoder_name, dilated=False)
+        self.decoder = UnetDecoder(self.encoder.out_channels)
+        self.segmentation_head = nn.Sequential(nn.Conv2d(16, classes, 3, padding=1), nn.Identity(), nn.Identity())
+        self.pool = nn.AdaptiveAvgPool2d(1)
+
+    def forward(self, x):
+        feats = self.encoder(x)
+        return self.segmentation_head(self.decoder(*feats)), torch.flatten(self.pool(feats[-1]), 1)
 
 
 def f1_samplewise(prob, target, thr=0.5):

@@ -401,3 +401,84 @@ def test_training_reduces_loss():
         first = v if first is None else first
         last = v
     assert np.isfinite(last) and last < 0.75 * first, (first, last)
+
+
+def test_nearest2x_and_head3x3(K):
+    torch.manual_seed(6)
+    x = torch.randn(2, 5, 7, 32, device="cuda").to(BF)
+    cat = torch.zeros(2, 10, 14, 48, device="cuda", dtype=BF)
+    K.nearest2x_fwd(x, cat[..., :32])
+    xr = nchw(x).requires_grad_(True)
+    o = F.interpolate(xr, scale_factor=2, mode="nearest")
+    assert torch.equal(nchw(cat[..., :32]), o) and cat[..., 32:].abs().max() == 0
+    dy = torch.randn(2, 10, 14, 32, device="cuda").to(BF)
+    o.backward(nchw(dy))
+    dx = torch.empty_like(x)
+    K.nearest2x_bwd(dy, dx)
+    rel_close(nchw(dx), xr.grad, 1e-2, "nearest bwd")
+    skip = torch.randn(2, 10, 14, 16, device="cuda").to(BF)
+    K.copy_(skip, cat[..., 32:])
+    assert torch.equal(cat[..., 32:], skip)
+    # 3x3 head
+    n, h, w, c, k = 2, 12, 10, 16, 1
+    a = torch.randn(n, h, w, c, device="cuda").to(BF)
+    wt = torch.randn(k, c, 3, 3, device="cuda") * 0.2
+    b = torch.randn(k, device="cuda")
+    w9 = wt.permute(0, 2, 3, 1).reshape(k, 9, c).contiguous()
+    z = K.seg_head3x3_fwd(a, w9, b)
+    ar, wr, br = nchw(a).requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    zr = F.conv2d(ar, wr, br, padding=1)
+    assert torch.allclose(nchw(z), zr, atol=2e-4, rtol=1e-4)
+    dz = torch.randn(n, h, w, k, device="cuda")
+    zr.backward(nchw(dz))
+    da = torch.empty_like(a)
+    dw, db = torch.zeros(k, 9, c, device="cuda"), torch.zeros(k, device="cuda")
+    K.seg_head3x3_bwd(dz, a, w9, da, dw, db)
+    rel_close(nchw(da), ar.grad, 1e-2, "head3x3 da")
+    rel_close(dw.reshape(k, 3, 3, c).permute(0, 3, 1, 2), wr.grad, 2e-3, "head3x3 dw")
+    rel_close(db, br.grad, 2e-3, "head3x3 db")
+
+
+def test_unet_resnet34_vs_oracle():
+    """smp.Unet / ResNet-34, one class (the RVS configuration): decoder teacher-forced + whole-step loss."""
+    from aadg_b200.nn import Unet
+    from aadg_b200.synth import vessel_batch
+    from oracle.segnet_torch import UnetTorch
+    torch.manual_seed(3)
+    ref = UnetTorch("resnet34", 1).cuda().train()
+    net = Unet(encoder_name="resnet34", encoder_weights=None, in_channels=3, classes=1)
+    net.load_state_dict(ref.state_dict())
+    assert set(net.state_dict()) == set(ref.state_dict())
+    imgs, masks = vessel_batch(4, 128, 128, seed=9)
+    x = (torch.from_numpy(imgs).cuda().permute(0, 3, 1, 2).float() / 127.5 - 1.0).contiguous()
+    target = (torch.from_numpy(masks).cuda() != 0).float().unsqueeze(1).contiguous()
+    with torch.no_grad():
+        feats = ref.encoder(x)
+    fb = [nhwc(f).to(BF) for f in feats[1:]]
+    fr = [None] + [nchw(f).requires_grad_(True) for f in fb]
+    want = ref.decoder(*fr)
+    got = net.decoder.forward(fb, True)
+    assert l2err(nchw(got), want) < 3e-2, l2err(nchw(got), want)
+    dy = torch.randn_like(want).to(BF)
+    want.backward(dy.float())
+    net.store.zero_grad()
+    d_last, d_skips = net.decoder.backward(nhwc(dy).to(BF))
+    assert l2err(nchw(d_last), fr[5].grad) < 0.3
+    for i, ds in enumerate(d_skips):
+        assert l2err(nchw(ds), fr[i + 1].grad) < 0.3, i
+    bad = _grad_report(net, ref, "decoder.", 0.9)
+    assert not bad, bad[:8]
+    # whole step
+    ref.zero_grad()
+    masks_r, pooled = ref(x)
+    loss = F.binary_cross_entropy(torch.sigmoid(masks_r), target)
+    net.store.zero_grad()
+    out = net.loss_step(x, target, want_logits=True)
+    assert abs(out["loss"].item() - loss.item()) <= 5e-3 * abs(loss.item()), (out["loss"].item(), loss.item())
+    assert l2err(out["pooled"], pooled) < 5e-2
+    first = out["loss"].item()
+    for _ in range(8):
+        net.store.zero_grad()
+        out = net.loss_step(x, target)
+        net.store.adam_step(1e-3)
+    assert out["loss"].item() < first

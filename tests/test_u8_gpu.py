@@ -122,6 +122,66 @@ def test_post_policy_golden(u8, golden_dir, tag):
     assert np.array_equal(out.reshape(g["post_policy"].shape), g["post_policy"])
 
 
+def replay_all(g):
+    seed, n_src = int(g["seed"]), int(g["n_src"])
+    h, w, crop = int(g["height"]), int(g["width"]), int(g["crop"])
+    parsed = parse_policies(g["policies"], Cfg)
+    py, npr = random.Random(seed), np.random.RandomState(seed)
+    state = D.PolicyState(len(parsed))
+    rows, raws = [], []
+    for s in range(n_src):
+        r, raw = D.replay_sample(parsed, s, w, h, crop, tuple(g["scale_range"]), py, npr, state)
+        D.soft_label(py, s % 3, 3)
+        rows.append(r)
+        raws.append(raw)
+    return np.concatenate(rows), np.stack(raws)
+
+
+@pytest.mark.parametrize("tag", ["optic64", "optic_rect", "rvs64"])
+def test_full_train_transform_golden(u8, golden_dir, tag):
+    """policy -> DGRandomScaleCrop -> Normalize_dg -> ToTensor == the reference pipeline, bit for bit
+    (Pillow BILINEAR/NEAREST resize, padding, crop), for the augmented copies and the raw image."""
+    g = np.load(os.path.join(golden_dir, "u8_pipeline_%s.npz" % tag))
+    gen = vessel_batch if bool(g["vessel"]) else fundus_batch
+    imgs, masks = gen(int(g["n_src"]), int(g["height"]), int(g["width"]), seed=int(g["seed"]))
+    rows, raws = replay_all(g)
+    crop, ds = int(g["crop"]), str(g["dataset"])
+    im, lb = u8.policy_scale_crop_normalize(dev(imgs), dev(masks), rows, crop, ds)
+    want = (g["aug_u8"].astype(np.float32) / np.float32(127.5) - np.float32(1)).transpose(0, 1, 4, 2, 3)
+    assert np.array_equal(im.cpu().numpy().reshape(want.shape), want)
+    assert np.array_equal(lb.cpu().numpy().reshape(g["aug_labels"].shape), g["aug_labels"].astype(np.float32))
+    im, lb = u8.scale_crop_normalize(dev(imgs), dev(masks), raws, crop, ds, image_by_row=False)
+    wraw = (g["raw_u8"].astype(np.float32) / np.float32(127.5) - np.float32(1)).transpose(0, 3, 1, 2)
+    assert np.array_equal(im.cpu().numpy(), wraw)
+    assert np.array_equal(lb.cpu().numpy(), g["raw_labels"].astype(np.float32))
+
+
+def test_scale_crop_vs_oracle_up_and_down(u8):
+    """down-scaling (antialias window > 3 taps), padding and every crop offset path vs the oracle."""
+    from oracle import u8_transform as T
+    h, w, crop = 60, 72, 48
+    imgs, masks = vessel_batch(2, h, w, seed=4)
+    rng = np.random.RandomState(3)
+    rows = np.zeros(12, D.ROW_DTYPE)
+    for i, row in enumerate(rows):
+        row["src"] = i % 2
+        row["do_scale"] = int(i % 4 != 0)
+        sw, sh = (int(rng.uniform(0.5, 2) * w), int(rng.uniform(0.5, 2) * h)) if row["do_scale"] else (w, h)
+        row["scale_w"], row["scale_h"] = sw, sh
+        pad = D.crop_padding(sw, sh, crop, crop)
+        row["pad"] = pad
+        row["crop_x"] = rng.randint(0, sw + 2 * pad - crop + 1)
+        row["crop_y"] = rng.randint(0, sh + 2 * pad - crop + 1)
+    im, lb = u8.scale_crop_normalize(dev(imgs), dev(masks), rows, crop, "vessel", image_by_row=False)
+    for i, row in enumerate(rows):
+        dec = dict(do_scale=int(row["do_scale"]), w=int(row["scale_w"]), h=int(row["scale_h"]),
+                   x1=int(row["crop_x"]), y1=int(row["crop_y"]))
+        wi, wm = T.scale_crop(imgs[row["src"]], masks[row["src"]], dec, crop, crop)
+        fi, fm = T.to_tensor_pair(T.normalize_image(wi), T.normalize_mask(wm, "vessel"))
+        assert np.array_equal(im[i].cpu().numpy(), fi), i
+        assert np.array_equal(lb[i].cpu().numpy(), fm), i
+
+
 CHAINS = [
     [("Sharpness", 1.0), ("Sharpness", 0.0)],
     [("Sharpness", 7 / 9), ("Equalize", 0.0)],
