@@ -370,6 +370,142 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_p_kernel(const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---- cosine-cost Gram matrix for the Sinkhorn set-up -------------------------------------------------------
+// C[i][j] = 1 - <A_i, B_j> / (na_i nb_j) with A [n,K], B [m,K] bf16 K-major (K = 6d: the bf16x3 split of the
+// fp32 features arranged so that one dot product sums the six significant cross terms), fp32 accumulation in
+// TMEM, fp32 output; optionally also the transpose.  Same pipeline as igemm_kernel, 2-D tensor maps.
+struct GramArgs {
+  int n, m, k_blocks;
+  const float* na; const float* nb;
+  float* c; long long ldc;
+  float* ct; long long ldct;
+};
+constexpr int GRAM_STAGES = 3;
+constexpr int gram_smem_bytes() { return GRAM_STAGES * (A_BYTES + 128 * 128) + 1024 + 256; }
+
+__global__ void __launch_bounds__(IG_THREADS) gram_cost_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const GramArgs a) {
+  constexpr int BN = 128, STAGES = GRAM_STAGES;
+  constexpr int STAGE_BYTES = A_BYTES + BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int i0 = blockIdx.y * 128, j0 = blockIdx.x * BN;     // x fastest: CTAs sharing the A rows run together
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0, phase = 0;
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        tma_load_2d(sa, &tmA, &full[stage], kb * 64, i0);
+        tma_load_2d(sa + A_BYTES, &tmB, &full[stage], kb * 64, j0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0, phase = 0;
+      for (int k = 0; k < a.k_blocks; ++k) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint64_t adesc = make_sdesc(sa, 16, 1024), bdesc = make_sdesc(sa + A_BYTES, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int i = i0 + q * 32 + lane;
+    const bool row_ok = i < a.n;
+    const float ni = row_ok ? a.na[i] : 1.f;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int j = j0 + c + e;
+        const float nj = j < a.m ? a.nb[j] : 1.f;
+        v[e] = __fsub_rn(1.0f, __fdiv_rn(__uint_as_float(r[e]), __fmul_rn(ni, nj)));
+      }
+      if (row_ok) {
+        float* crow = a.c + (long long)i * a.ldc + j0 + c;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          if (j0 + c + e < a.m) *reinterpret_cast<float4*>(crow + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
+      if (a.ct) {
+        // transposed copy: for a fixed column the 32 lanes (consecutive rows i) write 128 contiguous bytes
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = j0 + c + e;
+          if (row_ok && j < a.m) a.ct[(long long)j * a.ldct + i] = v[e];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+int gram_cost(const void* A, int n, const void* B, int m, int k, const float* na, const float* nb, float* c,
+              long long ldc, float* ct, long long ldct, cudaStream_t st) {
+  AADG_REQUIRE(k % 8 == 0 && ldc % 4 == 0, "gram_cost: k %% 8 and ldc %% 4 must be 0");
+  CUtensorMap mA, mB;
+  {
+    const long long dims[2] = {k, n};
+    const long long strides[1] = {k};
+    const int box[2] = {64, 128};
+    int rc = make_map_bf16(&mA, A, 2, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    const long long dims[2] = {k, m};
+    const long long strides[1] = {k};
+    const int box[2] = {64, 128};
+    int rc = make_map_bf16(&mB, B, 2, dims, strides, box, nullptr);
+    if (rc) return rc;
+  }
+  GramArgs a{};
+  a.n = n; a.m = m; a.k_blocks = (k + 63) / 64; a.na = na; a.nb = nb; a.c = c; a.ldc = ldc; a.ct = ct; a.ldct = ldct;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(gram_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes()));
+    attr_set = true;
+  }
+  dim3 grid((m + 127) / 128, (n + 127) / 128);
+  AADG_REQUIRE(grid.y <= 65535, "too many rows for one launch");
+  gram_cost_kernel<<<grid, IG_THREADS, gram_smem_bytes(), st>>>(mA, mB, a);
+  return check_launch("gram cost kernel");
+}
+
 // ---- wgrad --------------------------------------------------------------------------------------------
 struct WgradArgs {
   int lg_tw, lg_th;            // log2 extents of the 64-pixel K tile in x, y

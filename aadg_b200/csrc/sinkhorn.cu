@@ -14,9 +14,10 @@
 //     fp32 and every epsilon iteration streams them once (HBM-bound, 4*N*M*4 bytes): each soft-min
 //     is a column-direction online log-sum-exp (coalesced 16-byte loads, per-thread running
 //     max/sum, no cross-thread traffic), split over row bands and merged by a small combine kernel.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace aadg {
@@ -358,6 +359,24 @@ __global__ void __launch_bounds__(256) cost_kernel(const float* a, const float* 
   }
 }
 
+// fp32 -> three bf16 terms (hi + mid + lo reproduces x to ~2^-24), written in the two arrangements whose dot
+// product sums the six significant cross terms:  A = [hi, hi, mid, hi, lo, mid],  B = [hi, mid, hi, lo, hi, mid]
+__global__ void split3_kernel(const float* x, long long total, int d, __nv_bfloat16* arr_a, __nv_bfloat16* arr_b) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / d;
+    const int k = (int)(e - r * d);
+    const float v = x[e];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    __nv_bfloat16* pa = arr_a + r * 6 * d + k;
+    __nv_bfloat16* pb = arr_b + r * 6 * d + k;
+    pa[0] = hi; pa[d] = hi; pa[2 * d] = mid; pa[3 * d] = hi; pa[4 * d] = lo; pa[5 * d] = mid;
+    pb[0] = hi; pb[d] = mid; pb[2 * d] = hi; pb[3 * d] = lo; pb[4 * d] = hi; pb[5 * d] = mid;
+  }
+}
+
 // One soft-min family: out[c] = LSE_r( h[r] - P * C[r][c] ) over the rows of a row band.
 struct LseMat {
   const float* C;     // [rows][ld]
@@ -480,7 +499,7 @@ __global__ void final_kernel(const float* ax, const float* bx, int n, const floa
 }
 
 struct LargeLayout {
-  size_t cxx, cyy, cxy, cyx, nx, ny, lo, hi, diam, pot, h, part, total;
+  size_t cxx, cyy, cxy, cyx, nx, ny, lo, hi, diam, pot, h, part, arr, total;
   int ldn, ldm, splits_n, splits_m;
 };
 static int pick_splits(int rows, int cols) {
@@ -489,7 +508,12 @@ static int pick_splits(int rows, int cols) {
   s = std::max(1, std::min(s, (rows + 63) / 64));
   return s;
 }
-static LargeLayout large_layout(int n, int m) {
+static bool use_tc(int dim) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AADG_SINKHORN_TC"); v = e ? atoi(e) : 1; }
+  return v && dim % 8 == 0;
+}
+static LargeLayout large_layout(int n, int m, int dim = 0) {
   LargeLayout L{};
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = align_up(off, 256); off = o + b; return o; };
@@ -507,6 +531,7 @@ static LargeLayout large_layout(int n, int m) {
   L.h = take(sizeof(float) * 2 * ((size_t)n + m));        // hax, hay [n]; hby, hbx [m]
   const int smax = std::max(L.splits_n, L.splits_m);
   L.part = take(sizeof(float2) * (size_t)smax * 2 * ((size_t)n + m));
+  L.arr = take(dim > 0 && use_tc(dim) ? sizeof(__nv_bfloat16) * 2 * 6 * (size_t)dim * ((size_t)n + m) : 0);
   L.total = align_up(off, 256);
   return L;
 }
@@ -564,7 +589,7 @@ int aadg_sinkhorn_diversity_rewards(const float* features, const float* domain_c
 
 size_t aadg_sinkhorn_large_workspace_bytes(int n, int m, int dim) {
   if (n <= 0 || m <= 0 || dim <= 0) return 0;
-  return large_layout(n, m).total;
+  return large_layout(n, m, dim).total;
 }
 
 /* One divergence on big clouds.  Synchronises `stream` once (the diameter, like the reference's
@@ -591,7 +616,7 @@ static int sinkhorn_large_impl(const float* x, int n, const float* y, int m, int
                                int cost_only) {
   AADG_REQUIRE(n > 0 && m > 0 && dim > 0 && dim <= 4096, "bad sizes n=%d m=%d dim=%d", n, m, dim);
   AADG_REQUIRE(x && y && (out || cost_only), "null pointer");
-  const LargeLayout L = large_layout(n, m);
+  const LargeLayout L = large_layout(n, m, dim);
   if (!workspace || workspace_bytes < L.total) {
     set_error("workspace too small: need %zu bytes, got %zu", L.total, workspace_bytes);
     return AADG_ENOSPC;
@@ -630,7 +655,19 @@ static int sinkhorn_large_impl(const float* x, int n, const float* y, int m, int
   const int n_eps = eps_schedule(diam, eps);
   if (n_iterations_out) *n_iterations_out = n_eps;
 
-  {
+  if (use_tc(dim) && n >= 128 && m >= 128) {
+    // tensor-core cost build: bf16x3 split of the features, fp32 accumulation (tcgen05), ~fp32 accuracy
+    __nv_bfloat16* xa = (__nv_bfloat16*)(w + L.arr);
+    __nv_bfloat16* xb = xa + (size_t)6 * dim * n;
+    __nv_bfloat16* ya = xb + (size_t)6 * dim * n;
+    __nv_bfloat16* yb = ya + (size_t)6 * dim * m;
+    split3_kernel<<<148 * 8, 256, 0, st>>>(x, (long long)n * dim, dim, xa, xb);
+    split3_kernel<<<148 * 8, 256, 0, st>>>(y, (long long)m * dim, dim, ya, yb);
+    int rc2 = tc::gram_cost(xa, n, xb, n, 6 * dim, nx, nx, cxx, L.ldn, nullptr, 0, st);
+    if (!rc2) rc2 = tc::gram_cost(ya, m, yb, m, 6 * dim, ny, ny, cyy, L.ldm, nullptr, 0, st);
+    if (!rc2) rc2 = tc::gram_cost(xa, n, yb, m, 6 * dim, nx, ny, cxy, L.ldm, cyx, L.ldn, st);
+    if (rc2) return rc2;
+  } else {
     dim3 g((n + CT - 1) / CT, (n + CT - 1) / CT);
     cost_kernel<<<g, 256, 0, st>>>(x, nx, n, x, nx, n, dim, cxx, L.ldn, nullptr, 0);
     dim3 g2((m + CT - 1) / CT, (m + CT - 1) / CT);

@@ -20,6 +20,10 @@ EncodeTiledFn encode_fn();
 int make_map_bf16(CUtensorMap* map, const void* base, int rank, const long long* dims,
                   const long long* strides_elems, const int* box, const int* elem_strides);
 
+// C[i][j] = 1 - <A_i,B_j>/(na_i nb_j) on tensor cores (conv_tc.cu); A [n,k], B [m,k] bf16, optional transpose ct
+int gram_cost(const void* A, int n, const void* B, int m, int k, const float* na, const float* nb, float* c,
+              long long ldc, float* ct, long long ldct, cudaStream_t st);
+
 // ---- device ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {

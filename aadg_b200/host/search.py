@@ -77,8 +77,9 @@ class SearchEngine:
         self.rewards.zero_()
 
     def decision_rows(self, n_src, width, height):
-        rows, raws = D.philox_rows(self.policies, n_src, width, height, width, self.scale_range,
-                                   self.seed + 1000003 * self.rank, self.epoch, self.step_idx, scale_crop=False)
+        rows, raws = D.philox_rows(self.policies, n_src, width, height, self.crop or width, self.scale_range,
+                                   self.seed + 1000003 * self.rank, self.epoch, self.step_idx,
+                                   scale_crop=self.crop is not None)
         return rows
 
     def domain_codes(self, src_domains):
@@ -96,7 +97,10 @@ class SearchEngine:
         if dc is None:
             dc = self.domain_codes(src_domains)
         dc_dev = torch.from_numpy(dc).to(src_images.device, non_blocking=True)
-        images, labels = U8.policy_normalize(src_images, src_masks, rows, dataset=self.dataset)
+        if self.crop is not None:      # DGMultiPolicy -> DGRandomScaleCrop -> Normalize_dg -> ToTensor
+            images, labels = U8.policy_scale_crop_normalize(src_images, src_masks, rows, self.crop, self.dataset)
+        else:                          # DGMultiPolicy -> Normalize_dg -> ToTensor (one fused pass)
+            images, labels = U8.policy_normalize(src_images, src_masks, rows, dataset=self.dataset)
         model = self.model
         model.store.zero_grad()
         out = model.loss_step(images, labels)

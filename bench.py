@@ -37,6 +37,7 @@ def parse_args():
     ap.add_argument("--backbone", default="resnet50")
     ap.add_argument("--items", type=int, default=8, help="TRAIN.BATCH_SIZE: items per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scale-crop", action="store_true", help="skip DGRandomScaleCrop (fused policy+normalise pass)")
     return ap.parse_args()
 
 
@@ -55,7 +56,8 @@ def workload_config(a, n_gpus):
                         "search step (augment->fwd->rewards->bwd->Adam)" % (a.size, a.size, a.backbone),
             "items_per_gpu": a.items, "domains": d, "policies_M": m, "images_per_step_per_gpu": a.items * d * m,
             "global_images_per_step": a.items * d * m * n_gpus, "image_size": a.size, "sub_policy_ops_L": 2,
-            "scale_crop": "none (DGRandomScaleCrop is SURVEY.md 8f row N1, not yet on the device path)",
+            "scale_crop": "none" if a.no_scale_crop else
+            "DGRandomScaleCrop(%d, scale 1-1.5, p=0.8) on the device, bit-exact Pillow resize" % a.size,
             "parallelism": "dp%d (source images sharded; NCCL grad all-reduce + feature all-gather)" % n_gpus,
             "l2": "per-step working set (tens of GB of activations) >> 126 MB L2, no explicit flush needed"}
 
@@ -130,9 +132,9 @@ def cpu_joint_step_sample(a, threads=None):
     size = a.size
     imgs, masks = fundus_batch(1, size, size, seed=1023)
     parsed = parse_policies(random_policies(seed=1023), Cfg)
-    rows, _ = D.philox_rows(parsed, 1, size, size, size, (1, 1.5), seed=1023, scale_crop=False)
+    rows, _ = D.philox_rows(parsed, 1, size, size, size, (1, 1.5), seed=1023, scale_crop=not a.no_scale_crop)
     t0 = time.perf_counter()
-    out = OP.apply_rows(imgs, masks, rows, crop=None, dataset="optic")
+    out = OP.apply_rows(imgs, masks, rows, crop=None if a.no_scale_crop else size, dataset="optic")
     t_aug = (time.perf_counter() - t0) / len(rows)
     torch.manual_seed(0)
     model = DeepLabV3PlusTorch(a.backbone, 2).train()
@@ -155,7 +157,7 @@ def cpu_joint_step_sample(a, threads=None):
     t_sink = (time.perf_counter() - t0) / 144.0
     per_img = t_aug + t_model + t_sink
     info = {"cores": cores, "kind": "port",
-            "sample": "1 source image -> 6 augmented %dx%d copies (oracle uint8 bank, numpy, 1 core): %.3f s/img; "
+            "sample": "1 source image -> 6 augmented %dx%d copies (oracle uint8 bank + scale/crop, numpy, 1 core): %.3f s/img; "
                       "DeepLabV3+/%s fwd+bwd+Adam on 2 images (torch CPU fp32, %d threads): %.3f s/img; 18 Sinkhorn "
                       "divergences N=8 d=128 (numpy fp32): %.4f s per 144-image step" %
                       (size, size, t_aug, a.backbone, cores, t_model, t_sink * 144)}
@@ -217,7 +219,8 @@ def run_ours(a):
 
     model = DeepLabV3Plus(encoder_name=a.backbone, encoder_weights=None, in_channels=3, classes=2,
                           aux_params=dict(pooling="avg"), device=dev, seed=1023)
-    eng = SearchEngine(model, n_domains=d, M=m, lr=1e-3, dataset="optic", seed=1023)
+    eng = SearchEngine(model, n_domains=d, M=m, lr=1e-3, dataset="optic", seed=1023,
+                       crop=None if a.no_scale_crop else a.size, scale_range=(1, 1.5))
     eng.set_policies(parse_policies(random_policies(m=m, seed=1023), Cfg), epoch=0)
 
     def barrier():
@@ -286,9 +289,17 @@ def run_ours(a):
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    traffic = None
+    try:   # dram__bytes_read+write of the conv launches of ONE step, from the committed ncu capture (not live)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")))
+        traffic = tj["dram_bytes_per_launch_avg"]
+    except Exception:
+        pass
     roof = {"bound": "tensor", "kernel": "aadg::tc::igemm_kernel / wgrad_kernel (all conv fprop+dgrad+wgrad launches)",
             "achieved": tflops_achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": (tflops_achieved / peak_tf) if tflops_achieved else None, "traffic": None,
+            "frac": (tflops_achieved / peak_tf) if tflops_achieved else None, "traffic": traffic,
+            "traffic_note": "avg DRAM bytes per conv launch from profiles/r01_conv_traffic.json (ncu), same command",
+            "flops_per_launch_avg": (sum(r[1] for r in conv_records) / len(conv_records)) if conv_records else None,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
             "conv_ms_per_step": conv_ms / a.steps, "conv_share_of_step": conv_ms / ms if ms else None,
             "conv_launches_per_step": len(conv_records) / a.steps if conv_records else None}
