@@ -54,7 +54,7 @@ struct PassItem {
   int out;         // output image index (scratch slot or final row) / statistics slot
   int sharp;       // index of the SHARP step inside [s0,s1) or -1
   int gather;      // 1 if [s0,s1) contains AFFINE/FLIP (then sharp == -1 or gathers precede it)
-  int pad_;
+  int pad_;        // 1: every step in [s0,s1) is a look-up table (fast path)
 };
 struct Stat {      // one statistics slot
   unsigned int hist[3][256];
@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
   __shared__ __align__(128) uint8_t tile[(TH + 2) * RS];
   __shared__ __align__(16) uint8_t s_luts[AADG_MAX_OPS * 768];
   __shared__ float s_norm[256];
+  __shared__ __align__(16) uint8_t s_comp[768];                    // composition of an all-LUT program
+  __shared__ float s_fcomp[MODE == MODE_F32 ? 768 : 1];           // ... already normalised (MODE_F32)
   __shared__ __align__(8) uint64_t bar;
   __shared__ unsigned int s_hist[MODE == MODE_STATS ? (NT / 32) * 768 : 1];
   __shared__ DevRow s_row;
@@ -193,6 +195,19 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
   }
   __syncthreads();
   const DevRow& row = s_row;
+  // fast path: a program made only of look-up tables collapses into ONE table per channel (7 of the 10
+  // searchable ops are tables), so the per-pixel work is three shared-memory reads
+  const bool fast = it.pad_ != 0;
+  if (fast) {
+    for (int i = tid; i < 768; i += NT) {
+      const int c = i >> 8;
+      int v = i & 255;
+      for (int k = it.s0; k < it.s1; ++k) v = s_luts[k * 768 + c * 256 + v];
+      s_comp[i] = (uint8_t)v;
+      if (MODE == MODE_F32) s_fcomp[i] = __fsub_rn(__fdiv_rn((float)v, 127.5f), 1.0f);
+    }
+    __syncthreads();
+  }
   const uint8_t* base = it.base < 0 ? a.src + (size_t)row.src * H * W * 3
                                     : a.scratch + (size_t)it.base * H * W * 3;
   const int halo = it.sharp >= 0 ? 1 : 0;
@@ -273,6 +288,7 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
     if (row_ok && x < W) {
       const uint8_t* p = tile + (ty + 1) * RS + (x * 3 - sbase);
       r = p[0]; g = p[1]; b = p[2];
+      if (fast) { vr[i] = r; vg[i] = g; vb[i] = b; continue; }     // tables applied at the store
       int k = pre_applied ? pre_end : it.s0;
       if (it.sharp >= 0) {
         const DevStep& st = row.s[it.sharp];
@@ -290,6 +306,10 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
     vr[i] = r; vg[i] = g; vb[i] = b;
   }
 
+  if (fast && MODE != MODE_F32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { vr[i] = s_comp[vr[i]]; vg[i] = s_comp[256 + vg[i]]; vb[i] = s_comp[512 + vb[i]]; }
+  }
   if (MODE == MODE_STATS) {
     unsigned int* hh = s_hist + (tid >> 5) * 768;
 #pragma unroll
@@ -317,14 +337,17 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
     if (row_ok) {
       const size_t plane = (size_t)H * W;
       float* o = a.out_f32 + (size_t)it.out * 3 * plane + (size_t)y * W + xq;
+      const float* tr = fast ? s_fcomp : s_norm;
+      const float* tg = fast ? s_fcomp + 256 : s_norm;
+      const float* tb = fast ? s_fcomp + 512 : s_norm;
       if (xq + 3 < W && (W & 3) == 0) {
-        __stcs((float4*)o, make_float4(s_norm[vr[0]], s_norm[vr[1]], s_norm[vr[2]], s_norm[vr[3]]));
-        __stcs((float4*)(o + plane), make_float4(s_norm[vg[0]], s_norm[vg[1]], s_norm[vg[2]], s_norm[vg[3]]));
-        __stcs((float4*)(o + 2 * plane), make_float4(s_norm[vb[0]], s_norm[vb[1]], s_norm[vb[2]], s_norm[vb[3]]));
+        __stcs((float4*)o, make_float4(tr[vr[0]], tr[vr[1]], tr[vr[2]], tr[vr[3]]));
+        __stcs((float4*)(o + plane), make_float4(tg[vg[0]], tg[vg[1]], tg[vg[2]], tg[vg[3]]));
+        __stcs((float4*)(o + 2 * plane), make_float4(tb[vb[0]], tb[vb[1]], tb[vb[2]], tb[vb[3]]));
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (xq + i < W) { o[i] = s_norm[vr[i]]; o[plane + i] = s_norm[vg[i]]; o[2 * plane + i] = s_norm[vb[i]]; }
+          if (xq + i < W) { o[i] = tr[vr[i]]; o[plane + i] = tg[vg[i]]; o[2 * plane + i] = tb[vb[i]]; }
       }
     }
   }
@@ -576,9 +599,11 @@ static int compile(const aadg_aug_row_t* in, int n_rows, int n_src, Plan& pl) {
     auto item = [&](int s1) {
       PassItem it{};
       it.row = r; it.s0 = seg; it.s1 = s1; it.base = base; it.sharp = -1; it.gather = 0;
+      it.pad_ = 1;        // all steps are look-up tables (also true for an empty program)
       for (int k = seg; k < s1; ++k) {
         if (d.s[k].kind == K_SHARP) it.sharp = k;
         if (d.s[k].kind == K_AFFINE || d.s[k].kind == K_FLIP) it.gather = 1;
+        if (d.s[k].kind != K_LUT) it.pad_ = 0;
       }
       return it;
     };
@@ -647,7 +672,7 @@ static int compile(const aadg_aug_row_t* in, int n_rows, int n_src, Plan& pl) {
     const int s = it.pad_;
     for (int r = 0; r < n_rows; ++r)
       if (pl.rows[r].src == s) { it.row = r; break; }
-    it.pad_ = 0;
+    it.pad_ = 1;   // empty program: identity table, fast path
   }
   return AADG_OK;
 }

@@ -123,7 +123,7 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const f
 // y = act(x*scale + shift (+ res)) (* dropout) ; flags: 1 = relu, 2 = dropout(0.5)
 __global__ void bn_apply_kernel(const bf16* x, int ldx, const float* scale, const float* shift, const bf16* res,
                                 int ldr, bf16* y, int ldy, long long P, int C, int flags,
-                                unsigned long long seed) {
+                                unsigned long long seed, unsigned char* relu_bits) {
   const int G = C >> 3;
   AADG_FOR_PIXEL_GROUPS(P, G, p, g) {
     const long long e = p * G + g;
@@ -137,6 +137,12 @@ __global__ void bn_apply_kernel(const bf16* x, int ldx, const float* scale, cons
       for (int i = 0; i < 8; ++i) v.v[i] += r.v[i];
     }
     if (flags & 1) {
+      if (relu_bits) {      // one byte per 8 channels: backward reads it instead of the whole output tensor
+        unsigned int bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bits |= (v.v[i] > 0.f ? 1u : 0u) << i;
+        relu_bits[e] = (unsigned char)bits;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(v.v[i], 0.f);
     }
@@ -163,6 +169,10 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const bf16* dy, i
       const V8 is = ld8f(invstd + g * 8), ga = ld8f(gamma + g * 8), sh = ld8f(beta + g * 8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d.v[i] = fmaf(xv.v[i], ga.v[i] * is.v[i], sh.v[i]) > 0.f ? d.v[i] : 0.f;
+    } else if (flags & 8) {
+      const unsigned int bits = reinterpret_cast<const unsigned char*>(y)[(size_t)p * G + g];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.v[i] = (bits >> i) & 1 ? d.v[i] : 0.f;
     } else if (flags & 1) {
       const V8 yv = ld8(y + (size_t)p * ldy + g * 8);
 #pragma unroll
@@ -196,6 +206,10 @@ __global__ void bn_bwd_apply_kernel(const bf16* dy, int lddy, const bf16* x, int
       const V8 sh = ld8f(beta + g * 8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d.v[i] = fmaf(xv.v[i], ga.v[i] * is.v[i], sh.v[i]) > 0.f ? d.v[i] : 0.f;
+    } else if (flags & 8) {
+      const unsigned int bits = reinterpret_cast<const unsigned char*>(y)[e];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.v[i] = (bits >> i) & 1 ? d.v[i] : 0.f;
     } else if (flags & 1) {
       const V8 yv = ld8(y + p * ldy + g * 8);
 #pragma unroll
@@ -543,42 +557,54 @@ __global__ void dw3x3_d1_kernel(const bf16* x, int N, int H, int W, int C, int l
       }
   }
 }
-// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]; blockIdx.y = filter row r (3 taps, 24 register accumulators),
-// the three launches' dy reads overlap in L2; block reduction in shared memory [3][C], then atomics
-__global__ void __launch_bounds__(256, 3) dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
+// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]: ONE pass over dy and x (the nine shifted x reads of a pixel
+// hit L1/L2), four channels per thread so that the 36 accumulators fit without spilling; block reduction in
+// dynamic shared memory [9][C], then atomics.  blockDim = (channel quads rounded up to 32, pixel lanes)
+__global__ void __launch_bounds__(512) dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
                                                              const bf16* dy, int lddy, int dil, float* dw) {
   extern __shared__ float s_dw[];
-  const int G = C >> 3;
+  const int G4 = C >> 2;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int r = blockIdx.y;
   const long long P = (long long)N * H * W;
-  float acc[3][8] = {};
-  if (tx < G)
-    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y) {
+  float acc[9][4] = {};
+  // each block sweeps a CONTIGUOUS pixel range: the rows above / below a pixel were touched a few iterations
+  // earlier by the same block, so the nine shifted reads hit L1 instead of going back to L2
+  const long long chunk = (P + gridDim.x - 1) / gridDim.x;
+  const long long p_end = min(P, (long long)(blockIdx.x + 1) * chunk);
+  if (tx < G4)
+    for (long long p = (long long)blockIdx.x * chunk + ty; p < p_end; p += blockDim.y) {
       const int ox = (int)(p % W), oy = (int)((p / W) % H);
-      const int iy = oy + (r - 1) * dil;
-      if (iy < 0 || iy >= H) continue;
-      const V8 d = ld8(dy + (size_t)p * lddy + tx * 8);
-      const bf16* xr = x + (size_t)(p + (long long)(iy - oy) * W) * ldx + tx * 8;
+      const uint2 du = *reinterpret_cast<const uint2*>(dy + (size_t)p * lddy + tx * 4);
+      const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du.x));
+      const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du.y));
 #pragma unroll
-      for (int s2 = 0; s2 < 3; ++s2) {
-        const int ix = ox + (s2 - 1) * dil;
-        if (ix < 0 || ix >= W) continue;
-        const V8 v = ld8(xr + (long long)(ix - ox) * ldx);
+      for (int r = 0; r < 3; ++r) {
+        const int iy = oy + (r - 1) * dil;
+        if (iy < 0 || iy >= H) continue;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[s2][i] = fmaf(d.v[i], v.v[i], acc[s2][i]);
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const int ix = ox + (s2 - 1) * dil;
+          if (ix < 0 || ix >= W) continue;
+          const uint2 xu = *reinterpret_cast<const uint2*>(
+              x + (size_t)(p + (long long)(iy - oy) * W + (ix - ox)) * ldx + tx * 4);
+          const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xu.x));
+          const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xu.y));
+          float* a = acc[r * 3 + s2];
+          a[0] = fmaf(d01.x, x01.x, a[0]); a[1] = fmaf(d01.y, x01.y, a[1]);
+          a[2] = fmaf(d23.x, x23.x, a[2]); a[3] = fmaf(d23.y, x23.y, a[3]);
+        }
       }
     }
-  for (int i = ty * blockDim.x + tx; i < 3 * C; i += blockDim.x * blockDim.y) s_dw[i] = 0.f;
+  for (int i = ty * blockDim.x + tx; i < 9 * C; i += blockDim.x * blockDim.y) s_dw[i] = 0.f;
   __syncthreads();
-  if (tx < G) {
+  if (tx < G4) {
 #pragma unroll
-    for (int t = 0; t < 3; ++t)
+    for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * C + tx * 8 + i], acc[t][i]);
+      for (int i = 0; i < 4; ++i) atomicAdd(&s_dw[t * C + tx * 4 + i], acc[t][i]);
   }
   __syncthreads();
-  for (int i = ty * blockDim.x + tx; i < 3 * C; i += blockDim.x * blockDim.y) atomicAdd(&dw[(size_t)r * 3 * C + i], s_dw[i]);
+  for (int i = ty * blockDim.x + tx; i < 9 * C; i += blockDim.x * blockDim.y) atomicAdd(&dw[i], s_dw[i]);
 }
 
 // ---- stem im2col: fp32 NCHW [-1,1] image -> bf16 [N*Ho*Wo][KP] patches, k = (r*S + s)*3 + c --------------------
@@ -692,10 +718,12 @@ int aadg_bn_finalize(const float* sum, const float* sumsq, const float* gamma, c
 }
 
 int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr, void* y,
-                  int ldy, long long pixels, int c, int flags, unsigned long long seed, void* stream) {
+                  int ldy, long long pixels, int c, int flags, unsigned long long seed, void* relu_bits,
+                  void* stream) {
   NN_REQ_C(c);
   bn_apply_kernel<<<grid_for(pixels * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, ldx, scale, shift, (const bf16*)res, ldr, (bf16*)y, ldy, pixels, c, flags, seed);
+      (const bf16*)x, ldx, scale, shift, (const bf16*)res, ldr, (bf16*)y, ldy, pixels, c, flags, seed,
+      (unsigned char*)relu_bits);
   return check_launch("bn_apply");
 }
 
@@ -710,7 +738,7 @@ int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const voi
   AADG_CUDA_TRY(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
   const dim3 blk = reduce_block(c);
   const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 8);
-  AADG_REQUIRE(!(flags & 1) || (flags & 4) || y, "ReLU mask needs y (or flag 4 to recompute it from x)");
+  AADG_REQUIRE(!(flags & 1) || (flags & 4) || y, "ReLU mask needs y / the bit mask (or flag 4 to recompute it from x)");
   AADG_REQUIRE(!(flags & 4) || shift, "flag 4 needs the forward shift vector");
   bn_bwd_reduce_kernel<<<std::max(blocks, 1), blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y,
                                                            ldy, mean, invstd, gamma, shift, (int)pixels, c, flags, seed,
@@ -818,12 +846,17 @@ int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, con
   NN_REQ_C(c);
   const long long pixels = (long long)n * h * w;
   AADG_REQUIRE(pixels < (1ll << 31), "too many pixels");
-  const dim3 blk = reduce_block(c);
+  const int bx = std::min(512, ((c / 4) + 31) / 32 * 32);
+  const dim3 blk(bx, std::max(1, 256 / bx));
   const int blocks = (int)std::min<long long>((pixels + blk.y * 16 - 1) / (blk.y * 16), 148 * 6);
-  const size_t smem = (size_t)3 * c * sizeof(float);
-  dim3 grid(std::max(blocks, 1), 3);
-  dw3x3_wgrad_kernel<<<grid, blk, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, lddy,
-                                                               dil, dw);
+  const size_t smem = (size_t)9 * c * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(dw3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 2048 * 4));
+    attr_set = true;
+  }
+  dw3x3_wgrad_kernel<<<std::max(blocks, 1), blk, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx,
+                                                                              (const bf16*)dy, lddy, dil, dw);
   return check_launch("dwconv3x3 wgrad");
 }
 

@@ -153,7 +153,7 @@ class BatchNorm:
         self.num_batches_tracked = 0
         self.buf = torch.zeros(6, c, device=dev)    # sum, sumsq, mean, invstd, scale, shift
 
-    def forward(self, x, y, training, res=None, relu=True, dropout_seed=None):
+    def forward(self, x, y, training, res=None, relu=True, dropout_seed=None, relu_bits=None):
         s = self.buf
         if training:
             s[:2].zero_()
@@ -167,7 +167,7 @@ class BatchNorm:
             s[2].copy_(self.running_mean)
             torch.mul(self.gamma.data, s[3], out=s[4])
             torch.sub(self.beta.data, s[2] * s[4], out=s[5])
-        K.bn_apply(x, s[4], s[5], y, res=res, relu=relu, dropout_seed=dropout_seed)
+        K.bn_apply(x, s[4], s[5], y, res=res, relu=relu, dropout_seed=dropout_seed, relu_bits=relu_bits)
         self.saved = s[2:6].clone() if training else None       # mean, invstd, scale, shift
 
     def backward(self, dy, x, y, dx, relu=True, dropout_seed=None, dres=None, dres_accumulate=False):
@@ -199,9 +199,13 @@ class ConvBN:
         pre = C.fprop(x, self.w.bf16, self.k, self.k, self.stride, self.pad, self.dil)
         if out is None:
             out = torch.empty((n, ho, wo, self.cout), dtype=BF16, device=x.device)
-        self.bn.forward(pre, out, training, res=res, relu=self.relu, dropout_seed=dropout_seed)
-        # the output is only needed by backward for the ReLU mask of a residual sum
-        self.ctx = (x, pre, out if res is not None else None, dropout_seed) if training else None
+        # backward needs the ReLU mask: recomputed from `pre` when there is no residual, otherwise kept as one
+        # bit per element (reading it costs 1/16 of re-reading the output tensor)
+        bits = None
+        if training and res is not None and self.relu:
+            bits = torch.empty((pre.numel() // 8,), dtype=torch.uint8, device=x.device)
+        self.bn.forward(pre, out, training, res=res, relu=self.relu, dropout_seed=dropout_seed, relu_bits=bits)
+        self.ctx = (x, pre, bits, dropout_seed) if training else None
         return out
 
     def backward(self, dy, dx=None, accumulate=False, want_dres=False, dres=None, dres_accumulate=False):

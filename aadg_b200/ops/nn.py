@@ -36,17 +36,19 @@ def bn_finalize(sum_, sumsq, gamma, beta, count, eps, momentum, mean, invstd, sc
           p(mean), p(invstd), p(scale), p(shift), p(run_mean), p(run_var))
 
 
-def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None):
+def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None, relu_bits=None):
     flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0)
     _call("aadg_bn_apply", p(x), _ld(x), p(scale), p(shift), p(res), _ld(res) if res is not None else 0, p(y), _ld(y),
-          _pix(x), x.shape[-1], flags, int(dropout_seed or 0))
+          _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(relu_bits))
 
 
 def bn_backward(dy, x, y, mean, invstd, gamma, dgamma, dbeta, dx, relu=True, dropout_seed=None, dres=None,
                 dres_accumulate=False, shift=None):
     """y=None with relu=True recomputes the ReLU mask from x and the forward `shift` (no residual case)."""
-    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (4 if (relu and y is None) else 0)
-    _call("aadg_bn_backward", p(dy), _ld(dy), p(x), _ld(x), p(y), _ld(y) if y is not None else 0, p(mean), p(invstd),
+    bits = y is not None and y.dtype == torch.uint8        # relu bit mask written by bn_apply(relu_bits=...)
+    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (4 if (relu and y is None) else 0) | \
+        (8 if bits else 0)
+    _call("aadg_bn_backward", p(dy), _ld(dy), p(x), _ld(x), p(y), _ld(y) if (y is not None and not bits) else 0, p(mean), p(invstd),
           p(gamma), p(shift), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
           p(dres), _ld(dres) if dres is not None else 0, int(dres_accumulate))
 

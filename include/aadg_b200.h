@@ -194,12 +194,14 @@ int aadg_bn_stats(const void* x, long long pixels, int c, int ld, float* sum, fl
 int aadg_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int c, float count,
                      float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
                      float* run_mean, float* run_var, void* stream);
-/* y = act(x*scale + shift (+ res)) ; flags bit0 = ReLU, bit1 = Dropout(0.5) keyed by (seed, element) */
+/* y = act(x*scale + shift (+ res)) ; flags bit0 = ReLU, bit1 = Dropout(0.5) keyed by (seed, element);
+ * relu_bits (may be NULL): uint8 [pixels][c/8], bit i of byte g = (pre-activation of channel 8g+i > 0) */
 int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr, void* y,
-                  int ldy, long long pixels, int c, int flags, unsigned long long seed, void* stream);
+                  int ldy, long long pixels, int c, int flags, unsigned long long seed, void* relu_bits,
+                  void* stream);
 /* backward of aadg_bn_apply(training statistics): dgamma, dbeta (overwritten), dx, optional dres (+=).
  * flags bit2 (4): no residual was added, recompute the ReLU mask from x and the forward pass's `shift`
- * vector (y and ldy unused) */
+ * vector (y and ldy unused); flags bit3 (8): `y` points to the relu_bits written by aadg_bn_apply */
 int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
                      const float* invstd, const float* gamma, const float* shift, long long pixels, int c, int flags,
                      unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,

@@ -75,6 +75,16 @@ def test_batchnorm_forward_backward(K, c, res, relu):
     rel_close(nchw(dx), xr.grad, 2e-2, "bn dx")
     if res:
         rel_close(nchw(dres), mask * nchw(dy), 1e-2, "bn dres")
+        if relu:     # the same backward from the 1-bit mask written by the forward pass
+            bits = torch.empty(x.numel() // 8, dtype=torch.uint8, device="cuda")
+            y2 = torch.empty_like(x)
+            K.bn_apply(x, buf[4], buf[5], y2, res=r, relu=True, relu_bits=bits)
+            assert torch.equal(y2, y)
+            dx3, dres3 = torch.empty_like(x), torch.empty_like(x)
+            dg3, db3 = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+            K.bn_backward(dy, x, bits, buf[2].clone(), buf[3].clone(), gamma, dg3, db3, dx3, relu=True, dres=dres3)
+            rel_close(dx3, dx, 1e-2, "mask bits dx")
+            assert torch.equal(dres3, dres)
     elif relu:
         # mask recomputed from x instead of read from y: same result bit for bit
         dx2 = torch.empty_like(x)
