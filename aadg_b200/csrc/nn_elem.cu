@@ -5,6 +5,7 @@
 // the bf16 weight re-layout.  They replace the cuDNN / ATen kernels behind smp.DeepLabV3Plus
 // (models/__init__.py:17-23; search_dg.py:132,170-172; scheduler.py:10-11).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <algorithm>
 
 #include "common.cuh"
@@ -509,102 +510,148 @@ __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
     st8(yrow + (size_t)ox * ldy + g * 8, acc);
   }
 }
-// dilation 1: four consecutive output pixels per thread share a 3 x 6 window (18 loads instead of 36)
-__global__ void dw3x3_d1_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const float* s_w, int sign,
-                                bf16* y, int ldy) {
-  const int G = C >> 3;
-  const int oy = blockIdx.y, n = blockIdx.z;
-  const int W4 = (W + 3) >> 2;
-  const bf16* xn = x + (size_t)n * H * W * ldx;
-  bf16* yrow = y + ((size_t)n * H + oy) * W * ldy;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < W4 * G; e += gridDim.x * blockDim.x) {
-    const int q = e / G, g = e - q * G;
-    const int ox0 = q * 4;
-    float acc[4][8] = {};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int iy = oy + (r - 1);      // forward geometry; the data gradient flips the filter instead
-      if (iy < 0 || iy >= H) continue;
-      V8 col[6];
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int ix = ox0 - 1 + j;
-        if (ix >= 0 && ix < W) col[j] = ld8(xn + ((size_t)iy * W + ix) * ldx + g * 8);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) col[j].v[i] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int s2 = 0; s2 < 3; ++s2) {
-        const int tap = sign > 0 ? r * 3 + s2 : (2 - r) * 3 + (2 - s2);
-        const V8 wv = ld8f(s_w + tap * C + g * 8);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const V8& v = col[k + s2];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(wv.v[i], v.v[i], acc[k][i]);
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (ox0 + k < W) {
-        V8 o;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = acc[k][i];
-        st8(yrow + (size_t)(ox0 + k) * ldy + g * 8, o);
-      }
+// ---- dilation-1 depthwise 3x3 with a rolling three-row window in shared memory --------------------------------
+// block = (image, 32-pixel column strip, 64-channel chunk) walking down all rows: every input element is read
+// from global memory once (plus the 2-pixel halo), the nine taps come from shared memory (conflict-free 16-byte
+// reads), the thread's 9 x 8 filter taps (forward / data gradient) or 9 x 8 accumulators (weight gradient) live
+// in registers.  256 threads = 32 pixels x 8 channel groups.
+constexpr int DWR_XT = 32, DWR_CB = 64;
+struct DwRows {
+  const bf16* x; int ldx;
+  int N, H, W, C;
+};
+__device__ __forceinline__ void dwr_load_row(bf16 (*ring)[DWR_XT + 2][DWR_CB], const DwRows& a, int n, int row, int x0,
+                                             int c0) {
+  // row `row` of the strip (with halo) -> ring[(row + 3) % 3]; out-of-image -> zeros
+  bf16(*dst)[DWR_CB] = ring[(row + 3) % 3];
+  for (int i = threadIdx.x; i < (DWR_XT + 2) * (DWR_CB / 8); i += 256) {
+    const int px = i / (DWR_CB / 8), g = i % (DWR_CB / 8);
+    const int ix = x0 - 1 + px, c = c0 + g * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row >= 0 && row < a.H && ix >= 0 && ix < a.W && c < a.C)
+      v = *reinterpret_cast<const uint4*>(a.x + (((size_t)n * a.H + row) * a.W + ix) * a.ldx + c);
+    *reinterpret_cast<uint4*>(&dst[px][g * 8]) = v;
   }
 }
-// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]: ONE pass over dy and x (the nine shifted x reads of a pixel
-// hit L1/L2), four channels per thread so that the 36 accumulators fit without spilling; block reduction in
-// dynamic shared memory [9][C], then atomics.  blockDim = (channel quads rounded up to 32, pixel lanes)
-__global__ void __launch_bounds__(512) dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
-                                                             const bf16* dy, int lddy, int dil, float* dw) {
-  extern __shared__ float s_dw[];
-  const int G4 = C >> 2;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const long long P = (long long)N * H * W;
-  float acc[9][4] = {};
-  // each block sweeps a CONTIGUOUS pixel range: the rows above / below a pixel were touched a few iterations
-  // earlier by the same block, so the nine shifted reads hit L1 instead of going back to L2
-  const long long chunk = (P + gridDim.x - 1) / gridDim.x;
-  const long long p_end = min(P, (long long)(blockIdx.x + 1) * chunk);
-  if (tx < G4)
-    for (long long p = (long long)blockIdx.x * chunk + ty; p < p_end; p += blockDim.y) {
-      const int ox = (int)(p % W), oy = (int)((p / W) % H);
-      const uint2 du = *reinterpret_cast<const uint2*>(dy + (size_t)p * lddy + tx * 4);
-      const float2 d01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du.x));
-      const float2 d23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&du.y));
+// forward (flip = 0) / data gradient (flip = 1: the filter is rotated by 180 degrees)
+__global__ void __launch_bounds__(256) dw3x3_rows_kernel(const DwRows a, const float* w, int flip, bf16* y, int ldy) {
+  __shared__ __align__(16) bf16 ring[3][DWR_XT + 2][DWR_CB];
+  const int n = blockIdx.z, x0 = blockIdx.x * DWR_XT, c0 = blockIdx.y * DWR_CB;
+  const int px = threadIdx.x >> 3, g = threadIdx.x & 7;
+  const int c = c0 + g * 8, ox = x0 + px;
+  const bool active = c < a.C && ox < a.W;
+  float wt[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const V8 v = c < a.C ? ld8f(w + (size_t)(flip ? 8 - t : t) * a.C + c) : V8{};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wt[t][i] = v.v[i];
+  }
+  dwr_load_row(ring, a, n, -1, x0, c0);
+  dwr_load_row(ring, a, n, 0, x0, c0);
+  for (int oy = 0; oy < a.H; ++oy) {
+    dwr_load_row(ring, a, n, oy + 1, x0, c0);
+    __syncthreads();
+    if (active) {
+      float acc[8] = {};
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const int iy = oy + (r - 1) * dil;
-        if (iy < 0 || iy >= H) continue;
+        const bf16(*row)[DWR_CB] = ring[(oy + r - 1 + 3) % 3];
 #pragma unroll
         for (int s2 = 0; s2 < 3; ++s2) {
-          const int ix = ox + (s2 - 1) * dil;
-          if (ix < 0 || ix >= W) continue;
-          const uint2 xu = *reinterpret_cast<const uint2*>(
-              x + (size_t)(p + (long long)(iy - oy) * W + (ix - ox)) * ldx + tx * 4);
-          const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xu.x));
-          const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xu.y));
-          float* a = acc[r * 3 + s2];
-          a[0] = fmaf(d01.x, x01.x, a[0]); a[1] = fmaf(d01.y, x01.y, a[1]);
-          a[2] = fmaf(d23.x, x23.x, a[2]); a[3] = fmaf(d23.y, x23.y, a[3]);
+          const V8 v = ld8(&row[px + s2][g * 8]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(wt[r * 3 + s2][i], v.v[i], acc[i]);
+        }
+      }
+      V8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = acc[i];
+      st8(y + (((size_t)n * a.H + oy) * a.W + ox) * ldy + c, o);
+    }
+    __syncthreads();
+  }
+}
+// weight gradient: dw[t][c] += sum over the strip of dy[p][c] * x[p + tap t][c]
+__global__ void __launch_bounds__(256) dw3x3_rows_wgrad_kernel(const DwRows a, const bf16* dy, int lddy, float* dw) {
+  __shared__ __align__(16) bf16 ring[3][DWR_XT + 2][DWR_CB];
+  __shared__ float red[9][DWR_CB];
+  const int n = blockIdx.z, x0 = blockIdx.x * DWR_XT, c0 = blockIdx.y * DWR_CB;
+  const int px = threadIdx.x >> 3, g = threadIdx.x & 7;
+  const int c = c0 + g * 8, ox = x0 + px;
+  const bool active = c < a.C && ox < a.W;
+  float acc[9][8] = {};
+  for (int i = threadIdx.x; i < 9 * DWR_CB; i += 256) (&red[0][0])[i] = 0.f;
+  dwr_load_row(ring, a, n, -1, x0, c0);
+  dwr_load_row(ring, a, n, 0, x0, c0);
+  for (int oy = 0; oy < a.H; ++oy) {
+    dwr_load_row(ring, a, n, oy + 1, x0, c0);
+    V8 d = {};
+    if (active) d = ld8(dy + (((size_t)n * a.H + oy) * a.W + ox) * lddy + c);
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const bf16(*row)[DWR_CB] = ring[(oy + r - 1 + 3) % 3];
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const V8 v = ld8(&row[px + s2][g * 8]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[r * 3 + s2][i] = fmaf(d.v[i], v.v[i], acc[r * 3 + s2][i]);
         }
       }
     }
-  for (int i = ty * blockDim.x + tx; i < 9 * C; i += blockDim.x * blockDim.y) s_dw[i] = 0.f;
-  __syncthreads();
-  if (tx < G4) {
+    __syncthreads();
+  }
+  if (active) {
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(&s_dw[t * C + tx * 4 + i], acc[t][i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(&red[t][g * 8 + i], acc[t][i]);
   }
   __syncthreads();
-  for (int i = ty * blockDim.x + tx; i < 9 * C; i += blockDim.x * blockDim.y) atomicAdd(&dw[i], s_dw[i]);
+  for (int i = threadIdx.x; i < 9 * DWR_CB; i += 256) {
+    const int t = i / DWR_CB, cc = c0 + i % DWR_CB;
+    if (cc < a.C) atomicAdd(&dw[(size_t)t * a.C + cc], (&red[0][0])[i]);
+  }
+}
+
+// dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]; blockIdx.y = filter row r (3 taps, 24 register accumulators),
+// the three launches' dy reads overlap in L2; block reduction in shared memory [3][C], then atomics
+__global__ void __launch_bounds__(256, 3) dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
+                                                             const bf16* dy, int lddy, int dil, float* dw) {
+  extern __shared__ float s_dw[];
+  const int G = C >> 3;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int r = blockIdx.y;
+  const long long P = (long long)N * H * W;
+  float acc[3][8] = {};
+  if (tx < G)
+    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y) {
+      const int ox = (int)(p % W), oy = (int)((p / W) % H);
+      const int iy = oy + (r - 1) * dil;
+      if (iy < 0 || iy >= H) continue;
+      const V8 d = ld8(dy + (size_t)p * lddy + tx * 8);
+      const bf16* xr = x + (size_t)(p + (long long)(iy - oy) * W) * ldx + tx * 8;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int ix = ox + (s2 - 1) * dil;
+        if (ix < 0 || ix >= W) continue;
+        const V8 v = ld8(xr + (long long)(ix - ox) * ldx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[s2][i] = fmaf(d.v[i], v.v[i], acc[s2][i]);
+      }
+    }
+  for (int i = ty * blockDim.x + tx; i < 3 * C; i += blockDim.x * blockDim.y) s_dw[i] = 0.f;
+  __syncthreads();
+  if (tx < G) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&s_dw[t * C + tx * 8 + i], acc[t][i]);
+  }
+  __syncthreads();
+  for (int i = ty * blockDim.x + tx; i < 3 * C; i += blockDim.x * blockDim.y) atomicAdd(&dw[(size_t)r * 3 * C + i], s_dw[i]);
 }
 
 // ---- stem im2col: fp32 NCHW [-1,1] image -> bf16 [N*Ho*Wo][KP] patches, k = (r*S + s)*3 + c --------------------
@@ -679,6 +726,11 @@ __global__ void weight_prep_kernel(const float* master, bf16* wb, bf16* wbt, con
   }
 }
 
+static int tuning_dw_rows() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AADG_DW_ROWS"); v = e ? atoi(e) : 1; }
+  return v;
+}
 static inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   return (int)std::max<long long>(1, std::min<long long>(g, 148 * 16));
@@ -830,10 +882,10 @@ int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const flo
   NN_REQ_C(c);
   AADG_REQUIRE(h <= 65535 && n <= 65535, "image too tall / batch too large for the depthwise grid");
   const size_t smem = 0;
-  if (dil == 1) {
-    dim3 grid(std::max(1, std::min((((w + 3) / 4) * (c / 8) + 127) / 128, 64)), h, n);
-    dw3x3_d1_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, wgt, direction ? -1 : 1,
-                                                              (bf16*)y, ldy);
+  if (dil == 1 && tuning_dw_rows()) {
+    DwRows a{(const bf16*)x, ldx, n, h, w, c};
+    dim3 grid((w + DWR_XT - 1) / DWR_XT, (c + DWR_CB - 1) / DWR_CB, n);
+    dw3x3_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, wgt, direction ? 1 : 0, (bf16*)y, ldy);
   } else {
     dim3 grid(std::max(1, std::min((w * (c / 8) + 255) / 256, 64)), h, n);
     dw3x3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, wgt, dil,
@@ -846,17 +898,18 @@ int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, con
   NN_REQ_C(c);
   const long long pixels = (long long)n * h * w;
   AADG_REQUIRE(pixels < (1ll << 31), "too many pixels");
-  const int bx = std::min(512, ((c / 4) + 31) / 32 * 32);
-  const dim3 blk(bx, std::max(1, 256 / bx));
-  const int blocks = (int)std::min<long long>((pixels + blk.y * 16 - 1) / (blk.y * 16), 148 * 6);
-  const size_t smem = (size_t)9 * c * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    AADG_CUDA_TRY(cudaFuncSetAttribute(dw3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 2048 * 4));
-    attr_set = true;
+  if (dil == 1 && tuning_dw_rows()) {
+    DwRows a{(const bf16*)x, ldx, n, h, w, c};
+    dim3 grid((w + DWR_XT - 1) / DWR_XT, (c + DWR_CB - 1) / DWR_CB, n);
+    dw3x3_rows_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, (const bf16*)dy, lddy, dw);
+    return check_launch("dwconv3x3 rows wgrad");
   }
-  dw3x3_wgrad_kernel<<<std::max(blocks, 1), blk, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx,
-                                                                              (const bf16*)dy, lddy, dil, dw);
+  const dim3 blk = reduce_block(c);
+  const int blocks = (int)std::min<long long>((pixels + blk.y * 16 - 1) / (blk.y * 16), 148 * 6);
+  const size_t smem = (size_t)3 * c * sizeof(float);
+  dim3 grid(std::max(blocks, 1), 3);
+  dw3x3_wgrad_kernel<<<grid, blk, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, lddy,
+                                                               dil, dw);
   return check_launch("dwconv3x3 wgrad");
 }
 
