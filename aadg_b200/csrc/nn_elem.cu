@@ -68,20 +68,29 @@ __device__ __forceinline__ unsigned int dropout_bits8(unsigned long long seed, u
   for (; p < (P); p += _sp, g += _sg, (g >= (G) ? (g -= (G), ++p) : 0))
 
 // ---- batch-norm ------------------------------------------------------------------------------------
-// grid-stride over pixels; thread (tx, ty): tx = 8-channel group, ty = pixel lane
-template <int NACC, class F>
-__device__ __forceinline__ void channel_reduce(int P, int C, float* out0, float* out1, F&& f) {
-  // f(pixel, group, acc0[8], acc1[8]) accumulates; results atomically added to out0/out1[C]
-  const int G = C >> 3;
+// Thread-stationary layout for every pass over an activation tensor: block (TX, TY) with tx = 8-channel group
+// and ty = pixel lane.  A thread keeps its group's per-channel coefficients in registers for the whole kernel
+// and walks pixels p = blockIdx.x*TY + ty + k*gridDim.x*TY, BN_U pixels per trip with every 16-byte load
+// issued before the first use (memory-level parallelism instead of per-element coefficient reloads).
+constexpr int BN_U = 4;
+
+__device__ __forceinline__ uint4 ldg16(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ V8 unpack8(const uint4& u) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  V8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
+  return r;
+}
+
+// per-thread partial sums a0/a1[8] of channel group threadIdx.x -> out0/out1[C] (shared-memory then global atomics)
+template <int NACC>
+__device__ __forceinline__ void block_channel_sum(int C, const float* a0, const float* a1, float* out0, float* out1) {
   const int tx = threadIdx.x, ty = threadIdx.y;
-  float a0[8] = {}, a1[8] = {};
-  if (tx < G)
-    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y)
-      f((int)p, tx, a0, a1);
-  __shared__ float s0[2048], s1[2048];
-  for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) { s0[i] = 0.f; s1[i] = 0.f; }
+  __shared__ float s0[2048], s1[NACC > 1 ? 2048 : 1];
+  for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) { s0[i] = 0.f; if (NACC > 1) s1[i] = 0.f; }
   __syncthreads();
-  if (tx < G) {
+  if (tx < (C >> 3)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       atomicAdd(&s0[tx * 8 + i], a0[i]);
@@ -95,12 +104,29 @@ __device__ __forceinline__ void channel_reduce(int P, int C, float* out0, float*
   }
 }
 
-__global__ void __launch_bounds__(256, 4) bn_stats_kernel(const bf16* x, int P, int C, int ld, float* sum, float* sumsq) {
-  channel_reduce<2>(P, C, sum, sumsq, [&](int p, int g, float* a0, float* a1) {
-    const V8 v = ld8(x + (size_t)p * ld + g * 8);
+__global__ void __launch_bounds__(256, 4) bn_stats_kernel(const bf16* __restrict__ x, long long P, int C, int ld,
+                                                          float* sum, float* sumsq) {
+  const int g = threadIdx.x;
+  float a0[8] = {}, a1[8] = {};
+  if (g < (C >> 3)) {
+    const long long step = (long long)gridDim.x * blockDim.y;
+    const bf16* xb = x + g * 8;
+    for (long long p0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; p0 < P; p0 += BN_U * step) {
+      uint4 xv[BN_U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a0[i] += v.v[i]; a1[i] = fmaf(v.v[i], v.v[i], a1[i]); }
-  });
+      for (int u = 0; u < BN_U; ++u) {
+        const long long p = p0 + u * step;
+        xv[u] = p < P ? ldg16(xb + p * ld) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) {
+        const V8 v = unpack8(xv[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0[i] += v.v[i]; a1[i] = fmaf(v.v[i], v.v[i], a1[i]); }
+      }
+    }
+  }
+  block_channel_sum<2>(C, a0, a1, sum, sumsq);
 }
 
 // mean / invstd, fused scale-shift for the apply pass, running statistics (momentum 0.1, unbiased var)
@@ -122,122 +148,198 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const f
 }
 
 // y = act(x*scale + shift (+ res)) (* dropout) ; flags: 1 = relu, 2 = dropout(0.5)
-__global__ void bn_apply_kernel(const bf16* x, int ldx, const float* scale, const float* shift, const bf16* res,
-                                int ldr, bf16* y, int ldy, long long P, int C, int flags,
-                                unsigned long long seed, unsigned char* relu_bits) {
-  const int G = C >> 3;
-  AADG_FOR_PIXEL_GROUPS(P, G, p, g) {
-    const long long e = p * G + g;
-    V8 v = ld8(x + p * ldx + g * 8);
-    const V8 sc = ld8f(scale + g * 8), sh = ld8f(shift + g * 8);
+__global__ void __launch_bounds__(256, 3) bn_apply_kernel(const bf16* __restrict__ x, int ldx, const float* scale,
+                                                          const float* shift, const bf16* __restrict__ res, int ldr,
+                                                          bf16* __restrict__ y, int ldy, long long P, int C, int flags,
+                                                          unsigned long long seed, unsigned char* relu_bits) {
+  const int G = C >> 3, g = threadIdx.x;
+  if (g >= G) return;
+  const V8 sc = ld8f(scale + g * 8), sh = ld8f(shift + g * 8);
+  const long long step = (long long)gridDim.x * blockDim.y;
+  for (long long p0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; p0 < P; p0 += BN_U * step) {
+    uint4 xv[BN_U], rv[BN_U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v.v[i] = fmaf(v.v[i], sc.v[i], sh.v[i]);
-    if (res) {
-      const V8 r = ld8(res + p * ldr + g * 8);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v.v[i] += r.v[i];
-    }
-    if (flags & 1) {
-      if (relu_bits) {      // one byte per 8 channels: backward reads it instead of the whole output tensor
-        unsigned int bits = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bits |= (v.v[i] > 0.f ? 1u : 0u) << i;
-        relu_bits[e] = (unsigned char)bits;
+    for (int u = 0; u < BN_U; ++u) {
+      const long long p = p0 + u * step;
+      if (p < P) {
+        xv[u] = ldg16(x + p * ldx + g * 8);
+        if (res) rv[u] = ldg16(res + p * ldr + g * 8);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(v.v[i], 0.f);
     }
-    if (flags & 2) {
-      const unsigned int keep = dropout_bits8(seed, (unsigned long long)e * 8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v.v[i] = (keep >> i) & 1 ? v.v[i] * 2.f : 0.f;
+    for (int u = 0; u < BN_U; ++u) {
+      const long long p = p0 + u * step;
+      if (p >= P) break;
+      const long long e = p * G + g;
+      V8 v = unpack8(xv[u]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] = fmaf(v.v[i], sc.v[i], sh.v[i]);
+      if (res) {
+        const V8 r = unpack8(rv[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.v[i] += r.v[i];
+      }
+      if (flags & 1) {
+        if (relu_bits) {      // one byte per 8 channels: backward reads it instead of the whole output tensor
+          unsigned int bits = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bits |= (v.v[i] > 0.f ? 1u : 0u) << i;
+          relu_bits[e] = (unsigned char)bits;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(v.v[i], 0.f);
+      }
+      if (flags & 2) {
+        const unsigned int keep = dropout_bits8(seed, (unsigned long long)e * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.v[i] = (keep >> i) & 1 ? v.v[i] * 2.f : 0.f;
+      }
+      st8(y + p * ldy + g * 8, v);
     }
-    st8(y + p * ldy + g * 8, v);
   }
 }
 
-// g = dy * relu'(y) * dropout ; dbeta = sum g ; dgamma = sum g * xhat
-__global__ void __launch_bounds__(256, 4) bn_bwd_reduce_kernel(const bf16* dy, int lddy, const bf16* x, int ldx, const bf16* y, int ldy,
-                                     const float* mean, const float* invstd, const float* gamma,
-                                     const float* beta, int P, int C, int flags, unsigned long long seed,
-                                     float* dgamma, float* dbeta) {
-  const int G = C >> 3;
-  channel_reduce<2>(P, C, dgamma, dbeta, [&](int p, int g, float* a0, float* a1) {
-    V8 d = ld8(dy + (size_t)p * lddy + g * 8);
-    const V8 xv = ld8(x + (size_t)p * ldx + g * 8);
-    if (flags & 4) {
-      // no residual: relu(x*scale + shift) > 0 recomputed exactly as forward evaluated it (`beta` = saved shift)
-      const V8 is = ld8f(invstd + g * 8), ga = ld8f(gamma + g * 8), sh = ld8f(beta + g * 8);
+// The gradient that reaches the batch-norm output: g = dy * relu'(.) * dropout.  Mask source by flag:
+// 4 = recomputed from x exactly as forward evaluated it, 8 = bit mask (one byte per 8 channels), 1 = y tensor.
+// MASK (template) = 0 none, 4, 8 or 1; the runtime flag 2 adds dropout.
+template <int MASK> struct BnMaskSrc { };
+template <> struct BnMaskSrc<8> { unsigned int b; };
+template <> struct BnMaskSrc<1> { uint4 v; };
+template <int MASK>
+__device__ __forceinline__ void bn_mask_load(BnMaskSrc<MASK>& m, const bf16* y, int ldy, long long p, int G, int g) {
+  if constexpr (MASK == 8) m.b = reinterpret_cast<const unsigned char*>(y)[p * G + g];
+  if constexpr (MASK == 1) m.v = ldg16(y + p * ldy + g * 8);
+}
+template <int MASK>
+__device__ __forceinline__ void bn_mask_apply(V8& d, const V8& xv, const V8& sc, const V8& sh, const BnMaskSrc<MASK>& m,
+                                              int flags, unsigned long long seed, long long e) {
+  if constexpr (MASK == 4) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d.v[i] = fmaf(xv.v[i], ga.v[i] * is.v[i], sh.v[i]) > 0.f ? d.v[i] : 0.f;
-    } else if (flags & 8) {
-      const unsigned int bits = reinterpret_cast<const unsigned char*>(y)[(size_t)p * G + g];
+    for (int i = 0; i < 8; ++i) d.v[i] = fmaf(xv.v[i], sc.v[i], sh.v[i]) > 0.f ? d.v[i] : 0.f;
+  }
+  if constexpr (MASK == 8) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d.v[i] = (bits >> i) & 1 ? d.v[i] : 0.f;
-    } else if (flags & 1) {
-      const V8 yv = ld8(y + (size_t)p * ldy + g * 8);
+    for (int i = 0; i < 8; ++i) d.v[i] = (m.b >> i) & 1 ? d.v[i] : 0.f;
+  }
+  if constexpr (MASK == 1) {
+    const V8 yv = unpack8(m.v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
-    }
-    if (flags & 2) {
-      const unsigned int keep = dropout_bits8(seed, ((unsigned long long)p * G + g) * 8);
+    for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
+  }
+  if (flags & 2) {
+    const unsigned int keep = dropout_bits8(seed, (unsigned long long)e * 8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d.v[i] = (keep >> i) & 1 ? d.v[i] * 2.f : 0.f;
-    }
+    for (int i = 0; i < 8; ++i) d.v[i] = (keep >> i) & 1 ? d.v[i] * 2.f : 0.f;
+  }
+}
+
+// dbeta = sum g ; dgamma = sum g * xhat  (`beta` = the forward shift vector when flag 4 is set)
+template <int MASK>
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, int lddy,
+                                                               const bf16* __restrict__ x, int ldx, const bf16* y, int ldy,
+                                                               const float* mean, const float* invstd, const float* gamma,
+                                                               const float* beta, long long P, int C, int flags,
+                                                               unsigned long long seed, float* dgamma, float* dbeta) {
+  const int G = C >> 3, g = threadIdx.x;
+  float a0[8] = {}, a1[8] = {};
+  if (g < G) {
     const V8 m = ld8f(mean + g * 8), is = ld8f(invstd + g * 8);
+    V8 sc = {}, sh = {};
+    if (MASK == 4) {
+      const V8 ga = ld8f(gamma + g * 8);
+      sh = ld8f(beta + g * 8);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a0[i] = fmaf(d.v[i], (xv.v[i] - m.v[i]) * is.v[i], a0[i]); a1[i] += d.v[i]; }
-  });
+      for (int i = 0; i < 8; ++i) sc.v[i] = ga.v[i] * is.v[i];
+    }
+    const long long step = (long long)gridDim.x * blockDim.y;
+    for (long long p0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; p0 < P; p0 += BN_U * step) {
+      uint4 dv[BN_U], xv[BN_U];
+      BnMaskSrc<MASK> mv[BN_U];
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) {
+        const long long p = p0 + u * step;
+        if (p < P) {
+          dv[u] = ldg16(dy + p * lddy + g * 8);
+          xv[u] = ldg16(x + p * ldx + g * 8);
+          bn_mask_load(mv[u], y, ldy, p, G, g);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BN_U; ++u) {
+        const long long p = p0 + u * step;
+        if (p >= P) break;
+        V8 d = unpack8(dv[u]);
+        const V8 xx = unpack8(xv[u]);
+        bn_mask_apply(d, xx, sc, sh, mv[u], flags, seed, p * G + g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a0[i] = fmaf(d.v[i], xx.v[i] - m.v[i], a0[i]); a1[i] += d.v[i]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] *= is.v[i];
+  }
+  block_channel_sum<2>(C, a0, a1, dgamma, dbeta);
 }
 
 // dx = gamma*invstd * (g - dbeta/P - xhat*dgamma/P) ; optional dres = g (gradient of the residual input)
-__global__ void bn_bwd_apply_kernel(const bf16* dy, int lddy, const bf16* x, int ldx, const bf16* y, int ldy,
-                                    const float* mean, const float* invstd, const float* gamma, const float* beta,
-                                    const float* dgamma, const float* dbeta, long long P, int C, int flags,
-                                    unsigned long long seed, bf16* dx, int lddx, bf16* dres, int lddr,
-                                    int dres_accumulate) {
-  const int G = C >> 3;
+template <int MASK>
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __restrict__ dy, int lddy,
+                                                              const bf16* __restrict__ x, int ldx, const bf16* y, int ldy,
+                                                              const float* mean, const float* invstd, const float* gamma,
+                                                              const float* beta, const float* dgamma, const float* dbeta,
+                                                              long long P, int C, int flags, unsigned long long seed,
+                                                              bf16* __restrict__ dx, int lddx, bf16* dres, int lddr,
+                                                              int dres_accumulate) {
+  const int G = C >> 3, g = threadIdx.x;
+  if (g >= G) return;
   const float invP = 1.f / (float)P;
-  AADG_FOR_PIXEL_GROUPS(P, G, p, g) {
-    const long long e = p * G + g;
-    V8 d = ld8(dy + p * lddy + g * 8);
-    const V8 xv = ld8(x + p * ldx + g * 8);
-    const V8 m = ld8f(mean + g * 8), is = ld8f(invstd + g * 8), ga = ld8f(gamma + g * 8);
-    if (flags & 4) {
-      const V8 sh = ld8f(beta + g * 8);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d.v[i] = fmaf(xv.v[i], ga.v[i] * is.v[i], sh.v[i]) > 0.f ? d.v[i] : 0.f;
-    } else if (flags & 8) {
-      const unsigned int bits = reinterpret_cast<const unsigned char*>(y)[e];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d.v[i] = (bits >> i) & 1 ? d.v[i] : 0.f;
-    } else if (flags & 1) {
-      const V8 yv = ld8(y + p * ldy + g * 8);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
-    }
-    if (flags & 2) {
-      const unsigned int keep = dropout_bits8(seed, (unsigned long long)e * 8);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d.v[i] = (keep >> i) & 1 ? d.v[i] * 2.f : 0.f;
-    }
-    if (dres) {
-      V8 r = d;
-      if (dres_accumulate) {
-        const V8 o = ld8(dres + p * lddr + g * 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r.v[i] += o.v[i];
-      }
-      st8(dres + p * lddr + g * 8, r);
-    }
-    const V8 dg = ld8f(dgamma + g * 8), db = ld8f(dbeta + g * 8);
-    V8 o;
+  // dx = sc*g + kk + bb*(x - mean):  sc = gamma*invstd, bb = -sc*invstd*dgamma/P, kk = -sc*dbeta/P
+  const V8 m = ld8f(mean + g * 8);
+  V8 sc, sh = {}, bb, kk;
+  {
+    const V8 is = ld8f(invstd + g * 8), ga = ld8f(gamma + g * 8), dg = ld8f(dgamma + g * 8), db = ld8f(dbeta + g * 8);
+    if (MASK == 4) sh = ld8f(beta + g * 8);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float xh = (xv.v[i] - m.v[i]) * is.v[i];
-      o.v[i] = ga.v[i] * is.v[i] * (d.v[i] - db.v[i] * invP - xh * dg.v[i] * invP);
+      sc.v[i] = ga.v[i] * is.v[i];
+      bb.v[i] = -sc.v[i] * is.v[i] * dg.v[i] * invP;
+      kk.v[i] = -sc.v[i] * db.v[i] * invP;
     }
-    st8(dx + p * lddx + g * 8, o);
+  }
+  const long long step = (long long)gridDim.x * blockDim.y;
+  for (long long p0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; p0 < P; p0 += BN_U * step) {
+    uint4 dv[BN_U], xv[BN_U];
+    BnMaskSrc<MASK> mv[BN_U];
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+      const long long p = p0 + u * step;
+      if (p < P) {
+        dv[u] = ldg16(dy + p * lddy + g * 8);
+        xv[u] = ldg16(x + p * ldx + g * 8);
+        bn_mask_load(mv[u], y, ldy, p, G, g);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BN_U; ++u) {
+      const long long p = p0 + u * step;
+      if (p >= P) break;
+      V8 d = unpack8(dv[u]);
+      const V8 xx = unpack8(xv[u]);
+      bn_mask_apply(d, xx, sc, sh, mv[u], flags, seed, p * G + g);
+      if (dres) {
+        V8 r = d;
+        if (dres_accumulate) {
+          const V8 o = ld8(dres + p * lddr + g * 8);    // rare path: not prefetched
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r.v[i] += o.v[i];
+        }
+        st8(dres + p * lddr + g * 8, r);
+      }
+      V8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = fmaf(bb.v[i], xx.v[i] - m.v[i], fmaf(sc.v[i], d.v[i], kk.v[i]));
+      st8(dx + p * lddx + g * 8, o);
+    }
   }
 }
 
@@ -726,6 +828,16 @@ __global__ void weight_prep_kernel(const float* master, bf16* wb, bf16* wbt, con
   }
 }
 
+static int num_sms_nn() {
+  static int v = 0;
+  if (!v) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+  }
+  return v;
+}
 static int tuning_dw_rows() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("AADG_DW_ROWS"); v = e ? atoi(e) : 1; }
@@ -740,6 +852,12 @@ static inline dim3 reduce_block(int C) {
   while (tx < (C >> 3)) tx <<= 1;
   tx = std::min(tx, 256);
   return dim3(tx, 256 / tx);
+}
+// grid of a thread-stationary streaming pass: `per_sm` resident blocks on every SM, never more blocks than there
+// are BN_U-pixel trips to hand out
+static inline int stream_blocks(long long pixels, dim3 blk, int per_sm) {
+  const long long trips = (pixels + (long long)blk.y * BN_U - 1) / ((long long)blk.y * BN_U);
+  return (int)std::max<long long>(1, std::min<long long>(trips, (long long)num_sms_nn() * per_sm));
 }
 
 }  // namespace nn
@@ -756,8 +874,7 @@ int aadg_bn_stats(const void* x, long long pixels, int c, int ld, float* sum, fl
   NN_REQ_C(c);
   AADG_REQUIRE(pixels > 0 && pixels < (1ll << 31), "bad pixel count");
   const dim3 blk = reduce_block(c);
-  const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 8);
-  bn_stats_kernel<<<std::max(blocks, 1), blk, 0, (cudaStream_t)stream>>>((const bf16*)x, (int)pixels, c, ld, sum, sumsq);
+  bn_stats_kernel<<<stream_blocks(pixels, blk, 4), blk, 0, (cudaStream_t)stream>>>((const bf16*)x, pixels, c, ld, sum, sumsq);
   return check_launch("bn_stats");
 }
 
@@ -773,7 +890,8 @@ int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift
                   int ldy, long long pixels, int c, int flags, unsigned long long seed, void* relu_bits,
                   void* stream) {
   NN_REQ_C(c);
-  bn_apply_kernel<<<grid_for(pixels * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+  const dim3 blk = reduce_block(c);
+  bn_apply_kernel<<<stream_blocks(pixels, blk, 3), blk, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, ldx, scale, shift, (const bf16*)res, ldr, (bf16*)y, ldy, pixels, c, flags, seed,
       (unsigned char*)relu_bits);
   return check_launch("bn_apply");
@@ -789,15 +907,20 @@ int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const voi
   AADG_CUDA_TRY(cudaMemsetAsync(dgamma, 0, sizeof(float) * c, st));
   AADG_CUDA_TRY(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
   const dim3 blk = reduce_block(c);
-  const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 8);
   AADG_REQUIRE(!(flags & 1) || (flags & 4) || y, "ReLU mask needs y / the bit mask (or flag 4 to recompute it from x)");
   AADG_REQUIRE(!(flags & 4) || shift, "flag 4 needs the forward shift vector");
-  bn_bwd_reduce_kernel<<<std::max(blocks, 1), blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y,
-                                                           ldy, mean, invstd, gamma, shift, (int)pixels, c, flags, seed,
-                                                           dgamma, dbeta);
-  bn_bwd_apply_kernel<<<grid_for(pixels * (c / 8)), 256, 0, st>>>(
-      (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y, ldy, mean, invstd, gamma, shift, dgamma, dbeta, pixels, c,
-      flags, seed, (bf16*)dx, lddx, (bf16*)dres, lddr, dres_accumulate);
+  const int mask = (flags & 4) ? 4 : (flags & 8) ? 8 : (flags & 1) ? 1 : 0;
+  const int grid = stream_blocks(pixels, blk, 2);
+#define AADG_BN_BWD(MASK)                                                                                             \
+  {                                                                                                                   \
+    bn_bwd_reduce_kernel<MASK><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y, ldy,  \
+                                                     mean, invstd, gamma, shift, pixels, c, flags, seed, dgamma, dbeta); \
+    bn_bwd_apply_kernel<MASK><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y, ldy,   \
+                                                    mean, invstd, gamma, shift, dgamma, dbeta, pixels, c, flags, seed, \
+                                                    (bf16*)dx, lddx, (bf16*)dres, lddr, dres_accumulate);              \
+  }
+  if (mask == 4) AADG_BN_BWD(4) else if (mask == 8) AADG_BN_BWD(8) else if (mask == 1) AADG_BN_BWD(1) else AADG_BN_BWD(0)
+#undef AADG_BN_BWD
   return check_launch("bn_backward");
 }
 
