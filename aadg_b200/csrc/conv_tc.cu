@@ -40,7 +40,7 @@ EncodeTiledFn encode_fn() {
 }
 
 int make_map_bf16(CUtensorMap* map, const void* base, int rank, const long long* dims,
-                  const long long* strides_elems, const int* box, const int* elem_strides) {
+                  const long long* strides_elems, const int* box, const int* elem_strides, bool swizzle128) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return AADG_ECUDA; }
   cuuint64_t gd[5], gs[5];
@@ -52,7 +52,8 @@ int make_map_bf16(CUtensorMap* map, const void* base, int rank, const long long*
     if (i > 0) gs[i - 1] = (cuuint64_t)strides_elems[i - 1] * 2;
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %lld %lld %lld %lld box %d %d %d %d", (int)r, rank,

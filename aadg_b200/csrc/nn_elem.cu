@@ -390,40 +390,59 @@ __global__ void maxpool_fwd_kernel(const bf16* x, int N, int H, int W, int C, bf
     *reinterpret_cast<uint2*>(arg + o) = packed;
   }
 }
-// gather form: input pixel (iy,ix) collects dy of every window whose arg-max it is
-__global__ void maxpool_bwd_kernel(const bf16* dy, const unsigned char* arg, int N, int H, int W, int C, int Ho,
-                                   int Wo, bf16* dx) {
+// gather form, one thread per 2x2 block of input pixels (rows 2i, 2i+1; columns 2j, 2j+1) x 8 channels: the block
+// is covered by exactly the four windows (i..i+1, j..j+1), each loaded once; input pixel (2i+a, 2j+b) is tap
+// (r, s) = (1 + a - 2di, 1 + b - 2dj) of window (i + di, j + dj) whenever that tap index is in 0..2.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const bf16* __restrict__ dy, const unsigned char* __restrict__ arg,
+                                                          int N, int H, int W, int C, int Ho, int Wo, bf16* __restrict__ dx) {
   const int G = C >> 3;
-  const long long total = (long long)N * H * W * G;
+  const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;
+  const long long total = (long long)N * Hb * Wb * G;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(e % G);
     long long p = e / G;
-    const int ix = (int)(p % W); p /= W;
-    const int iy = (int)(p % H);
-    const int n = (int)(p / H);
-    V8 acc;
+    const int j = (int)(p % Wb); p /= Wb;
+    const int i = (int)(p % Hb);
+    const int n = (int)(p / Hb);
+    uint4 dv[2][2];
+    uint2 av[2][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
-    for (int oy = (iy) / 2; oy <= (iy + 1) / 2; ++oy) {
-      if (oy >= Ho) continue;
-      const int r = iy - (oy * 2 - 1);
-      if (r < 0 || r > 2) continue;
-      for (int ox = (ix) / 2; ox <= (ix + 1) / 2; ++ox) {
-        if (ox >= Wo) continue;
-        const int s = ix - (ox * 2 - 1);
-        if (s < 0 || s > 2) continue;
-        const size_t o = (((size_t)n * Ho + oy) * Wo + ox) * C + g * 8;
-        const uint2 packed = *reinterpret_cast<const uint2*>(arg + o);
-        const V8 d = ld8(dy + o);
-        const int code = r * 3 + s;
+    for (int di = 0; di < 2; ++di)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int a = ((i < 4 ? packed.x : packed.y) >> ((i & 3) * 8)) & 0xff;
-          if (a == code) acc.v[i] += d.v[i];
+      for (int dj = 0; dj < 2; ++dj) {
+        dv[di][dj] = make_uint4(0, 0, 0, 0);
+        av[di][dj] = make_uint2(0xffffffffu, 0xffffffffu);          // no tap has code 255
+        if (i + di < Ho && j + dj < Wo) {
+          const size_t o = (((size_t)n * Ho + i + di) * Wo + j + dj) * C + g * 8;
+          dv[di][dj] = __ldg(reinterpret_cast<const uint4*>(dy + o));
+          av[di][dj] = __ldg(reinterpret_cast<const uint2*>(arg + o));
         }
       }
-    }
-    st8(dx + (((size_t)n * H + iy) * W + ix) * C + g * 8, acc);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int iy = 2 * i + a, ix = 2 * j + b;
+        if (iy >= H || ix >= W) continue;
+        V8 acc;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
+#pragma unroll
+        for (int di = 0; di < 2; ++di)
+#pragma unroll
+          for (int dj = 0; dj < 2; ++dj) {
+            const int r = 1 + a - 2 * di, s2 = 1 + b - 2 * dj;
+            if (r < 0 || r > 2 || s2 < 0 || s2 > 2) continue;       // resolved at compile time
+            const unsigned int code = (unsigned int)(r * 3 + s2);
+            const V8 d = unpack8(dv[di][dj]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const unsigned int am = ((q < 4 ? av[di][dj].x : av[di][dj].y) >> ((q & 3) * 8)) & 0xffu;
+              if (am == code) acc.v[q] += d.v[q];
+            }
+          }
+        st8(dx + (((size_t)n * H + iy) * W + ix) * C + g * 8, acc);
+      }
   }
 }
 
@@ -435,31 +454,55 @@ __device__ __forceinline__ void src_index(int o, float scale, int in, int& i0, i
   i1 = min(i0 + 1, in - 1);
   lam = s - (float)i0;
 }
-__global__ void upsample_fwd_kernel(const bf16* x, int N, int H, int W, int C, int ldx, bf16* y, int Ho, int Wo, int ldy) {
+// forward: a thread produces 4 consecutive output pixels of one row x 8 channels; they share the two source rows
+// and (for scale factors >= 2) at most 3 source columns, cached in registers between consecutive outputs
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int ldx,
+                                                           bf16* __restrict__ y, int Ho, int Wo, int ldy) {
   const int G = C >> 3;
   const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
-  const long long total = (long long)N * Ho * Wo * G;
+  const int Wq = (Wo + 3) >> 2;
+  const long long total = (long long)N * Ho * Wq * G;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(e % G);
     long long p = e / G;
-    const int ox = (int)(p % Wo); p /= Wo;
+    const int oq = (int)(p % Wq); p /= Wq;
     const int oy = (int)(p % Ho);
     const int n = (int)(p / Ho);
-    int y0, y1, x0, x1; float ly, lx;
+    int y0, y1; float ly;
     src_index(oy, sy, H, y0, y1, ly);
-    src_index(ox, sx, W, x0, x1, lx);
-    const bf16* b = x + (size_t)n * H * W * ldx + g * 8;
-    const V8 v00 = ld8(b + ((size_t)y0 * W + x0) * ldx), v01 = ld8(b + ((size_t)y0 * W + x1) * ldx);
-    const V8 v10 = ld8(b + ((size_t)y1 * W + x0) * ldx), v11 = ld8(b + ((size_t)y1 * W + x1) * ldx);
-    V8 o;
+    const bf16* r0 = x + ((size_t)n * H + y0) * W * ldx + g * 8;
+    const bf16* r1 = x + ((size_t)n * H + y1) * W * ldx + g * 8;
+    auto column = [&](int xx) {      // source column xx blended between the two source rows
+      const V8 a = unpack8(ldg16(r0 + (size_t)xx * ldx)), b = unpack8(ldg16(r1 + (size_t)xx * ldx));
+      V8 o;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      o.v[i] = (1.f - ly) * ((1.f - lx) * v00.v[i] + lx * v01.v[i]) + ly * ((1.f - lx) * v10.v[i] + lx * v11.v[i]);
-    st8(y + (((size_t)n * Ho + oy) * Wo + ox) * ldy + g * 8, o);
+      for (int i = 0; i < 8; ++i) o.v[i] = (1.f - ly) * a.v[i] + ly * b.v[i];
+      return o;
+    };
+    int hx0 = -1, hx1 = -1;
+    V8 h0, h1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ox = oq * 4 + q;
+      if (ox >= Wo) break;
+      int x0, x1; float lx;
+      src_index(ox, sx, W, x0, x1, lx);
+      V8 a, b;
+      if (x0 == hx0) a = h0; else if (x0 == hx1) a = h1; else a = column(x0);
+      if (x1 == x0) b = a; else if (x1 == hx1) b = h1; else if (x1 == hx0) b = h0; else b = column(x1);
+      h0 = a; hx0 = x0; h1 = b; hx1 = x1;
+      V8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = (1.f - lx) * a.v[i] + lx * b.v[i];
+      st8(y + (((size_t)n * Ho + oy) * Wo + ox) * ldy + g * 8, o);
+    }
   }
 }
-// gather form of the transpose: input pixel collects from every output pixel that samples it
-__global__ void upsample_bwd_kernel(const bf16* dy, int N, int Ho, int Wo, int C, int lddy, bf16* dx, int H, int W, int lddx) {
+// gather form of the transpose: input pixel collects from every output pixel that samples it.  The column weights
+// of the (at most UPB_MAX) candidate output columns are computed once per thread, not once per candidate row.
+constexpr int UPB_MAX = 12;
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const bf16* __restrict__ dy, int N, int Ho, int Wo, int C, int lddy,
+                                                           bf16* __restrict__ dx, int H, int W, int lddx) {
   const int G = C >> 3;
   const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
   const long long total = (long long)N * H * W * G;
@@ -477,24 +520,43 @@ __global__ void upsample_bwd_kernel(const bf16* dy, int N, int Ho, int Wo, int C
     V8 acc;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-      int y0, y1; float ly;
-      src_index(oy, sy, H, y0, y1, ly);
-      float wy = 0.f;
-      if (y0 == iy) wy += 1.f - ly;
-      if (y1 == iy) wy += ly;
-      if (wy == 0.f) continue;
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        int x0, x1; float lx;
-        src_index(ox, sx, W, x0, x1, lx);
-        float wx = 0.f;
-        if (x0 == ix) wx += 1.f - lx;
-        if (x1 == ix) wx += lx;
-        if (wx == 0.f) continue;
-        const V8 d = ld8(dy + (((size_t)n * Ho + oy) * Wo + ox) * lddy + g * 8);
-        const float wgt = wy * wx;
+    auto weight = [](int o, float scale, int in, int i) {
+      int a0, a1; float l;
+      src_index(o, scale, in, a0, a1, l);
+      float wgt = 0.f;
+      if (a0 == i) wgt += 1.f - l;
+      if (a1 == i) wgt += l;
+      return wgt;
+    };
+    if (ox_hi - ox_lo < UPB_MAX) {
+      float wx[UPB_MAX];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wgt, d.v[i], acc.v[i]);
+      for (int j = 0; j < UPB_MAX; ++j) wx[j] = ox_lo + j <= ox_hi ? weight(ox_lo + j, sx, W, ix) : 0.f;
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        const float wy = weight(oy, sy, H, iy);
+        if (wy == 0.f) continue;
+        const bf16* row = dy + (((size_t)n * Ho + oy) * Wo + ox_lo) * lddy + g * 8;
+#pragma unroll
+        for (int j = 0; j < UPB_MAX; ++j) {
+          if (wx[j] == 0.f) continue;
+          const V8 d = unpack8(ldg16(row + (size_t)j * lddy));
+          const float wgt = wy * wx[j];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wgt, d.v[i], acc.v[i]);
+        }
+      }
+    } else {
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        const float wy = weight(oy, sy, H, iy);
+        if (wy == 0.f) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          const float wxx = weight(ox, sx, W, ix);
+          if (wxx == 0.f) continue;
+          const V8 d = ld8(dy + (((size_t)n * Ho + oy) * Wo + ox) * lddy + g * 8);
+          const float wgt = wy * wxx;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wgt, d.v[i], acc.v[i]);
+        }
       }
     }
     st8(dx + (((size_t)n * H + iy) * W + ix) * lddx + g * 8, acc);
@@ -612,112 +674,6 @@ __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
     st8(yrow + (size_t)ox * ldy + g * 8, acc);
   }
 }
-// ---- dilation-1 depthwise 3x3 with a rolling three-row window in shared memory --------------------------------
-// block = (image, 32-pixel column strip, 64-channel chunk) walking down all rows: every input element is read
-// from global memory once (plus the 2-pixel halo), the nine taps come from shared memory (conflict-free 16-byte
-// reads), the thread's 9 x 8 filter taps (forward / data gradient) or 9 x 8 accumulators (weight gradient) live
-// in registers.  256 threads = 32 pixels x 8 channel groups.
-constexpr int DWR_XT = 32, DWR_CB = 64;
-struct DwRows {
-  const bf16* x; int ldx;
-  int N, H, W, C;
-};
-__device__ __forceinline__ void dwr_load_row(bf16 (*ring)[DWR_XT + 2][DWR_CB], const DwRows& a, int n, int row, int x0,
-                                             int c0) {
-  // row `row` of the strip (with halo) -> ring[(row + 3) % 3]; out-of-image -> zeros
-  bf16(*dst)[DWR_CB] = ring[(row + 3) % 3];
-  for (int i = threadIdx.x; i < (DWR_XT + 2) * (DWR_CB / 8); i += 256) {
-    const int px = i / (DWR_CB / 8), g = i % (DWR_CB / 8);
-    const int ix = x0 - 1 + px, c = c0 + g * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row >= 0 && row < a.H && ix >= 0 && ix < a.W && c < a.C)
-      v = *reinterpret_cast<const uint4*>(a.x + (((size_t)n * a.H + row) * a.W + ix) * a.ldx + c);
-    *reinterpret_cast<uint4*>(&dst[px][g * 8]) = v;
-  }
-}
-// forward (flip = 0) / data gradient (flip = 1: the filter is rotated by 180 degrees)
-__global__ void __launch_bounds__(256) dw3x3_rows_kernel(const DwRows a, const float* w, int flip, bf16* y, int ldy) {
-  __shared__ __align__(16) bf16 ring[3][DWR_XT + 2][DWR_CB];
-  const int n = blockIdx.z, x0 = blockIdx.x * DWR_XT, c0 = blockIdx.y * DWR_CB;
-  const int px = threadIdx.x >> 3, g = threadIdx.x & 7;
-  const int c = c0 + g * 8, ox = x0 + px;
-  const bool active = c < a.C && ox < a.W;
-  float wt[9][8];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const V8 v = c < a.C ? ld8f(w + (size_t)(flip ? 8 - t : t) * a.C + c) : V8{};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) wt[t][i] = v.v[i];
-  }
-  dwr_load_row(ring, a, n, -1, x0, c0);
-  dwr_load_row(ring, a, n, 0, x0, c0);
-  for (int oy = 0; oy < a.H; ++oy) {
-    dwr_load_row(ring, a, n, oy + 1, x0, c0);
-    __syncthreads();
-    if (active) {
-      float acc[8] = {};
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const bf16(*row)[DWR_CB] = ring[(oy + r - 1 + 3) % 3];
-#pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) {
-          const V8 v = ld8(&row[px + s2][g * 8]);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(wt[r * 3 + s2][i], v.v[i], acc[i]);
-        }
-      }
-      V8 o;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = acc[i];
-      st8(y + (((size_t)n * a.H + oy) * a.W + ox) * ldy + c, o);
-    }
-    __syncthreads();
-  }
-}
-// weight gradient: dw[t][c] += sum over the strip of dy[p][c] * x[p + tap t][c]
-__global__ void __launch_bounds__(256) dw3x3_rows_wgrad_kernel(const DwRows a, const bf16* dy, int lddy, float* dw) {
-  __shared__ __align__(16) bf16 ring[3][DWR_XT + 2][DWR_CB];
-  __shared__ float red[9][DWR_CB];
-  const int n = blockIdx.z, x0 = blockIdx.x * DWR_XT, c0 = blockIdx.y * DWR_CB;
-  const int px = threadIdx.x >> 3, g = threadIdx.x & 7;
-  const int c = c0 + g * 8, ox = x0 + px;
-  const bool active = c < a.C && ox < a.W;
-  float acc[9][8] = {};
-  for (int i = threadIdx.x; i < 9 * DWR_CB; i += 256) (&red[0][0])[i] = 0.f;
-  dwr_load_row(ring, a, n, -1, x0, c0);
-  dwr_load_row(ring, a, n, 0, x0, c0);
-  for (int oy = 0; oy < a.H; ++oy) {
-    dwr_load_row(ring, a, n, oy + 1, x0, c0);
-    V8 d = {};
-    if (active) d = ld8(dy + (((size_t)n * a.H + oy) * a.W + ox) * lddy + c);
-    __syncthreads();
-    if (active) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const bf16(*row)[DWR_CB] = ring[(oy + r - 1 + 3) % 3];
-#pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) {
-          const V8 v = ld8(&row[px + s2][g * 8]);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[r * 3 + s2][i] = fmaf(d.v[i], v.v[i], acc[r * 3 + s2][i]);
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (active) {
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&red[t][g * 8 + i], acc[t][i]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 9 * DWR_CB; i += 256) {
-    const int t = i / DWR_CB, cc = c0 + i % DWR_CB;
-    if (cc < a.C) atomicAdd(&dw[(size_t)t * a.C + cc], (&red[0][0])[i]);
-  }
-}
-
 // dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]; blockIdx.y = filter row r (3 taps, 24 register accumulators),
 // the three launches' dy reads overlap in L2; block reduction in shared memory [3][C], then atomics
 __global__ void __launch_bounds__(256, 3) dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
@@ -795,6 +751,51 @@ __global__ void im2col_stem_kernel(const float* img, int N, int H, int W, int R,
   }
 }
 
+// Row-pitched patch layout k = r*RP + s*3 + c (RP a multiple of 8, >= 3*S): the 3*S values of one filter row are
+// contiguous in an [x][c]-interleaved staged image row, so a (pixel, filter row) unit is a copy of RP/2 32-bit
+// words from shared memory (tail masked to zero) into RP/8 aligned 16-byte stores -- no per-element index table.
+// One CTA per (image, output row); stride must be even (word-aligned source runs).
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const float* __restrict__ img, int N, int H, int W, int R, int S,
+                                                          int stride, int pad, int Ho, int Wo, int RP, int KP,
+                                                          bf16* __restrict__ col) {
+  extern __shared__ bf16 s_rows[];                   // [R][WP*3 (+1 to keep rows word aligned)]
+  const int oy = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  const int WP = W + 2 * pad;
+  const int pitch = (WP * 3 + RP + 1) & ~1;          // elements; the slack keeps the last pixel's masked tail in bounds
+  for (int e = threadIdx.x; e < R * pitch; e += blockDim.x) s_rows[e] = __float2bfloat16_rn(0.f);
+  __syncthreads();
+  for (int rc = 0; rc < R * 3; ++rc) {
+    const int r = rc / 3, c = rc - r * 3;
+    const int iy = oy * stride - pad + r;
+    if (iy < 0 || iy >= H) continue;
+    const float* src = img + (((size_t)n * 3 + c) * H + iy) * W;
+    bf16* dst = s_rows + r * pitch + pad * 3 + c;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) dst[x * 3] = __float2bfloat16_rn(__ldg(src + x));
+  }
+  __syncthreads();
+  const int groups = RP >> 3, valid = S * 3;
+  bf16* orow = col + ((size_t)n * Ho + oy) * Wo * KP;
+  for (int u = threadIdx.x; u < Wo * R * groups; u += blockDim.x) {
+    const int q = u % groups, t = u / groups;
+    const int r = t % R, ox = t / R;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(s_rows + r * pitch + ox * stride * 3) + q * 4;
+    uint32_t wv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = q * 8 + 2 * j;
+      uint32_t v = src[j];
+      if (e + 1 >= valid) v = e < valid ? (v & 0xffffu) : 0u;
+      wv[j] = v;
+    }
+    *reinterpret_cast<uint4*>(orow + (size_t)ox * KP + r * RP + q * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+  }
+  const int tail = (KP - R * RP) >> 3;
+  for (int u = threadIdx.x; u < Wo * tail; u += blockDim.x) {
+    const int q = u % tail, ox = u / tail;
+    *reinterpret_cast<uint4*>(orow + (size_t)ox * KP + R * RP + q * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+
 // ---- Adam (torch.optim.Adam defaults, scheduler.py:10-11) over a flat parameter buffer ------------------------
 __global__ void adam_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
                             float eps, float bc1, float bc2_sqrt, float wd) {
@@ -838,11 +839,6 @@ static int num_sms_nn() {
   }
   return v;
 }
-static int tuning_dw_rows() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("AADG_DW_ROWS"); v = e ? atoi(e) : 1; }
-  return v;
-}
 static inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   return (int)std::max<long long>(1, std::min<long long>(g, 148 * 16));
@@ -858,6 +854,24 @@ static inline dim3 reduce_block(int C) {
 static inline int stream_blocks(long long pixels, dim3 blk, int per_sm) {
   const long long trips = (pixels + (long long)blk.y * BN_U - 1) / ((long long)blk.y * BN_U);
   return (int)std::max<long long>(1, std::min<long long>(trips, (long long)num_sms_nn() * per_sm));
+}
+
+// generic depthwise fallbacks (any dilation / image size); csrc/dwconv.cu holds the TMA-tiled fast paths and the C ABI
+int dwconv3x3_generic(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int direction,
+                      void* y, int ldy, cudaStream_t st) {
+  dim3 grid(std::max(1, std::min((w * (c / 8) + 255) / 256, 64)), h, n);
+  dw3x3_kernel<<<grid, 256, 0, st>>>((const bf16*)x, n, h, w, c, ldx, wgt, dil, direction ? -1 : 1, (bf16*)y, ldy);
+  return check_launch("dwconv3x3");
+}
+int dwconv3x3_wgrad_generic(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil,
+                            float* dw, cudaStream_t st) {
+  const long long pixels = (long long)n * h * w;
+  const dim3 blk = reduce_block(c);
+  const int blocks = (int)std::min<long long>((pixels + blk.y * 16 - 1) / (blk.y * 16), 148 * 6);
+  const size_t smem = (size_t)3 * c * sizeof(float);
+  dim3 grid(std::max(blocks, 1), 3);
+  dw3x3_wgrad_kernel<<<grid, blk, smem, st>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, lddy, dil, dw);
+  return check_launch("dwconv3x3 wgrad");
 }
 
 }  // namespace nn
@@ -940,7 +954,7 @@ int aadg_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, void* y, vo
 int aadg_maxpool3x3s2_bwd(const void* dy, const void* argmax, int n, int h, int w, int c, void* dx, void* stream) {
   NN_REQ_C(c);
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+  maxpool_bwd_kernel<<<grid_for((long long)n * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, (const unsigned char*)argmax, n, h, w, c, ho, wo, (bf16*)dx);
   return check_launch("maxpool bwd");
 }
@@ -969,7 +983,7 @@ int aadg_copy_bf16(const void* x, int ldx, void* y, int ldy, long long pixels, i
 int aadg_upsample_bilinear_fwd(const void* x, int n, int h, int w, int c, int ldx, void* y, int ho, int wo, int ldy,
                                void* stream) {
   NN_REQ_C(c);
-  upsample_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+  upsample_fwd_kernel<<<grid_for((long long)n * ho * ((wo + 3) / 4) * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, n, h, w, c, ldx, (bf16*)y, ho, wo, ldy);
   return check_launch("upsample fwd");
 }
@@ -999,43 +1013,6 @@ int aadg_f32_to_bf16(const float* x, void* y, long long count, float scale, void
   return check_launch("f32_to_bf16");
 }
 
-/* depthwise 3x3, stride 1, padding = dilation. direction 0: forward, 1: data gradient. w fp32 [9][c] */
-int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int direction, void* y,
-                   int ldy, void* stream) {
-  NN_REQ_C(c);
-  AADG_REQUIRE(h <= 65535 && n <= 65535, "image too tall / batch too large for the depthwise grid");
-  const size_t smem = 0;
-  if (dil == 1 && tuning_dw_rows()) {
-    DwRows a{(const bf16*)x, ldx, n, h, w, c};
-    dim3 grid((w + DWR_XT - 1) / DWR_XT, (c + DWR_CB - 1) / DWR_CB, n);
-    dw3x3_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, wgt, direction ? 1 : 0, (bf16*)y, ldy);
-  } else {
-    dim3 grid(std::max(1, std::min((w * (c / 8) + 255) / 256, 64)), h, n);
-    dw3x3_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, wgt, dil,
-                                                           direction ? -1 : 1, (bf16*)y, ldy);
-  }
-  return check_launch("dwconv3x3");
-}
-int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil, float* dw,
-                         void* stream) {
-  NN_REQ_C(c);
-  const long long pixels = (long long)n * h * w;
-  AADG_REQUIRE(pixels < (1ll << 31), "too many pixels");
-  if (dil == 1 && tuning_dw_rows()) {
-    DwRows a{(const bf16*)x, ldx, n, h, w, c};
-    dim3 grid((w + DWR_XT - 1) / DWR_XT, (c + DWR_CB - 1) / DWR_CB, n);
-    dw3x3_rows_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, (const bf16*)dy, lddy, dw);
-    return check_launch("dwconv3x3 rows wgrad");
-  }
-  const dim3 blk = reduce_block(c);
-  const int blocks = (int)std::min<long long>((pixels + blk.y * 16 - 1) / (blk.y * 16), 148 * 6);
-  const size_t smem = (size_t)3 * c * sizeof(float);
-  dim3 grid(std::max(blocks, 1), 3);
-  dw3x3_wgrad_kernel<<<grid, blk, smem, (cudaStream_t)stream>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, lddy,
-                                                               dil, dw);
-  return check_launch("dwconv3x3 wgrad");
-}
-
 /* img fp32 [n,3,h,w] -> col bf16 [n*ho*wo][kp], k = (r*S+s)*3 + c, zero padded to kp (multiple of 8) */
 int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int kp, void* col,
                      void* stream) {
@@ -1051,6 +1028,28 @@ int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int st
   }
   im2col_stem_kernel<<<n * ho, 256, smem, (cudaStream_t)stream>>>(img, n, h, w, r, s, stride, pad, ho, wo, kp, (bf16*)col);
   return check_launch("im2col");
+}
+
+/* same patches in the row-pitched layout k = r*row_pitch + s*3 + c (row_pitch % 8 == 0, >= 3*s; kp % 8 == 0,
+ * >= r*row_pitch; stride even): every filter row starts on a 16-byte boundary of the patch */
+int aadg_im2col_stem_rows(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int row_pitch, int kp,
+                          void* col, void* stream) {
+  AADG_REQUIRE(row_pitch % 8 == 0 && row_pitch >= 3 * s && kp % 8 == 0 && kp >= r * row_pitch,
+               "row_pitch must be a multiple of 8 >= 3*S and kp a multiple of 8 >= R*row_pitch");
+  AADG_REQUIRE(stride % 2 == 0 && stride > 0, "the row-pitched im2col needs an even stride");
+  AADG_REQUIRE(((uintptr_t)col & 15) == 0, "col must be 16-byte aligned");
+  const int ho = (h + 2 * pad - r) / stride + 1, wo = (w + 2 * pad - s) / stride + 1;
+  const int pitch = ((w + 2 * pad) * 3 + row_pitch + 1) & ~1;
+  const size_t smem = (size_t)r * pitch * sizeof(bf16);
+  AADG_REQUIRE(smem <= 200 * 1024, "image too wide for the staged im2col (%zu bytes of shared memory)", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(im2col_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  im2col_rows_kernel<<<n * ho, 256, smem, (cudaStream_t)stream>>>(img, n, h, w, r, s, stride, pad, ho, wo, row_pitch, kp,
+                                                                 (bf16*)col);
+  return check_launch("im2col rows");
 }
 
 int aadg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count, float lr,

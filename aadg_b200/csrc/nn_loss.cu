@@ -14,30 +14,66 @@ namespace nnl {
 typedef __nv_bfloat16 bf16;
 constexpr int MAXK = 2;
 
-// z[p][k] = b[k] + sum_c w[k][c] * a[p][c] ; one warp per pixel
-__global__ void head_fwd_kernel(const bf16* a, long long P, int C, int lda, const float* w, const float* b, int K,
-                                float* z) {
+// z[p][k] = b[k] + sum_c w[k][c] * a[p][c] ; one warp per pixel, HEAD_U pixels per trip with the loads issued
+// first; for C <= 256 (one 16-byte load per lane) the lane's 8 x K weights stay in registers
+constexpr int HEAD_U = 4;
+template <bool SMALL_C>
+__global__ void __launch_bounds__(256) head_fwd_kernel(const bf16* __restrict__ a, long long P, int C, int lda,
+                                                       const float* __restrict__ w, const float* __restrict__ b, int K,
+                                                       float* __restrict__ z) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long p = warp; p < P; p += nwarps) {
-    float acc[MAXK] = {};
-    for (int c = lane * 8; c < C; c += 256) {
-      const uint4 u = *reinterpret_cast<const uint4*>(a + p * lda + c);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  float wk[MAXK][8] = {};
+  if (SMALL_C && lane * 8 < C)
+    for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(h[i]);
+      for (int i = 0; i < 8; ++i) wk[k][i] = w[k * C + lane * 8 + i];
+  const float b0 = b[0], b1 = K > 1 ? b[1] : 0.f;
+  for (long long p0 = warp; p0 < P; p0 += HEAD_U * nwarps) {
+    float acc[HEAD_U][MAXK] = {};
+    if (SMALL_C) {
+      uint4 u[HEAD_U];
 #pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-          if (k < K) acc[k] = fmaf(f.x, w[k * C + c + 2 * i], fmaf(f.y, w[k * C + c + 2 * i + 1], acc[k]));
+      for (int j = 0; j < HEAD_U; ++j) {
+        const long long p = p0 + j * nwarps;
+        u[j] = (p < P && lane * 8 < C) ? __ldg(reinterpret_cast<const uint4*>(a + p * lda + lane * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < HEAD_U; ++j) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+#pragma unroll
+          for (int k = 0; k < MAXK; ++k) acc[j][k] = fmaf(f.x, wk[k][2 * i], fmaf(f.y, wk[k][2 * i + 1], acc[j][k]));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < HEAD_U; ++j) {
+        const long long p = p0 + j * nwarps;
+        if (p >= P) break;
+        for (int c = lane * 8; c < C; c += 256) {
+          const uint4 u = *reinterpret_cast<const uint4*>(a + p * lda + c);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+#pragma unroll
+            for (int k = 0; k < MAXK; ++k)
+              if (k < K) acc[j][k] = fmaf(f.x, w[k * C + c + 2 * i], fmaf(f.y, w[k * C + c + 2 * i + 1], acc[j][k]));
+          }
+        }
       }
     }
 #pragma unroll
-    for (int k = 0; k < MAXK; ++k) {
-      if (k < K) {
-        const float t = warp_sum(acc[k]);
-        if (lane == 0) z[p * K + k] = t + b[k];
+    for (int j = 0; j < HEAD_U; ++j) {
+      const long long p = p0 + j * nwarps;
+      const float t0 = warp_sum(acc[j][0]), t1 = warp_sum(acc[j][1]);
+      if (lane == 0 && p < P) {
+        z[p * K] = t0 + b0;
+        if (K > 1) z[p * K + 1] = t1 + b1;
       }
     }
   }
@@ -88,12 +124,21 @@ __global__ void loss_fwd_kernel(const float* z, int N, int h, int w, int K, cons
     tp += __shfl_xor_sync(0xffffffffu, tp, o); fp += __shfl_xor_sync(0xffffffffu, fp, o);
     fn += __shfl_xor_sync(0xffffffffu, fn, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(loss_sum, (double)lsum);
+  // one set of atomics per CTA (147 456 warps hammering a single double was most of this kernel's time)
+  __shared__ float s_l[8];
+  __shared__ int s_c[8][3];
+  const int wid = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { s_l[wid] = lsum; s_c[wid][0] = tp; s_c[wid][1] = fp; s_c[wid][2] = fn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = 0.0;
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { l += (double)s_l[i]; c0 += s_c[i][0]; c1 += s_c[i][1]; c2 += s_c[i][2]; }
+    atomicAdd(loss_sum, l);
     int* c = counts + ((size_t)n * K + k) * 3;
-    if (tp) atomicAdd(c, tp);
-    if (fp) atomicAdd(c + 1, fp);
-    if (fn) atomicAdd(c + 2, fn);
+    if (c0) atomicAdd(c, c0);
+    if (c1) atomicAdd(c + 1, c1);
+    if (c2) atomicAdd(c + 2, c2);
   }
 }
 
@@ -140,52 +185,161 @@ __global__ void loss_bwd_kernel(const float* z, int N, int h, int w, int K, cons
   }
 }
 
+// Scatter form of the same gradient for the up-sampling factor smp uses (H = 4h, W = 4w): a CTA owns a 64 x 64
+// block of output pixels of one (image, class); a thread owns a 4 x 4 patch (four float4 target loads), evaluates
+// the up-sampled logit from a shared-memory copy of the low-resolution logits, folds its 16 gradients into the
+// <= 3 x 3 low-resolution cells they touch in registers, and adds those to a shared-memory tile; the tile leaves
+// with one global atomic per cell (cells on a block border are shared with the neighbouring CTA; dz is zeroed first).
+constexpr int LB_T = 64, LB_Z = 20;
+__global__ void __launch_bounds__(256) loss_bwd_x4_kernel(const float* __restrict__ z, int h, int w, int K,
+                                                          const float* __restrict__ target, int H, int W, float gscale,
+                                                          float* dz) {
+  __shared__ float sz[LB_Z][LB_Z], sacc[LB_Z][LB_Z];
+  const int n = blockIdx.z, k = blockIdx.y;
+  const int tiles_x = (W + LB_T - 1) / LB_T;
+  const int X0 = (blockIdx.x % tiles_x) * LB_T, Y0 = (blockIdx.x / tiles_x) * LB_T;
+  const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
+  int yb, xb, t1; float tl;
+  src_index(Y0, sy, h, yb, t1, tl);
+  src_index(X0, sx, w, xb, t1, tl);
+  const float* zn = z + (size_t)n * h * w * K + k;
+  for (int i = threadIdx.x; i < LB_Z * LB_Z; i += 256) {
+    const int r = i / LB_Z, c = i - r * LB_Z;
+    const int yy = min(yb + r, h - 1), xx = min(xb + c, w - 1);
+    sz[r][c] = zn[((size_t)yy * w + xx) * K];
+    sacc[r][c] = 0.f;
+  }
+  const int oy0 = Y0 + (threadIdx.x >> 4) * 4, ox0 = X0 + (threadIdx.x & 15) * 4;
+  const bool active = oy0 < H && ox0 < W;      // H, W multiples of 4: a patch is entirely inside or outside
+  const float* tn = target + ((size_t)n * K + k) * H * W;
+  float4 tv[4];
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tv[j] = __ldg(reinterpret_cast<const float4*>(tn + (size_t)(oy0 + j) * W + ox0));
+  }
+  __syncthreads();
+  if (active) {
+    int py, px;
+    src_index(oy0, sy, h, py, t1, tl);
+    src_index(ox0, sx, w, px, t1, tl);
+    int x0[4], x1[4]; float lx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) src_index(ox0 + i, sx, w, x0[i], x1[i], lx[i]);
+    float a[3][3] = {};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int y0, y1; float ly;
+      src_index(oy0 + j, sy, h, y0, y1, ly);
+      const float tj[4] = {tv[j].x, tv[j].y, tv[j].z, tv[j].w};
+      float row[3] = {};       // this output row's gradients folded onto the three low-resolution columns
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float v00 = sz[y0 - yb][x0[i] - xb], v01 = sz[y0 - yb][x1[i] - xb];
+        const float v10 = sz[y1 - yb][x0[i] - xb], v11 = sz[y1 - yb][x1[i] - xb];
+        const float zu = (1.f - ly) * ((1.f - lx[i]) * v00 + lx[i] * v01) + ly * ((1.f - lx[i]) * v10 + lx[i] * v11);
+        const float pr = sigmoidf_(zu);
+        const float pq = pr * (1.f - pr);
+        const float gr = (pr - tj[i]) * (pq / fmaxf(pq, 1e-12f));
+        const int c0 = x0[i] - px, c1 = x1[i] - px;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) row[c] += ((c == c0 ? 1.f - lx[i] : 0.f) + (c == c1 ? lx[i] : 0.f)) * gr;
+      }
+      const int r0 = y0 - py, r1 = y1 - py;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float wr = (r == r0 ? 1.f - ly : 0.f) + (r == r1 ? ly : 0.f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a[r][c] = fmaf(wr, row[c], a[r][c]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (a[r][c] != 0.f) atomicAdd(&sacc[py - yb + r][px - xb + c], a[r][c]);
+  }
+  __syncthreads();
+  float* dzn = dz + (size_t)n * h * w * K + k;
+  for (int i = threadIdx.x; i < LB_Z * LB_Z; i += 256) {
+    const int r = i / LB_Z, c = i - r * LB_Z;
+    const float v = sacc[r][c];
+    if (v != 0.f && yb + r < h && xb + c < w) atomicAdd(&dzn[((size_t)(yb + r) * w + xb + c) * K], v * gscale);
+  }
+}
+
 // da[p][c] = sum_k dz[p][k] w[k][c] (bf16) ; dw[k][c] += sum_p dz[p][k] a[p][c] ; db[k] += sum_p dz[p][k]
-__global__ void head_bwd_kernel(const float* dz, const bf16* a, long long P, int C, int lda, const float* w, int K,
-                                bf16* da, int ldda, float* dw, float* db) {
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dz, const bf16* __restrict__ a, long long P,
+                                                       int C, int lda, const float* w, int K, bf16* __restrict__ da, int ldda,
+                                                       float* dw, float* db) {
   const int G = C >> 3;
   const int tx = threadIdx.x, ty = threadIdx.y;
   float acc[MAXK][8] = {};
   float accb[MAXK] = {};
   float wk[MAXK][8] = {};
-  if (tx < G)
-    for (int k = 0; k < K; ++k)
+  if (tx < G) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) wk[k][i] = w[k * C + tx * 8 + i];
-  if (tx < G)
-    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y) {
-      const uint4 u = *reinterpret_cast<const uint4*>(a + p * lda + tx * 8);
-      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-      float av[8];
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(hh[i]); av[2 * i] = f.x; av[2 * i + 1] = f.y; }
-      float o[8] = {};
+        for (int i = 0; i < 8; ++i) wk[k][i] = w[k * C + tx * 8 + i];
+      }
+  }
+  if (tx < G) {
+    constexpr int U = 4;
+    const long long step = (long long)gridDim.x * blockDim.y;
+    for (long long p0 = (long long)blockIdx.x * blockDim.y + ty; p0 < P; p0 += U * step) {
+      uint4 u[U];
+      float d[U][MAXK];
 #pragma unroll
-      for (int k = 0; k < MAXK; ++k) {
-        if (k < K) {
-          const float d = dz[p * K + k];
-          if (tx == 0) accb[k] += d;
+      for (int j = 0; j < U; ++j) {
+        const long long p = p0 + j * step;
+        u[j] = make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { acc[k][i] = fmaf(d, av[i], acc[k][i]); o[i] = fmaf(d, wk[k][i], o[i]); }
+        for (int k = 0; k < MAXK; ++k) d[j][k] = 0.f;
+        if (p < P) {
+          u[j] = __ldg(reinterpret_cast<const uint4*>(a + p * lda + tx * 8));
+#pragma unroll
+          for (int k = 0; k < MAXK; ++k)
+            if (k < K) d[j][k] = __ldg(dz + p * K + k);
         }
       }
-      uint4 ou;
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ou);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-      *reinterpret_cast<uint4*>(da + p * ldda + tx * 8) = ou;
+      for (int j = 0; j < U; ++j) {
+        const long long p = p0 + j * step;
+        if (p >= P) break;
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u[j]);
+        float av[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(hh[i]); av[2 * i] = f.x; av[2 * i + 1] = f.y; }
+        float o[8] = {};
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k) {
+          if (tx == 0) accb[k] += d[j][k];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { acc[k][i] = fmaf(d[j][k], av[i], acc[k][i]); o[i] = fmaf(d[j][k], wk[k][i], o[i]); }
+        }
+        uint4 ou;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&ou);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<uint4*>(da + p * ldda + tx * 8) = ou;
+      }
     }
+  }
   __shared__ float s[MAXK][2048];
   __shared__ float sb[MAXK];
   for (int i = ty * blockDim.x + tx; i < MAXK * 2048; i += blockDim.x * blockDim.y) (&s[0][0])[i] = 0.f;
   if (tx == 0 && ty == 0) for (int k = 0; k < MAXK; ++k) sb[k] = 0.f;
   __syncthreads();
-  if (tx < G)
-    for (int k = 0; k < K; ++k) {
+  if (tx < G) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&s[k][tx * 8 + i], acc[k][i]);
-      if (tx == 0) atomicAdd(&sb[k], accb[k]);
-    }
+    for (int k = 0; k < MAXK; ++k)
+      if (k < K) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&s[k][tx * 8 + i], acc[k][i]);
+        if (tx == 0) atomicAdd(&sb[k], accb[k]);
+      }
+  }
   __syncthreads();
   for (int k = 0; k < K; ++k) {
     for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) atomicAdd(&dw[k * C + i], s[k][i]);
@@ -303,8 +457,11 @@ extern "C" {
 int aadg_seg_head_fwd(const void* a, long long pixels, int c, int lda, const float* w, const float* bias, int classes,
                       float* z, void* stream) {
   AADG_REQUIRE(classes >= 1 && classes <= MAXK && c % 8 == 0 && c > 0, "classes must be 1..%d, channels a multiple of 8", MAXK);
-  const int blocks = (int)std::min<long long>((pixels * 32 + 255) / 256, 148 * 16);
-  head_fwd_kernel<<<std::max(blocks, 1), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, pixels, c, lda, w, bias, classes, z);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((pixels * 32 + 255) / 256, 148 * 8));
+  if (c <= 256)
+    head_fwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, pixels, c, lda, w, bias, classes, z);
+  else
+    head_fwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, pixels, c, lda, w, bias, classes, z);
   return check_launch("seg_head_fwd");
 }
 
@@ -324,6 +481,12 @@ int aadg_seg_loss_bwd(const float* z, int n, int h, int w, int classes, const fl
                       float grad_scale, float* dz, void* stream) {
   AADG_REQUIRE(classes >= 1 && classes <= MAXK && n > 0, "bad sizes");
   const long long total = (long long)n * h * w * classes;
+  if (H == 4 * h && W == 4 * w && h > 1 && w > 1 && n <= 65535 && ((uintptr_t)target & 15) == 0) {
+    AADG_CUDA_TRY(cudaMemsetAsync(dz, 0, sizeof(float) * total, (cudaStream_t)stream));
+    dim3 grid(((W + LB_T - 1) / LB_T) * ((H + LB_T - 1) / LB_T), classes, n);
+    loss_bwd_x4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, h, w, classes, target, H, W, grad_scale, dz);
+    return check_launch("seg_loss_bwd x4");
+  }
   const int blocks = (int)std::min<long long>((total + 127) / 128, 148 * 32);
   loss_bwd_kernel<<<std::max(blocks, 1), 128, 0, (cudaStream_t)stream>>>(z, n, h, w, classes, target, H, W, grad_scale, dz);
   return check_launch("seg_loss_bwd");
@@ -337,7 +500,7 @@ int aadg_seg_head_bwd(const float* dz, const void* a, long long pixels, int c, i
   while (tx < (c >> 3)) tx <<= 1;
   tx = std::min(tx, 256);
   dim3 blk(tx, 256 / tx);
-  const int blocks = (int)std::min<long long>((pixels + blk.y * 8 - 1) / (blk.y * 8), 148 * 4);
+  const int blocks = (int)std::min<long long>((pixels + blk.y * 4 - 1) / (blk.y * 4), 148 * 4);
   head_bwd_kernel<<<std::max(blocks, 1), blk, 0, (cudaStream_t)stream>>>(dz, (const bf16*)a, pixels, c, lda, w, classes,
                                                                         (bf16*)da, ldda, dw, db);
   return check_launch("seg_head_bwd");

@@ -15,10 +15,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn();
 
-// bf16 tensor, innermost dimension first; strides in ELEMENTS for dims 1..rank-1; 128-byte swizzle,
-// out-of-bounds elements read as zero.
+// bf16 tensor, innermost dimension first; strides in ELEMENTS for dims 1..rank-1; 128-byte swizzle (or a
+// plain row-major box with swizzle128 = false), out-of-bounds elements read as zero.
 int make_map_bf16(CUtensorMap* map, const void* base, int rank, const long long* dims,
-                  const long long* strides_elems, const int* box, const int* elem_strides);
+                  const long long* strides_elems, const int* box, const int* elem_strides, bool swizzle128 = true);
 
 // C[i][j] = 1 - <A_i,B_j>/(na_i nb_j) on tensor cores (conv_tc.cu); A [n,k], B [m,k] bf16, optional transpose ct
 int gram_cost(const void* A, int n, const void* B, int m, int k, const float* na, const float* nb, float* c,

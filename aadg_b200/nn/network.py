@@ -296,7 +296,21 @@ RESNETS = {
     "resnet34": (BasicBlock, [3, 4, 6, 3]),
     "resnet50": (Bottleneck, [3, 4, 6, 3]),
 }
-STEM_KP = 192   # 7*7*3 = 147 patch values, zero padded to a multiple of 64
+STEM_RP = 24    # stem patch layout k = r*24 + s*3 + c: 21 values of a filter row + 3 zeros (16-byte aligned rows)
+STEM_KP = 7 * STEM_RP
+
+
+def stem_pack(w):
+    """torch [64,3,7,7] -> [1,64,STEM_KP] in the row-pitched patch order of K.im2col_stem(row_pitch=STEM_RP)."""
+    co = w.shape[0]
+    v = w.permute(0, 2, 3, 1).reshape(co, 7, 21)
+    return torch.cat([v, torch.zeros(co, 7, STEM_RP - 21, dtype=w.dtype, device=w.device)], 2).reshape(1, co, STEM_KP)
+
+
+def stem_unpack(d):
+    """[1,64,STEM_KP] -> torch [64,3,7,7]"""
+    co = d.shape[1]
+    return d[0].reshape(co, 7, STEM_RP)[:, :, :21].reshape(co, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
 
 
 class ResNetEncoder:
@@ -308,8 +322,7 @@ class ResNetEncoder:
         block, layers = RESNETS[name]
 
         def stem_init(shape):
-            w = kaiming_fan_out((64, 3, 7, 7)).permute(0, 2, 3, 1).reshape(64, 147)   # k = (r*7+s)*3 + c
-            return torch.cat([w, torch.zeros(64, STEM_KP - 147)], 1).reshape(1, 64, STEM_KP)
+            return stem_pack(kaiming_fan_out((64, 3, 7, 7)))
         self.stem_w = store.add("encoder.conv1.weight", (1, 64, STEM_KP), "conv_nt", stem_init)
         self.stem_bn = BatchNorm(store, "encoder.bn1", 64)
         self.blocks = []
@@ -330,7 +343,7 @@ class ResNetEncoder:
             self.out_channels.append(cin)
 
     def forward(self, img, training):
-        col = K.im2col_stem(img, 7, 7, 2, 3, STEM_KP)
+        col = K.im2col_stem(img, 7, 7, 2, 3, STEM_KP, row_pitch=STEM_RP)
         pre = C.fprop(col, self.stem_w.bf16, 1, 1)
         f1 = torch.empty_like(pre)
         self.stem_bn.forward(pre, f1, training)
@@ -558,7 +571,7 @@ class SegNet:
         for p in self.store.items:
             d = p.data.detach().clone()
             if p.name == "encoder.conv1.weight":
-                d = d[0, :, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+                d = stem_unpack(d)
             elif p.kind in ("conv", "conv_nt"):
                 k = int(round(math.sqrt(p.shape[0])))
                 d = from_taps(d, k, k)
@@ -584,8 +597,7 @@ class SegNet:
                 continue
             w = sd[name].detach().to(self.device, torch.float32)
             if name == "encoder.conv1.weight":
-                w = torch.cat([w.permute(0, 2, 3, 1).reshape(64, 147),
-                               torch.zeros(64, STEM_KP - 147, device=self.device)], 1).reshape(1, 64, STEM_KP)
+                w = stem_pack(w)
             elif p.kind in ("conv", "conv_nt"):
                 w = to_taps(w)
             elif name == "segmentation_head.0.weight":

@@ -111,12 +111,16 @@ def dwconv3x3_wgrad(x, dy, dil, dw):
     _call("aadg_dwconv3x3_wgrad", p(x), n, h, wd, c, _ld(x), p(dy), _ld(dy), dil, p(dw))
 
 
-def im2col_stem(img, r, s, stride, pad, kp):
+def im2col_stem(img, r, s, stride, pad, kp, row_pitch=None):
+    """fp32 NCHW image -> bf16 patches [n,ho,wo,kp]; k = (r*S+s)*3+c, or r*row_pitch + s*3 + c when row_pitch is given."""
     img = img.contiguous()
     n, _, h, w = img.shape
     ho, wo = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
     col = torch.empty((n, ho, wo, kp), dtype=BF16, device=img.device)
-    _call("aadg_im2col_stem", p(img), n, h, w, r, s, stride, pad, kp, p(col))
+    if row_pitch is None:
+        _call("aadg_im2col_stem", p(img), n, h, w, r, s, stride, pad, kp, p(col))
+    else:
+        _call("aadg_im2col_stem_rows", p(img), n, h, w, r, s, stride, pad, row_pitch, kp, p(col))
     return col
 
 

@@ -232,6 +232,10 @@ int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, con
 /* img fp32 [n,3,h,w] -> col bf16 [n*ho*wo][kp], k = (r*S+s)*3 + c, zero padded to kp */
 int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int kp, void* col,
                      void* stream);
+/* the same patches in a row-pitched layout k = r*row_pitch + s*3 + c (row_pitch % 8 == 0, >= 3*s; kp % 8 == 0,
+ * >= r*row_pitch; even stride): every filter row starts on a 16-byte boundary, the pass is a run copy */
+int aadg_im2col_stem_rows(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int row_pitch,
+                          int kp, void* col, void* stream);
 /* torch.optim.Adam step `step` (1-based) over flat fp32 buffers */
 int aadg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, void* stream);

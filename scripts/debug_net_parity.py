@@ -19,7 +19,7 @@ for enc, size, n in [("resnet18", 128, 4), ("resnet50", 128, 4), ("resnet50", 25
     for name, p in net.named_params().items():
         g = p.grad.detach()
         if name == "encoder.conv1.weight":
-            g = g[0, :, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
+            g = __import__('aadg_b200.nn.network', fromlist=['stem_unpack']).stem_unpack(g)
         elif p.kind in ("conv", "conv_nt"):
             k = int(round(p.shape[0] ** 0.5))
             g = g.reshape(k, k, p.shape[1], p.shape[2]).permute(2, 3, 0, 1)

@@ -174,6 +174,17 @@ def test_global_sum_broadcast_im2col_adam(K):
     ref = F.unfold(img, 7, padding=3, stride=2)                      # [N, 3*49, L], k = c*49 + r*7 + s
     ref = ref.view(2, 3, 49, 10, 12).permute(0, 3, 4, 2, 1).reshape(2, 10, 12, 147)
     assert torch.equal(col[..., :147], ref.to(BF)) and col[..., 147:].abs().max() == 0
+    # row-pitched layout used by the network's stem: k = r*24 + s*3 + c, zero tails
+    for kp in (168, 192):
+        colr = K.im2col_stem(img, 7, 7, 2, 3, kp, row_pitch=24)
+        rows = colr[..., :168].reshape(2, 10, 12, 7, 24)
+        assert torch.equal(rows[..., :21].reshape(2, 10, 12, 147), ref.to(BF))
+        assert rows[..., 21:].abs().max() == 0 and (kp == 168 or colr[..., 168:].abs().max() == 0)
+    img2 = torch.rand(1, 3, 17, 22, device="cuda") * 2 - 1       # 3x3 stride-2 stem (MobileNetV2), odd sizes
+    col3 = K.im2col_stem(img2, 3, 3, 2, 1, 64, row_pitch=16)
+    ref3 = F.unfold(img2, 3, padding=1, stride=2).view(1, 3, 9, 9, 11).permute(0, 3, 4, 2, 1).reshape(1, 9, 11, 3, 9)
+    assert torch.equal(col3[..., :48].reshape(1, 9, 11, 3, 16)[..., :9], ref3.to(BF))
+    assert col3[..., :48].reshape(1, 9, 11, 3, 16)[..., 9:].abs().max() == 0 and col3[..., 48:].abs().max() == 0
     p = torch.randn(1000, device="cuda")
     gr = torch.randn(1000, device="cuda")
     pt = p.clone().requires_grad_(True)
@@ -253,7 +264,8 @@ def _ref_grads(ref):
 def _my_grad_as_torch(name, p):
     g = p.grad.detach()
     if name == "encoder.conv1.weight":
-        return g[0, :, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
+        from aadg_b200.nn.network import stem_unpack
+        return stem_unpack(g)
     if p.kind in ("conv", "conv_nt"):
         k = int(round(p.shape[0] ** 0.5))
         return g.reshape(k, k, p.shape[1], p.shape[2]).permute(2, 3, 0, 1)
