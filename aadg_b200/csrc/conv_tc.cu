@@ -217,32 +217,43 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_kernel(const __grid_constant
 
 // ---- persistent variant: tile loop per CTA, two TMEM accumulators, TMA-store epilogue -----------------------
 // One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the MMA issuer fills accumulator
-// (t & 1) while the epilogue warps drain the other one: TMEM -> registers -> bf16 -> 128B-swizzled staging
-// tile in shared memory -> one TMA tensor store (or reduce-add) per 64-channel half, so the output leaves
-// the SM as full 128-byte lines and the epilogue overlaps the next tile's main loop.
+// (t & 1) while the epilogue warps drain the other one, 64 output channels at a time: TMEM -> registers -> bf16 ->
+// 128B-swizzled staging slot (a ring of two 16 KB slots) -> one TMA tensor store (or reduce-add) per slot, so the
+// output leaves the SM as full 128-byte lines and the epilogue overlaps the next tile's main loop.
+// STATS: the batch-norm statistics of the output (per-channel sum and sum of squares of the bf16 values that were
+// stored) are accumulated from the staged slot into per-CTA shared-memory arrays and flushed with one atomic per
+// channel per CTA -- the separate statistics pass over the tensor (one full HBM read) disappears.
 struct IgemmPArgs {
   int lg_tw, lg_th;
   int tiles_x, tiles_y, tiles_n, cout_tiles;
   int in_step, k_blocks;
   int accumulate;
+  int Wout, Hout, Nimg, Cout;
+  float* stat_sum; float* stat_sq;
   Taps taps;
 };
+constexpr int SLOT_BYTES = 128 * 128;     // 128 rows x 64 bf16
 template <int BN, int STAGES>
-constexpr int igemm_p_smem_bytes() { return STAGES * (A_BYTES + BN * 128) + 2 * 128 * BN * 2 + 1024 + 256; }
+constexpr int igemm_p_smem_bytes(int stat_channels) {
+  return STAGES * (A_BYTES + BN * 128) + 2 * SLOT_BYTES + 2 * stat_channels * 4 + 1024 + 256;
+}
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(IG_THREADS, 1) igemm_p_kernel(const __grid_constant__ CUtensorMap tmA,
+constexpr int IGP_THREADS_STATS = IG_THREADS + 128;    // + four warps that only accumulate the statistics
+template <int BN, int STAGES, bool STATS>
+__global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) igemm_p_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
                                                                 const IgemmPArgs a) {
   constexpr int B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int OUT_BYTES = 128 * BN * 2;           // one staged output tile: BN/64 halves of [128][128 B]
   constexpr uint32_t TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* stage_out = smem + STAGES * STAGE_BYTES;
-  uint64_t* full = (uint64_t*)(stage_out + 2 * OUT_BYTES);
+  uint8_t* ring = smem + STAGES * STAGE_BYTES;
+  const int stat_c = STATS ? ((a.Cout + 63) & ~63) : 0;
+  float* s_sum = (float*)(ring + 2 * SLOT_BYTES);
+  float* s_sq = s_sum + stat_c;
+  uint64_t* full = (uint64_t*)(s_sq + stat_c);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
@@ -254,6 +265,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_p_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_mbar_init();
   }
+  if (STATS)
+    for (int i = threadIdx.x; i < 2 * stat_c; i += blockDim.x) s_sum[i] = 0.f;
   if (warp == 0 && lane == 0) { prefetch_map(&tmA); prefetch_map(&tmB); prefetch_map(&tmC); }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -316,29 +329,42 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_p_kernel(const __grid_con
         umma_commit(&acc_full[buf]);
       }
     }
-  } else {
+  } else if (warp < 6) {
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const bool leader = threadIdx.x == 64;     // first epilogue thread issues the TMA stores
-    int it = 0;
+    const int tw = m & ((1 << a.lg_tw) - 1);
+    const int th = (m >> a.lg_tw) & ((1 << a.lg_th) - 1);
+    const int tn = m >> (a.lg_tw + a.lg_th);
+    int it = 0, slot = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       int sx0, sy0, img0, n0;
       decode(t, sx0, sy0, img0, n0);
-      uint8_t* so = stage_out + buf * OUT_BYTES;
-      // the staging buffer was last used two tiles ago: its TMA store must have finished reading it
-      if (leader) tma_store_wait_read<1>();
-      named_bar_sync(1, 128);
+      // rows of a partial tile that fall outside the tensor: the TMA store clips them, the statistics must not see them
+      const bool row_ok = !STATS || (sx0 + tw < a.Wout && sy0 + th < a.Hout && img0 + tn < a.Nimg);
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int h = 0; h < BN / 64; ++h) {
+      for (int h = 0; h < BN / 64; ++h, ++slot) {
+        uint8_t* so = ring + (slot & 1) * SLOT_BYTES;
+        // this slot was handed to the TMA two stores ago: that store must have finished reading it (and, with
+        // STATS, the statistics warps must be done with it: barrier 4 + slot, 256 threads)
+        if (leader) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        if (STATS && slot >= 2) named_bar_sync(4 + (slot & 1), 256);
         uint32_t r[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + h * 64;
         tmem_ld32(taddr, r);
         tmem_ld32(taddr + 32, r + 32);
         tmem_ld_wait();
-        uint8_t* row = so + h * (128 * 128) + m * 128;
+        if (h == BN / 64 - 1) {
+          // accumulator drained: hand it back to the MMA issuer (one arrival per epilogue warp)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        uint8_t* row = so + m * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint4 v;
@@ -346,29 +372,71 @@ __global__ void __launch_bounds__(IG_THREADS, 1) igemm_p_kernel(const __grid_con
           v.y = pack_bf16x2(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
           v.z = pack_bf16x2(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
           v.w = pack_bf16x2(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+          if (!row_ok) v = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(row + ((j ^ (m & 7)) << 4)) = v;
         }
-      }
-      // accumulator drained: hand it back to the MMA issuer (one arrival per epilogue warp)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      fence_proxy_async();
-      named_bar_sync(1, 128);
-      if (leader) {
-#pragma unroll
-        for (int h = 0; h < BN / 64; ++h) {
-          if (a.accumulate) tma_reduce_add_4d(&tmC, so + h * (128 * 128), n0 + h * 64, sx0, sy0, img0);
-          else tma_store_4d(&tmC, so + h * (128 * 128), n0 + h * 64, sx0, sy0, img0);
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (leader) {
+          if (a.accumulate) tma_reduce_add_4d(&tmC, so, n0 + h * 64, sx0, sy0, img0);
+          else tma_store_4d(&tmC, so, n0 + h * 64, sx0, sy0, img0);
+          tma_store_commit();
         }
-        tma_store_commit();
+        if (STATS) named_bar_arrive(2 + (slot & 1), 256);      // slot staged: the statistics warps may read it
       }
     }
     if (leader) tma_store_wait<0>();
+  } else if (STATS) {
+    // statistics warps: warp w owns channels [16w, 16w + 16) of every staged 64-channel slot (bf16 values exactly
+    // as stored).  Lane = (column pair cp8, row quarter rsub): 32 rows x 2 channels each, the four row quarters
+    // folded with two shuffle steps, then lanes 0..7 add into the CTA's shared accumulators -- always the same
+    // thread for a given channel, so no atomics.  The quarters walk their rows with a stagger of two so that the
+    // 128-byte swizzle sends the four concurrent rows to different banks.
+    // Barriers 2/3 = slot 0/1 staged, 4/5 = slot 0/1 consumed.
+    const int et = threadIdx.x - IG_THREADS;
+    const int cpair = (et >> 5) * 8 + (lane & 7), rsub = lane >> 3;
+    const int total_slots = (int)(BN / 64) * ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+    int slot = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      int sx0, sy0, img0, n0;
+      decode(t, sx0, sy0, img0, n0);
+#pragma unroll 1
+      for (int h = 0; h < BN / 64; ++h, ++slot) {
+        const uint8_t* so = ring + (slot & 1) * SLOT_BYTES + (cpair & 3) * 4;
+        named_bar_sync(2 + (slot & 1), 256);
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int rr = rsub * 32 + ((i + 2 * rsub) & 31);
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(so + rr * 128 + (((cpair >> 2) ^ (rr & 7)) << 4));
+          const float v0 = __uint_as_float(u << 16), v1 = __uint_as_float(u & 0xffff0000u);
+          s0 += v0; s1 += v1;
+          q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
+        }
+        // done reading: the epilogue warps may overwrite the slot (only waited for when the slot is used again)
+        if (slot + 2 < total_slots) named_bar_arrive(4 + (slot & 1), 256);
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        }
+        const int c = n0 + h * 64 + cpair * 2;
+        if (rsub == 0 && c < a.Cout) {
+          s_sum[c] += s0; s_sum[c + 1] += s1;
+          s_sq[c] += q0; s_sq[c + 1] += q1;
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (STATS) {
+    for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) {
+      atomicAdd(&a.stat_sum[i], s_sum[i]);
+      atomicAdd(&a.stat_sq[i], s_sq[i]);
+    }
+  }
 }
 
 // ---- cosine-cost Gram matrix for the Sinkhorn set-up -------------------------------------------------------
@@ -686,12 +754,35 @@ static int launch_igemm_t(const CUtensorMap& mA, const CUtensorMap& mB, const Ig
   return check_launch("igemm kernel");
 }
 
+static int tuning_bn256() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AADG_CONV_BN256");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+template <int BN, int STAGES, bool STATS>
+static int launch_igemm_p_t(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, const IgemmPArgs& pa,
+                            int grid, cudaStream_t st) {
+  const int stat_c = STATS ? ((pa.Cout + 63) & ~63) : 0;
+  const int smem = igemm_p_smem_bytes<BN, STAGES>(stat_c);
+  static int attr_bytes = 0;
+  if (smem > attr_bytes) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(igemm_p_kernel<BN, STAGES, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_bytes = smem;
+  }
+  igemm_p_kernel<BN, STAGES, STATS><<<grid, STATS ? IGP_THREADS_STATS : IG_THREADS, smem, st>>>(mA, mB, mC, pa);
+  return check_launch("igemm persistent kernel");
+}
+
 // One implicit-GEMM launch.  in: bf16 [Nimg, Hin, Win, ld_in] (Cin channels used); wgt: bf16 [n_w_taps][Cn][Cin];
 // logical output grid Wsub x Hsub mapped to physical pixels by (o_step, o_y0, o_x0).
 static int launch_igemm(const void* in, int Nimg, int Hin, int Win, int Cin, int ld_in, int in_step,
                         const void* wgt, int n_w_taps, int Cn, const Taps& taps, int Wsub, int Hsub, void* out,
                         int Hout, int Wout, int ldc, int c_off, int o_step, int o_y0, int o_x0, int accumulate,
-                        cudaStream_t st) {
+                        cudaStream_t st, float* stat_sum = nullptr, float* stat_sq = nullptr) {
   AADG_REQUIRE(ld_in % 8 == 0 && ldc % 8 == 0 && c_off % 8 == 0 && Cn % 8 == 0 && Cin % 8 == 0,
                "channel counts/strides must be multiples of 8 (Cin %d ld_in %d Cout %d ldc %d off %d)", Cin, ld_in,
                Cn, ldc, c_off);
@@ -723,7 +814,15 @@ static int launch_igemm(const void* in, int Nimg, int Hin, int Win, int Cin, int
     int rc = make_map_bf16(&mA, in, 4, dims, strides, box, es);
     if (rc) return rc;
   }
-  const int bn = Cn <= 64 ? 64 : 128;
+  const bool persistent = o_step == 1 && o_y0 == 0 && o_x0 == 0 && Wsub == Wout && Hsub == Hout && tuning_persistent();
+  AADG_REQUIRE(!stat_sum || persistent, "fused statistics need the persistent kernel (dense stride-1 output grid)");
+  AADG_REQUIRE(!stat_sum || Cn <= 2048, "fused statistics support at most 2048 output channels");
+  // 256-wide tiles halve the A-operand traffic per flop; worth it once there are enough 256-column tiles to fill
+  // the SMs and the main loop is long enough to hide the 4-slot epilogue
+  const long long pix_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
+  const bool wide = persistent && tuning_bn256() && Cn % 256 == 0 && a.k_blocks * taps.n >= 4 &&
+                    pix_tiles * (Cn / 256) >= num_sms();
+  const int bn = Cn <= 64 ? 64 : (wide ? 256 : 128);
   {
     const long long dims[3] = {Cin, Cn, n_w_taps};
     const long long strides[2] = {Cin, (long long)Cn * Cin};
@@ -732,7 +831,7 @@ static int launch_igemm(const void* in, int Nimg, int Hin, int Win, int Cin, int
     if (rc) return rc;
   }
   const int cout_tiles = (Cn + bn - 1) / bn;
-  if (o_step == 1 && o_y0 == 0 && o_x0 == 0 && Wsub == Wout && Hsub == Hout && tuning_persistent()) {
+  if (persistent) {
     // persistent kernel with TMA-store epilogue: output = channel slice [c_off, c_off + Cn) of the NHWC tensor
     CUtensorMap mC;
     const long long dims[4] = {Cn, Wout, Hout, Nimg};
@@ -744,21 +843,19 @@ static int launch_igemm(const void* in, int Nimg, int Hin, int Win, int Cin, int
     pa.lg_tw = a.lg_tw; pa.lg_th = a.lg_th;
     pa.tiles_x = a.tiles_x; pa.tiles_y = a.tiles_y; pa.tiles_n = a.tiles_n; pa.cout_tiles = cout_tiles;
     pa.in_step = in_step; pa.k_blocks = a.k_blocks; pa.accumulate = accumulate;
+    pa.Wout = Wout; pa.Hout = Hout; pa.Nimg = Nimg; pa.Cout = Cn;
+    pa.stat_sum = stat_sum; pa.stat_sq = stat_sq;
     pa.taps = taps;
     const int n_tiles = pa.tiles_x * pa.tiles_y * pa.tiles_n * cout_tiles;
     const int grid = std::min(n_tiles, num_sms());
-    if (bn == 64) {
-      constexpr int smem = igemm_p_smem_bytes<64, 6>();
-      static bool set64 = false;
-      if (!set64) { AADG_CUDA_TRY(cudaFuncSetAttribute(igemm_p_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set64 = true; }
-      igemm_p_kernel<64, 6><<<grid, IG_THREADS, smem, st>>>(mA, mB, mC, pa);
-    } else {
-      constexpr int smem = igemm_p_smem_bytes<128, 4>();
-      static bool set128 = false;
-      if (!set128) { AADG_CUDA_TRY(cudaFuncSetAttribute(igemm_p_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set128 = true; }
-      igemm_p_kernel<128, 4><<<grid, IG_THREADS, smem, st>>>(mA, mB, mC, pa);
+    if (stat_sum) {
+      if (bn == 64) return launch_igemm_p_t<64, 6, true>(mA, mB, mC, pa, grid, st);
+      if (bn == 128) return launch_igemm_p_t<128, 4, true>(mA, mB, mC, pa, grid, st);
+      return launch_igemm_p_t<256, 3, true>(mA, mB, mC, pa, grid, st);
     }
-    return check_launch("igemm persistent kernel");
+    if (bn == 64) return launch_igemm_p_t<64, 6, false>(mA, mB, mC, pa, grid, st);
+    if (bn == 128) return launch_igemm_p_t<128, 4, false>(mA, mB, mC, pa, grid, st);
+    return launch_igemm_p_t<256, 4, false>(mA, mB, mC, pa, grid, st);
   }
   // fewer stages = less shared memory = more CTAs per SM: the per-CTA latencies (TMEM allocation, first TMA
   // round trip, epilogue) of one CTA overlap the main loop of its neighbours
@@ -822,6 +919,28 @@ int aadg_conv_fprop_bf16(const void* x, int n, int h, int w, int cin, int ldx, c
     }
   return launch_igemm(x, n, h, w, cin, ldx, stride, wgt, r * s, cout, taps, wo, ho, y, ho, wo, ldy, y_c_off, 1, 0, 0,
                       accumulate, (cudaStream_t)stream);
+}
+
+/* the same forward convolution, and the batch-norm statistics of its output in the same pass: stat_sum[co] and
+ * stat_sq[co] (fp32, `cout` entries each, ACCUMULATED: zero them first) receive the per-channel sum and sum of
+ * squares of the bf16 values written to y.  Replaces aadg_bn_stats over y (one full read of the tensor). */
+int aadg_conv_fprop_stats_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* wgt, int cout, int r,
+                               int s, int stride, int pad, int dil, void* y, int ho, int wo, int ldy, int y_c_off,
+                               float* stat_sum, float* stat_sq, void* stream) {
+  ConvGeom g{n, h, w, cin, ldx, ho, wo, cout, ldy, r, s, stride, pad, dil};
+  int rc = check_geom(g);
+  if (rc) return rc;
+  AADG_REQUIRE(stat_sum && stat_sq, "statistics buffers are required");
+  Taps taps{};
+  taps.n = r * s;
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < s; ++j) {
+      taps.dy[i * s + j] = (short)(i * dil - pad);
+      taps.dx[i * s + j] = (short)(j * dil - pad);
+      taps.w[i * s + j] = (short)(i * s + j);
+    }
+  return launch_igemm(x, n, h, w, cin, ldx, stride, wgt, r * s, cout, taps, wo, ho, y, ho, wo, ldy, y_c_off, 1, 0, 0, 0,
+                      (cudaStream_t)stream, stat_sum, stat_sq);
 }
 
 /* dx[n,iy,ix,c_off+ci] (+)= sum over (r,s,co) with iy = oy*stride-pad+r*dil of dy[n,oy,ox,co] * wt[r*S+s][ci][co]

@@ -83,24 +83,41 @@ __device__ __forceinline__ V8 unpack8(const uint4& u) {
   return r;
 }
 
-// per-thread partial sums a0/a1[8] of channel group threadIdx.x -> out0/out1[C] (shared-memory then global atomics)
+// per-thread partial sums a0/a1[8] of channel group threadIdx.x -> out0/out1[C].  No shared-memory atomics (a float
+// atomicAdd on shared memory is a compare-and-swap loop): pixel lanes that share a warp are folded with shuffles,
+// every (row, channel) partial then has exactly one writer in a [rows][C] shared array (rows * C == 2048 for the
+// block shapes of reduce_block()), and each channel's column is summed and sent out with one global reduction.
 template <int NACC>
-__device__ __forceinline__ void block_channel_sum(int C, const float* a0, const float* a1, float* out0, float* out1) {
-  const int tx = threadIdx.x, ty = threadIdx.y;
+__device__ __forceinline__ void block_channel_sum(int C, float* a0, float* a1, float* out0, float* out1) {
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x;
   __shared__ float s0[2048], s1[NACC > 1 ? 2048 : 1];
-  for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) { s0[i] = 0.f; if (NACC > 1) s1[i] = 0.f; }
-  __syncthreads();
-  if (tx < (C >> 3)) {
+  int row, rows;
+  if (TX < 32) {
+    for (int o = TX; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a0[i] += __shfl_xor_sync(0xffffffffu, a0[i], o);
+        if (NACC > 1) a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
+      }
+    }
+    row = (ty * TX + tx) >> 5; rows = (TX * blockDim.y) >> 5;
+    if ((((ty * TX + tx) & 31) >= TX)) row = -1;          // one writer per warp and channel group
+  } else {
+    row = ty; rows = blockDim.y;
+  }
+  if (row >= 0 && tx < (C >> 3)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s0[tx * 8 + i], a0[i]);
-      if (NACC > 1) atomicAdd(&s1[tx * 8 + i], a1[i]);
+      s0[row * C + tx * 8 + i] = a0[i];
+      if (NACC > 1) s1[row * C + tx * 8 + i] = a1[i];
     }
   }
   __syncthreads();
-  for (int i = ty * blockDim.x + tx; i < C; i += blockDim.x * blockDim.y) {
-    atomicAdd(&out0[i], s0[i]);
-    if (NACC > 1) atomicAdd(&out1[i], s1[i]);
+  for (int c = ty * TX + tx; c < C; c += TX * blockDim.y) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int r = 0; r < rows; ++r) { t0 += s0[r * C + c]; if (NACC > 1) t1 += s1[r * C + c]; }
+    atomicAdd(&out0[c], t0);
+    if (NACC > 1) atomicAdd(&out1[c], t1);
   }
 }
 

@@ -13,6 +13,7 @@ explicit backward pass (no autograd graph) and a fused Adam over one flat parame
 Architecture: SURVEY.md App. A.3 (smp DeepLabV3Plus, output stride 16, ASPP rates 12/24/36, separable).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -22,6 +23,8 @@ from ..ops import nn as K
 
 BF16 = torch.bfloat16
 BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+# batch-norm statistics accumulated in the convolution epilogue (aadg_conv_fprop_stats_bf16) instead of a separate pass
+FUSE_BN_STATS = os.environ.get("AADG_FUSE_BN_STATS", "1") != "0"
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -153,11 +156,17 @@ class BatchNorm:
         self.num_batches_tracked = 0
         self.buf = torch.zeros(6, c, device=dev)    # sum, sumsq, mean, invstd, scale, shift
 
-    def forward(self, x, y, training, res=None, relu=True, dropout_seed=None, relu_bits=None):
+    def stats_buffers(self):
+        """zeroed (sum, sumsq) accumulators for a convolution epilogue to fill (C.fprop(stats=...))"""
+        self.buf[:2].zero_()
+        return self.buf[0], self.buf[1]
+
+    def forward(self, x, y, training, res=None, relu=True, dropout_seed=None, relu_bits=None, have_stats=False):
         s = self.buf
         if training:
-            s[:2].zero_()
-            K.bn_stats(x, s[0], s[1])
+            if not have_stats:
+                s[:2].zero_()
+                K.bn_stats(x, s[0], s[1])
             count = x.numel() // x.shape[-1]
             K.bn_finalize(s[0], s[1], self.gamma.data, self.beta.data, count, BN_EPS, BN_MOMENTUM, s[2], s[3], s[4],
                           s[5], self.running_mean, self.running_var)
@@ -196,7 +205,9 @@ class ConvBN:
     def forward(self, x, training, out=None, res=None, dropout_seed=None):
         n, h, w, _ = x.shape
         ho, wo = self.out_hw(h, w)
-        pre = C.fprop(x, self.w.bf16, self.k, self.k, self.stride, self.pad, self.dil)
+        fused = training and FUSE_BN_STATS
+        pre = C.fprop(x, self.w.bf16, self.k, self.k, self.stride, self.pad, self.dil,
+                      stats=self.bn.stats_buffers() if fused else None)
         if out is None:
             out = torch.empty((n, ho, wo, self.cout), dtype=BF16, device=x.device)
         # backward needs the ReLU mask: recomputed from `pre` when there is no residual, otherwise kept as one
@@ -204,7 +215,8 @@ class ConvBN:
         bits = None
         if training and res is not None and self.relu:
             bits = torch.empty((pre.numel() // 8,), dtype=torch.uint8, device=x.device)
-        self.bn.forward(pre, out, training, res=res, relu=self.relu, dropout_seed=dropout_seed, relu_bits=bits)
+        self.bn.forward(pre, out, training, res=res, relu=self.relu, dropout_seed=dropout_seed, relu_bits=bits,
+                        have_stats=fused)
         self.ctx = (x, pre, bits, dropout_seed) if training else None
         return out
 
@@ -344,9 +356,10 @@ class ResNetEncoder:
 
     def forward(self, img, training):
         col = K.im2col_stem(img, 7, 7, 2, 3, STEM_KP, row_pitch=STEM_RP)
-        pre = C.fprop(col, self.stem_w.bf16, 1, 1)
+        fused = training and FUSE_BN_STATS
+        pre = C.fprop(col, self.stem_w.bf16, 1, 1, stats=self.stem_bn.stats_buffers() if fused else None)
         f1 = torch.empty_like(pre)
-        self.stem_bn.forward(pre, f1, training)
+        self.stem_bn.forward(pre, f1, training, have_stats=fused)
         pooled, arg = K.maxpool_fwd(f1)
         feats = [f1]
         x = pooled

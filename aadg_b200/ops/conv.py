@@ -13,8 +13,8 @@ TIMING = None
 
 
 class _timed:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, geom=None):
+        self.kind, self.flops, self.geom = kind, flops, geom
 
     def __enter__(self):
         if TIMING is not None:
@@ -25,7 +25,7 @@ class _timed:
     def __exit__(self, *exc):
         if TIMING is not None:
             self.e1.record()
-            TIMING.append((self.kind, self.flops, self.e0, self.e1))
+            TIMING.append((self.kind, self.flops, self.e0, self.e1, self.geom))
 
 
 def _nhwc(t, name):
@@ -42,8 +42,10 @@ def out_size(h, w, r, s, stride, pad, dil):
     return ((h + 2 * pad - dil * (r - 1) - 1) // stride + 1, (w + 2 * pad - dil * (s - 1) - 1) // stride + 1)
 
 
-def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False):
-    """x [N,H,W,Cin] bf16, wgt [R*S,Cout,Cin] bf16 -> y [N,Ho,Wo,Cout] bf16 (or written into `out`)."""
+def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False, stats=None):
+    """x [N,H,W,Cin] bf16, wgt [R*S,Cout,Cin] bf16 -> y [N,Ho,Wo,Cout] bf16 (or written into `out`).
+    stats = (sum, sumsq) fp32 [Cout] tensors (zeroed by the caller): the batch-norm statistics of y are accumulated
+    in the convolution's epilogue instead of a separate pass over y."""
     n, h, w, cin, ldx = _nhwc(x, "x")
     cout = wgt.shape[1]
     assert wgt.shape == (r * s, cout, cin) and wgt.dtype == torch.bfloat16 and wgt.is_contiguous()
@@ -52,10 +54,19 @@ def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False):
         out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
     _, oh, ow, oc, ldy = _nhwc(out, "out")
     assert (oh, ow, oc) == (ho, wo, cout)
-    with torch.cuda.device(x.device), _timed("fprop", 2.0 * n * ho * wo * cout * cin * r * s):
-        _lib.check(_lib.lib().aadg_conv_fprop_bf16(x.data_ptr(), n, h, w, cin, ldx, wgt.data_ptr(), cout, r, s, stride,
-                                                   pad, dil, out.data_ptr(), ho, wo, ldy, 0, int(accumulate),
-                                                   _lib.stream_ptr()))
+    with torch.cuda.device(x.device), _timed("fprop", 2.0 * n * ho * wo * cout * cin * r * s,
+                                              (n, h, w, cin, ho, wo, cout, r, stride, dil)):
+        if stats is not None:
+            assert not accumulate
+            ssum, ssq = stats
+            assert ssum.dtype == torch.float32 and ssq.dtype == torch.float32 and ssum.numel() == cout == ssq.numel()
+            _lib.check(_lib.lib().aadg_conv_fprop_stats_bf16(x.data_ptr(), n, h, w, cin, ldx, wgt.data_ptr(), cout, r, s,
+                                                             stride, pad, dil, out.data_ptr(), ho, wo, ldy, 0,
+                                                             ssum.data_ptr(), ssq.data_ptr(), _lib.stream_ptr()))
+        else:
+            _lib.check(_lib.lib().aadg_conv_fprop_bf16(x.data_ptr(), n, h, w, cin, ldx, wgt.data_ptr(), cout, r, s, stride,
+                                                       pad, dil, out.data_ptr(), ho, wo, ldy, 0, int(accumulate),
+                                                       _lib.stream_ptr()))
     return out
 
 
@@ -69,7 +80,8 @@ def dgrad(dy, wgt_t, r, s, stride, pad, dil, in_hw, out=None, accumulate=False):
         out = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=dy.device)
     _, xh, xw, xc, lddx = _nhwc(out, "out")
     assert (xh, xw, xc) == (h, w, cin)
-    with torch.cuda.device(dy.device), _timed("dgrad", 2.0 * n * ho * wo * cout * cin * r * s):
+    with torch.cuda.device(dy.device), _timed("dgrad", 2.0 * n * ho * wo * cout * cin * r * s,
+                                               (n, h, w, cin, ho, wo, cout, r, stride, dil)):
         _lib.check(_lib.lib().aadg_conv_dgrad_bf16(dy.data_ptr(), n, ho, wo, cout, lddy, wgt_t.data_ptr(), cin, r, s,
                                                    stride, pad, dil, out.data_ptr(), h, w, lddx, 0, int(accumulate),
                                                    _lib.stream_ptr()))
@@ -83,7 +95,8 @@ def wgrad(x, dy, r, s, stride, pad, dil, out=None):
     if out is None:
         out = torch.zeros((r * s, cout, cin), dtype=torch.float32, device=x.device)
     assert out.shape == (r * s, cout, cin) and out.dtype == torch.float32 and out.is_contiguous()
-    with torch.cuda.device(x.device), _timed("wgrad", 2.0 * n * ho * wo * cout * cin * r * s):
+    with torch.cuda.device(x.device), _timed("wgrad", 2.0 * n * ho * wo * cout * cin * r * s,
+                                              (n, h, w, cin, ho, wo, cout, r, stride, dil)):
         _lib.check(_lib.lib().aadg_conv_wgrad_bf16(x.data_ptr(), n, h, w, cin, ldx, dy.data_ptr(), ho, wo, cout, lddy,
                                                    r, s, stride, pad, dil, out.data_ptr(), _lib.stream_ptr()))
     return out

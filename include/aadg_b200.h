@@ -170,6 +170,12 @@ int aadg_sinkhorn_large_setup(const float* x, int n, const float* y, int m, int 
 int aadg_conv_fprop_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* wgt, int cout, int r,
                          int s, int stride, int pad, int dil, void* y, int ho, int wo, int ldy, int y_c_off,
                          int accumulate, void* stream);
+/* the same forward convolution plus the batch-norm statistics of its output in the same pass: stat_sum / stat_sq
+ * (fp32 [cout], ACCUMULATED -- zero them first) receive the per-channel sum and sum of squares of the bf16 values
+ * written to y (replaces aadg_bn_stats over y: BatchNorm2d batch statistics, smp Conv2dReLU / torchvision blocks) */
+int aadg_conv_fprop_stats_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* wgt, int cout, int r,
+                               int s, int stride, int pad, int dil, void* y, int ho, int wo, int ldy, int y_c_off,
+                               float* stat_sum, float* stat_sq, void* stream);
 
 /* Data gradient of the same convolution: dx (+)= conv_transpose(dy, w).  wgt_t bf16 [R*S][cin][cout]
  * (channel axes swapped); all geometry arguments are the forward convolution's. */

@@ -49,6 +49,10 @@ CASES = [
     (1, 130, 70, 64, 64, 3, 3, 1, 1, 1),
     (2, 17, 19, 192, 64, 1, 1, 1, 0, 1),
     (1, 30, 30, 64, 64, 7, 7, 2, 3, 1),
+    # enough 256-column tiles for the BN = 256 kernel
+    (8, 64, 64, 256, 512, 1, 1, 1, 0, 1),
+    (5, 64, 64, 64, 256, 3, 3, 1, 1, 1),
+    (6, 60, 50, 320, 256, 1, 1, 1, 0, 1),
 ]
 
 
@@ -114,3 +118,21 @@ def test_channel_slices_and_accumulate(conv):
     assert out_full[..., :128].abs().max() == 0 and out_full[..., 192:].abs().max() == 0
     conv.fprop(x, to_taps(wt), 3, 3, 1, 1, 1, out=out, accumulate=True)
     close(out, 2 * want, "accumulate")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fprop_fused_statistics(conv, case):
+    """the epilogue's per-channel sum / sum of squares equal those of the bf16 tensor it stored (partial tiles,
+    channel tails and the 64/128/256-column kernels included) and the output is unchanged"""
+    n, h, w, cin, cout, r, s, stride, pad, dil = case
+    x, wt = rand_case(n, h, w, cin, cout, r, s, seed=4)
+    ssum = torch.zeros(cout, device="cuda")
+    ssq = torch.zeros(cout, device="cuda")
+    y = conv.fprop(x, to_taps(wt), r, s, stride, pad, dil, stats=(ssum, ssq))
+    y0 = conv.fprop(x, to_taps(wt), r, s, stride, pad, dil)
+    assert torch.equal(y, y0)
+    yf = y.double().reshape(-1, cout)
+    want_sum, want_sq = yf.sum(0), (yf * yf).sum(0)
+    tol = 1e-4 * (yf.abs().sum(0) + 1e-3)
+    assert ((ssum.double() - want_sum).abs() <= tol).all(), (case, (ssum.double() - want_sum).abs().max().item())
+    assert ((ssq.double() - want_sq).abs() <= 1e-4 * want_sq + 1e-6).all(), case
