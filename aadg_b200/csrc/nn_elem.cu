@@ -251,8 +251,11 @@ __device__ __forceinline__ void bn_mask_apply(V8& d, const V8& xv, const V8& sc,
 }
 
 // dbeta = sum g ; dgamma = sum g * xhat  (`beta` = the forward shift vector when flag 4 is set)
-template <int MASK>
+// (all backward kernels: DY2 adds a second incoming gradient tensor on load -- the two branches of a residual block
+// are summed here instead of by a read-modify-write accumulation in the convolution that produced one of them)
+template <int MASK, bool DY2>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const bf16* __restrict__ dy, int lddy,
+                                                               const bf16* __restrict__ dy2, int lddy2,
                                                                const bf16* __restrict__ x, int ldx, const bf16* y, int ldy,
                                                                const float* mean, const float* invstd, const float* gamma,
                                                                const float* beta, long long P, int C, int flags,
@@ -270,13 +273,14 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const bf16* __res
     }
     const long long step = (long long)gridDim.x * blockDim.y;
     for (long long p0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; p0 < P; p0 += BN_U * step) {
-      uint4 dv[BN_U], xv[BN_U];
+      uint4 dv[BN_U], xv[BN_U], ev[DY2 ? BN_U : 1];
       BnMaskSrc<MASK> mv[BN_U];
 #pragma unroll
       for (int u = 0; u < BN_U; ++u) {
         const long long p = p0 + u * step;
         if (p < P) {
           dv[u] = ldg16(dy + p * lddy + g * 8);
+          if (DY2) ev[u] = ldg16(dy2 + p * lddy2 + g * 8);
           xv[u] = ldg16(x + p * ldx + g * 8);
           bn_mask_load(mv[u], y, ldy, p, G, g);
         }
@@ -286,6 +290,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const bf16* __res
         const long long p = p0 + u * step;
         if (p >= P) break;
         V8 d = unpack8(dv[u]);
+        if (DY2) {
+          const V8 d2 = unpack8(ev[u]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
+        }
         const V8 xx = unpack8(xv[u]);
         bn_mask_apply(d, xx, sc, sh, mv[u], flags, seed, p * G + g);
 #pragma unroll
@@ -299,8 +308,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const bf16* __res
 }
 
 // dx = gamma*invstd * (g - dbeta/P - xhat*dgamma/P) ; optional dres = g (gradient of the residual input)
-template <int MASK>
+template <int MASK, bool DY2>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __restrict__ dy, int lddy,
+                                                              const bf16* __restrict__ dy2, int lddy2,
                                                               const bf16* __restrict__ x, int ldx, const bf16* y, int ldy,
                                                               const float* mean, const float* invstd, const float* gamma,
                                                               const float* beta, const float* dgamma, const float* dbeta,
@@ -325,13 +335,14 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
   }
   const long long step = (long long)gridDim.x * blockDim.y;
   for (long long p0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; p0 < P; p0 += BN_U * step) {
-    uint4 dv[BN_U], xv[BN_U];
+    uint4 dv[BN_U], xv[BN_U], ev[DY2 ? BN_U : 1];
     BnMaskSrc<MASK> mv[BN_U];
 #pragma unroll
     for (int u = 0; u < BN_U; ++u) {
       const long long p = p0 + u * step;
       if (p < P) {
         dv[u] = ldg16(dy + p * lddy + g * 8);
+        if (DY2) ev[u] = ldg16(dy2 + p * lddy2 + g * 8);
         xv[u] = ldg16(x + p * ldx + g * 8);
         bn_mask_load(mv[u], y, ldy, p, G, g);
       }
@@ -341,6 +352,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
       const long long p = p0 + u * step;
       if (p >= P) break;
       V8 d = unpack8(dv[u]);
+      if (DY2) {
+        const V8 d2 = unpack8(ev[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
+      }
       const V8 xx = unpack8(xv[u]);
       bn_mask_apply(d, xx, sc, sh, mv[u], flags, seed, p * G + g);
       if (dres) {
@@ -928,10 +944,10 @@ int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift
   return check_launch("bn_apply");
 }
 
-int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
-                     const float* invstd, const float* gamma, const float* shift, long long pixels, int c, int flags,
-                     unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,
-                     int dres_accumulate, void* stream) {
+static int bn_backward_impl(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const void* y,
+                            int ldy, const float* mean, const float* invstd, const float* gamma, const float* shift,
+                            long long pixels, int c, int flags, unsigned long long seed, float* dgamma, float* dbeta,
+                            void* dx, int lddx, void* dres, int lddr, int dres_accumulate, void* stream) {
   NN_REQ_C(c);
   AADG_REQUIRE(pixels > 0 && pixels < (1ll << 31), "bad pixel count");
   cudaStream_t st = (cudaStream_t)stream;
@@ -942,17 +958,42 @@ int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const voi
   AADG_REQUIRE(!(flags & 4) || shift, "flag 4 needs the forward shift vector");
   const int mask = (flags & 4) ? 4 : (flags & 8) ? 8 : (flags & 1) ? 1 : 0;
   const int grid = stream_blocks(pixels, blk, 2);
-#define AADG_BN_BWD(MASK)                                                                                             \
-  {                                                                                                                   \
-    bn_bwd_reduce_kernel<MASK><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y, ldy,  \
-                                                     mean, invstd, gamma, shift, pixels, c, flags, seed, dgamma, dbeta); \
-    bn_bwd_apply_kernel<MASK><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)y, ldy,   \
-                                                    mean, invstd, gamma, shift, dgamma, dbeta, pixels, c, flags, seed, \
-                                                    (bf16*)dx, lddx, (bf16*)dres, lddr, dres_accumulate);              \
+#define AADG_BN_BWD(MASK, DY2)                                                                                         \
+  {                                                                                                                    \
+    bn_bwd_reduce_kernel<MASK, DY2><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)dy2, lddy2, (const bf16*)x, \
+                                                          ldx, (const bf16*)y, ldy, mean, invstd, gamma, shift, pixels, c, \
+                                                          flags, seed, dgamma, dbeta);                                  \
+    bn_bwd_apply_kernel<MASK, DY2><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)dy2, lddy2, (const bf16*)x,  \
+                                                         ldx, (const bf16*)y, ldy, mean, invstd, gamma, shift, dgamma,   \
+                                                         dbeta, pixels, c, flags, seed, (bf16*)dx, lddx, (bf16*)dres,    \
+                                                         lddr, dres_accumulate);                                        \
   }
-  if (mask == 4) AADG_BN_BWD(4) else if (mask == 8) AADG_BN_BWD(8) else if (mask == 1) AADG_BN_BWD(1) else AADG_BN_BWD(0)
+  if (dy2) {
+    if (mask == 4) AADG_BN_BWD(4, true) else if (mask == 8) AADG_BN_BWD(8, true) else if (mask == 1) AADG_BN_BWD(1, true) else AADG_BN_BWD(0, true)
+  } else {
+    if (mask == 4) AADG_BN_BWD(4, false) else if (mask == 8) AADG_BN_BWD(8, false) else if (mask == 1) AADG_BN_BWD(1, false) else AADG_BN_BWD(0, false)
+  }
 #undef AADG_BN_BWD
   return check_launch("bn_backward");
+}
+
+int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
+                     const float* invstd, const float* gamma, const float* shift, long long pixels, int c, int flags,
+                     unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,
+                     int dres_accumulate, void* stream) {
+  return bn_backward_impl(dy, lddy, nullptr, 0, x, ldx, y, ldy, mean, invstd, gamma, shift, pixels, c, flags, seed, dgamma,
+                          dbeta, dx, lddx, dres, lddr, dres_accumulate, stream);
+}
+
+/* the same backward with the incoming gradient given as the sum of two tensors (dy + dy2): the two gradient
+ * branches that meet at a residual block's input are added on load */
+int aadg_bn_backward2(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const void* y, int ldy,
+                      const float* mean, const float* invstd, const float* gamma, const float* shift, long long pixels,
+                      int c, int flags, unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx,
+                      void* dres, int lddr, int dres_accumulate, void* stream) {
+  AADG_REQUIRE(dy2, "dy2 is required (use aadg_bn_backward for a single gradient tensor)");
+  return bn_backward_impl(dy, lddy, dy2, lddy2, x, ldx, y, ldy, mean, invstd, gamma, shift, pixels, c, flags, seed, dgamma,
+                          dbeta, dx, lddx, dres, lddr, dres_accumulate, stream);
 }
 
 int aadg_add_bf16(void* a, int lda, const void* b, int ldb, long long pixels, int c, void* stream) {

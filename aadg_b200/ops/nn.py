@@ -43,14 +43,20 @@ def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None, relu_bi
 
 
 def bn_backward(dy, x, y, mean, invstd, gamma, dgamma, dbeta, dx, relu=True, dropout_seed=None, dres=None,
-                dres_accumulate=False, shift=None):
-    """y=None with relu=True recomputes the ReLU mask from x and the forward `shift` (no residual case)."""
+                dres_accumulate=False, shift=None, dy2=None):
+    """y=None with relu=True recomputes the ReLU mask from x and the forward `shift` (no residual case).
+    dy2: a second gradient tensor added to dy on load."""
     bits = y is not None and y.dtype == torch.uint8        # relu bit mask written by bn_apply(relu_bits=...)
     flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (4 if (relu and y is None) else 0) | \
         (8 if bits else 0)
-    _call("aadg_bn_backward", p(dy), _ld(dy), p(x), _ld(x), p(y), _ld(y) if (y is not None and not bits) else 0, p(mean), p(invstd),
-          p(gamma), p(shift), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
-          p(dres), _ld(dres) if dres is not None else 0, int(dres_accumulate))
+    tail = (p(x), _ld(x), p(y), _ld(y) if (y is not None and not bits) else 0, p(mean), p(invstd),
+            p(gamma), p(shift), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
+            p(dres), _ld(dres) if dres is not None else 0, int(dres_accumulate))
+    if dy2 is None:
+        _call("aadg_bn_backward", p(dy), _ld(dy), *tail)
+    else:
+        assert dy2.shape == dy.shape
+        _call("aadg_bn_backward2", p(dy), _ld(dy), p(dy2), _ld(dy2), *tail)
 
 
 def add_(a, b):

@@ -228,12 +228,16 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_issue = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_issue["ms"] = (time.perf_counter() - t0) * 1e3 / steps     # CPU time to enqueue one step (no sync)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -262,6 +266,7 @@ def run_ours(a):
     calls0 = _lib.CALLS
     ms = timed(step_resident, a.steps)
     launches = (_lib.CALLS - calls0)
+    host_ms = host_issue.get("ms")
     conv_records = C.TIMING
     C.TIMING = None
     clk = clocks.stop() if rank == 0 else None
@@ -309,7 +314,7 @@ def run_ours(a):
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": int(h_imgs.numel() + h_masks.numel()) + 160 * n_img + 4 * d * n_img,
                     "d2h_bytes_per_step": 16},
-            "gpu_launches": launches, "roofline": roof}
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "roofline": roof}
     if world == 1 and not a.no_cpu_baseline:
         try:
             v, info = cpu_joint_step_sample(a)

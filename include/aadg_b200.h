@@ -212,6 +212,12 @@ int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const voi
                      const float* invstd, const float* gamma, const float* shift, long long pixels, int c, int flags,
                      unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,
                      int dres_accumulate, void* stream);
+/* the same backward with the incoming gradient given as dy + dy2 (two gradient branches meeting at a residual
+ * block's input are added on load instead of by a read-modify-write pass) */
+int aadg_bn_backward2(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const void* y, int ldy,
+                      const float* mean, const float* invstd, const float* gamma, const float* shift, long long pixels,
+                      int c, int flags, unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx,
+                      void* dres, int lddr, int dres_accumulate, void* stream);
 int aadg_add_bf16(void* a, int lda, const void* b, int ldb, long long pixels, int c, void* stream);
 /* MaxPool2d(3, stride 2, padding 1): argmax uint8 [n,ho,wo,c] */
 int aadg_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, void* y, void* argmax, void* stream);
