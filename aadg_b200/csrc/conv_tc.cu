@@ -1020,10 +1020,14 @@ int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, c
       a.taps.dx[i * s + j] = (short)(j * dil - pad);
       a.taps.w[i * s + j] = (short)(i * s + j);
     }
-  const int bn = cin <= 64 ? 64 : 128;
+  // 256-wide Cin tiles halve the dY traffic per flop (one CTA per SM pair of stages in flight instead of four small ones)
+  static int wide_mode = -1;
+  if (wide_mode < 0) { const char* e = getenv("AADG_WGRAD_BN256"); wide_mode = e ? atoi(e) : 0; }   // measured neutral on the ResNet-50 step: off by default
   const int n_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const bool wide = wide_mode > 0 && cin % 256 == 0 && n_tiles >= 64;
+  const int bn = cin <= 64 ? 64 : (wide ? 256 : 128);
   const int base_ctas = ((cout + 127) / 128) * ((cin + bn - 1) / bn) * r * s;
-  int ksplit = (148 * 4 + base_ctas - 1) / base_ctas;
+  int ksplit = (148 * (wide ? 2 : 4) + base_ctas - 1) / base_ctas;
   ksplit = std::max(1, std::min(ksplit, (n_tiles + 7) / 8));
   ksplit = std::min(ksplit, 65535 / (r * s));
   a.ksplit = ksplit;
@@ -1046,6 +1050,10 @@ int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, c
   }
   dim3 grid((cout + 127) / 128, (cin + bn - 1) / bn, r * s * ksplit);
   const int stages = tuning_stages();
+  if (bn == 256) {
+    if (wide_mode == 3) return launch_wgrad_t<256, 3>(mDY, mX, a, grid, (cudaStream_t)stream);
+    return launch_wgrad_t<256, 2>(mDY, mX, a, grid, (cudaStream_t)stream);
+  }
   if (bn == 64) {
     if (stages == 2) return launch_wgrad_t<64, 2>(mDY, mX, a, grid, (cudaStream_t)stream);
     if (stages == 3) return launch_wgrad_t<64, 3>(mDY, mX, a, grid, (cudaStream_t)stream);

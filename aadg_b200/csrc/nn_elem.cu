@@ -147,13 +147,14 @@ __global__ void __launch_bounds__(256, 4) bn_stats_kernel(const bf16* __restrict
 }
 
 // mean / invstd, fused scale-shift for the apply pass, running statistics (momentum 0.1, unbiased var)
-__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const float* gamma, const float* beta,
+__global__ void bn_finalize_kernel(float* sum, float* sumsq, const float* gamma, const float* beta,
                                    int C, float count, float eps, float momentum, float* mean, float* invstd,
-                                   float* scale, float* shift, float* run_mean, float* run_var) {
+                                   float* scale, float* shift, float* run_mean, float* run_var, int reset_sums) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float m = sum[c] / count;
   const float var = fmaxf(sumsq[c] / count - m * m, 0.f);
+  if (reset_sums) { sum[c] = 0.f; sumsq[c] = 0.f; }     // ready for the next accumulation (no separate memset launch)
   const float is = rsqrtf(var + eps);
   mean[c] = m; invstd[c] = is;
   const float sc = gamma[c] * is;
@@ -925,11 +926,12 @@ int aadg_bn_stats(const void* x, long long pixels, int c, int ld, float* sum, fl
   return check_launch("bn_stats");
 }
 
-int aadg_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int c, float count,
+int aadg_bn_finalize(float* sum, float* sumsq, const float* gamma, const float* beta, int c, float count,
                      float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
-                     float* run_mean, float* run_var, void* stream) {
+                     float* run_mean, float* run_var, int reset_sums, void* stream) {
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, gamma, beta, c, count, eps, momentum,
-                                                                        mean, invstd, scale, shift, run_mean, run_var);
+                                                                        mean, invstd, scale, shift, run_mean, run_var,
+                                                                        reset_sums);
   return check_launch("bn_finalize");
 }
 
@@ -951,8 +953,10 @@ static int bn_backward_impl(const void* dy, int lddy, const void* dy2, int lddy2
   NN_REQ_C(c);
   AADG_REQUIRE(pixels > 0 && pixels < (1ll << 31), "bad pixel count");
   cudaStream_t st = (cudaStream_t)stream;
-  AADG_CUDA_TRY(cudaMemsetAsync(dgamma, 0, sizeof(float) * c, st));
-  AADG_CUDA_TRY(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
+  if (!(flags & 16)) {     // flag 16: dgamma / dbeta are accumulated into (the caller zeroed its gradient buffer)
+    AADG_CUDA_TRY(cudaMemsetAsync(dgamma, 0, sizeof(float) * c, st));
+    AADG_CUDA_TRY(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
+  }
   const dim3 blk = reduce_block(c);
   AADG_REQUIRE(!(flags & 1) || (flags & 4) || y, "ReLU mask needs y / the bit mask (or flag 4 to recompute it from x)");
   AADG_REQUIRE(!(flags & 4) || shift, "flag 4 needs the forward shift vector");

@@ -160,8 +160,8 @@ class BatchNorm:
         self.buf = torch.zeros(6, c, device=dev)    # sum, sumsq, mean, invstd, scale, shift
 
     def stats_buffers(self):
-        """zeroed (sum, sumsq) accumulators for a convolution epilogue to fill (C.fprop(stats=...))"""
-        self.buf[:2].zero_()
+        """zeroed (sum, sumsq) accumulators for a convolution epilogue to fill (C.fprop(stats=...)): they start at zero
+        and bn_finalize(reset_sums=True) zeroes them again after reading"""
         return self.buf[0], self.buf[1]
 
     def forward(self, x, y, training, res=None, relu=True, dropout_seed=None, relu_bits=None, have_stats=False):
@@ -172,7 +172,7 @@ class BatchNorm:
                 K.bn_stats(x, s[0], s[1])
             count = x.numel() // x.shape[-1]
             K.bn_finalize(s[0], s[1], self.gamma.data, self.beta.data, count, BN_EPS, BN_MOMENTUM, s[2], s[3], s[4],
-                          s[5], self.running_mean, self.running_var)
+                          s[5], self.running_mean, self.running_var, reset_sums=True)
             self.num_batches_tracked += 1
         else:
             torch.rsqrt(self.running_var + BN_EPS, out=s[3])
@@ -180,14 +180,15 @@ class BatchNorm:
             torch.mul(self.gamma.data, s[3], out=s[4])
             torch.sub(self.beta.data, s[2] * s[4], out=s[5])
         K.bn_apply(x, s[4], s[5], y, res=res, relu=relu, dropout_seed=dropout_seed, relu_bits=relu_bits)
-        self.saved = s[2:6].clone() if training else None       # mean, invstd, scale, shift
+        self.saved = s[2:6] if training else None       # mean, invstd, scale, shift (this layer's own buffer)
 
     def backward(self, dy, x, y, dx, relu=True, dropout_seed=None, dres=None, dres_accumulate=False, dy2=None):
         """y=None: no residual was added in forward, the ReLU mask is recomputed from x (saves reading y).
         dy2: second gradient branch, added to dy on load."""
         sv = self.saved
         K.bn_backward(dy, x, y, sv[0], sv[1], self.gamma.data, self.gamma.grad, self.beta.grad, dx, relu=relu,
-                      dropout_seed=dropout_seed, dres=dres, dres_accumulate=dres_accumulate, shift=sv[3], dy2=dy2)
+                      dropout_seed=dropout_seed, dres=dres, dres_accumulate=dres_accumulate, shift=sv[3], dy2=dy2,
+                      grads_zeroed=True)       # gamma.grad / beta.grad: slices of the flat buffer zero_grad() cleared
         self.saved = None
 
 

@@ -31,9 +31,10 @@ def bn_stats(x, sum_, sumsq):
     _call("aadg_bn_stats", p(x), _pix(x), x.shape[-1], _ld(x), p(sum_), p(sumsq))
 
 
-def bn_finalize(sum_, sumsq, gamma, beta, count, eps, momentum, mean, invstd, scale, shift, run_mean, run_var):
+def bn_finalize(sum_, sumsq, gamma, beta, count, eps, momentum, mean, invstd, scale, shift, run_mean, run_var,
+                reset_sums=False):
     _call("aadg_bn_finalize", p(sum_), p(sumsq), p(gamma), p(beta), gamma.numel(), float(count), eps, momentum,
-          p(mean), p(invstd), p(scale), p(shift), p(run_mean), p(run_var))
+          p(mean), p(invstd), p(scale), p(shift), p(run_mean), p(run_var), int(reset_sums))
 
 
 def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None, relu_bits=None):
@@ -43,12 +44,12 @@ def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None, relu_bi
 
 
 def bn_backward(dy, x, y, mean, invstd, gamma, dgamma, dbeta, dx, relu=True, dropout_seed=None, dres=None,
-                dres_accumulate=False, shift=None, dy2=None):
+                dres_accumulate=False, shift=None, dy2=None, grads_zeroed=False):
     """y=None with relu=True recomputes the ReLU mask from x and the forward `shift` (no residual case).
     dy2: a second gradient tensor added to dy on load."""
     bits = y is not None and y.dtype == torch.uint8        # relu bit mask written by bn_apply(relu_bits=...)
     flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (4 if (relu and y is None) else 0) | \
-        (8 if bits else 0)
+        (8 if bits else 0) | (16 if grads_zeroed else 0)
     tail = (p(x), _ld(x), p(y), _ld(y) if (y is not None and not bits) else 0, p(mean), p(invstd),
             p(gamma), p(shift), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
             p(dres), _ld(dres) if dres is not None else 0, int(dres_accumulate))

@@ -196,10 +196,11 @@ int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, c
 
 /* sum[c] += sum_p x[p][c]; sumsq[c] += sum_p x[p][c]^2 (fp32; zero them first) */
 int aadg_bn_stats(const void* x, long long pixels, int c, int ld, float* sum, float* sumsq, void* stream);
-/* mean, 1/sqrt(var+eps), scale = gamma*invstd, shift = beta - mean*scale, running stats (may be NULL) */
-int aadg_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int c, float count,
+/* mean, 1/sqrt(var+eps), scale = gamma*invstd, shift = beta - mean*scale, running stats (may be NULL);
+ * reset_sums != 0 zeroes sum / sumsq after reading them (ready for the next accumulation) */
+int aadg_bn_finalize(float* sum, float* sumsq, const float* gamma, const float* beta, int c, float count,
                      float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
-                     float* run_mean, float* run_var, void* stream);
+                     float* run_mean, float* run_var, int reset_sums, void* stream);
 /* y = act(x*scale + shift (+ res)) ; flags bit0 = ReLU, bit1 = Dropout(0.5) keyed by (seed, element);
  * relu_bits (may be NULL): uint8 [pixels][c/8], bit i of byte g = (pre-activation of channel 8g+i > 0) */
 int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr, void* y,
@@ -207,7 +208,9 @@ int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift
                   void* stream);
 /* backward of aadg_bn_apply(training statistics): dgamma, dbeta (overwritten), dx, optional dres (+=).
  * flags bit2 (4): no residual was added, recompute the ReLU mask from x and the forward pass's `shift`
- * vector (y and ldy unused); flags bit3 (8): `y` points to the relu_bits written by aadg_bn_apply */
+ * vector (y and ldy unused); flags bit3 (8): `y` points to the relu_bits written by aadg_bn_apply;
+ * flags bit4 (16): dgamma / dbeta are NOT cleared first -- they must be zero on entry (a gradient buffer the caller
+ * zeroed once per step), which saves two memset launches per layer */
 int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
                      const float* invstd, const float* gamma, const float* shift, long long pixels, int c, int flags,
                      unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx, void* dres, int lddr,

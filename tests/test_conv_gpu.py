@@ -53,6 +53,7 @@ CASES = [
     (8, 64, 64, 256, 512, 1, 1, 1, 0, 1),
     (5, 64, 64, 64, 256, 3, 3, 1, 1, 1),
     (6, 60, 50, 320, 256, 1, 1, 1, 0, 1),
+    (4, 32, 32, 256, 128, 3, 3, 1, 1, 1),       # 256-wide weight-gradient tiles
 ]
 
 
