@@ -25,6 +25,10 @@ int dwconv3x3_generic(const void* x, int n, int h, int w, int c, int ldx, const 
                       void* y, int ldy, cudaStream_t st);
 int dwconv3x3_wgrad_generic(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil,
                             float* dw, cudaStream_t st);
+int dwconv3x3_strided(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int stride, int direction,
+                      void* y, int ho, int wo, int ldy, cudaStream_t st);
+int dwconv3x3_strided_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int ho, int wo, int lddy,
+                            int dil, int stride, float* dw, cudaStream_t st);
 }  // namespace nn
 
 namespace dw {
@@ -434,6 +438,31 @@ int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, con
     return check_launch("dwconv3x3 direct wgrad");
   }
   return nn::dwconv3x3_wgrad_generic(x, n, h, w, c, ldx, dy, lddy, dil, dwgt, st);
+}
+
+/* strided depthwise 3x3 (padding = dilation, output ho x wo = floor((h-1)/stride)+1 ...): the down-sampling blocks of
+ * MobileNetV2.  direction 0: y [n,ho,wo] <- x [n,h,w]; direction 1 (data gradient): `x` is dy [n,ho,wo] with stride
+ * ldx, `y` is dx [n,h,w] with stride ldy.  stride 1 is forwarded to aadg_dwconv3x3. */
+int aadg_dwconv3x3_strided(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int stride,
+                           int direction, void* y, int ho, int wo, int ldy, void* stream) {
+  DW_REQ_C(c);
+  AADG_REQUIRE(stride >= 1 && dil >= 1 && h > 0 && w > 0 && n > 0, "bad depthwise geometry");
+  AADG_REQUIRE(ho == (h - 1) / stride + 1 && wo == (w - 1) / stride + 1, "output size mismatch: expected %dx%d", (h - 1) / stride + 1,
+               (w - 1) / stride + 1);
+  if (stride == 1) return aadg_dwconv3x3(x, n, h, w, c, ldx, wgt, dil, direction, y, ldy, stream);
+  AADG_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0,
+               "depthwise tensors must be 16-byte aligned with channel strides that are multiples of 8");
+  return nn::dwconv3x3_strided(x, n, h, w, c, ldx, wgt, dil, stride, direction, y, ho, wo, ldy, (cudaStream_t)stream);
+}
+int aadg_dwconv3x3_strided_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int ho, int wo, int lddy,
+                                 int dil, int stride, float* dwgt, void* stream) {
+  DW_REQ_C(c);
+  AADG_REQUIRE(stride >= 1 && dil >= 1 && h > 0 && w > 0 && n > 0, "bad depthwise geometry");
+  AADG_REQUIRE(ho == (h - 1) / stride + 1 && wo == (w - 1) / stride + 1, "output size mismatch");
+  if (stride == 1) return aadg_dwconv3x3_wgrad(x, n, h, w, c, ldx, dy, lddy, dil, dwgt, stream);
+  AADG_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0,
+               "depthwise tensors must be 16-byte aligned with channel strides that are multiples of 8");
+  return nn::dwconv3x3_strided_wgrad(x, n, h, w, c, ldx, dy, ho, wo, lddy, dil, stride, dwgt, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -206,6 +206,10 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const bf16* __restrict
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(v.v[i], 0.f);
+        if (flags & 32) {     // ReLU6
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v.v[i] = fminf(v.v[i], 6.f);
+        }
       }
       if (flags & 2) {
         const unsigned int keep = dropout_bits8(seed, (unsigned long long)e * 8);
@@ -231,9 +235,13 @@ __device__ __forceinline__ void bn_mask_load(BnMaskSrc<MASK>& m, const bf16* y, 
 template <int MASK>
 __device__ __forceinline__ void bn_mask_apply(V8& d, const V8& xv, const V8& sc, const V8& sh, const BnMaskSrc<MASK>& m,
                                               int flags, unsigned long long seed, long long e) {
+  const float hi = (flags & 32) ? 6.f : INFINITY;      // ReLU6: the gradient also vanishes where the output saturates
   if constexpr (MASK == 4) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d.v[i] = fmaf(xv.v[i], sc.v[i], sh.v[i]) > 0.f ? d.v[i] : 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const float t = fmaf(xv.v[i], sc.v[i], sh.v[i]);
+      d.v[i] = (t > 0.f && t < hi) ? d.v[i] : 0.f;
+    }
   }
   if constexpr (MASK == 8) {
 #pragma unroll
@@ -242,7 +250,7 @@ __device__ __forceinline__ void bn_mask_apply(V8& d, const V8& xv, const V8& sc,
   if constexpr (MASK == 1) {
     const V8 yv = unpack8(m.v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
+    for (int i = 0; i < 8; ++i) d.v[i] = (yv.v[i] > 0.f && yv.v[i] < hi) ? d.v[i] : 0.f;
   }
   if (flags & 2) {
     const unsigned int keep = dropout_bits8(seed, (unsigned long long)e * 8);
@@ -708,6 +716,105 @@ __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
     st8(yrow + (size_t)ox * ldy + g * 8, acc);
   }
 }
+// ---- strided depthwise 3x3 (MobileNetV2 down-sampling blocks): padding = dilation, output (ho, wo) ---------------
+// forward: y[n,oy,ox,c] = sum_t w[t][c] * x[n, oy*stride + (r-1)*dil, ox*stride + (s-1)*dil, c]
+__global__ void __launch_bounds__(256) dw3x3_strided_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int ldx,
+                                                                const float* __restrict__ wgt, int dil, int stride,
+                                                                bf16* __restrict__ y, int Ho, int Wo, int ldy) {
+  const int G = C >> 3;
+  const long long total = (long long)N * Ho * Wo * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % G);
+    long long p = e / G;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    V8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy * stride + (r - 1) * dil;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int ix = ox * stride + (s2 - 1) * dil;
+        if (ix < 0 || ix >= W) continue;
+        const V8 v = unpack8(ldg16(x + (((size_t)n * H + iy) * W + ix) * ldx + g * 8));
+        const V8 wv = ld8f(wgt + (r * 3 + s2) * C + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wv.v[i], v.v[i], acc.v[i]);
+      }
+    }
+    st8(y + (((size_t)n * Ho + oy) * Wo + ox) * ldy + g * 8, acc);
+  }
+}
+// data gradient (gather form): dx[n,iy,ix,c] = sum over taps with (iy - (r-1)*dil) divisible by stride of w[t][c] * dy[...]
+__global__ void __launch_bounds__(256) dw3x3_strided_dgrad_kernel(const bf16* __restrict__ dy, int N, int Ho, int Wo, int C,
+                                                                  int lddy, const float* __restrict__ wgt, int dil, int stride,
+                                                                  bf16* __restrict__ dx, int H, int W, int lddx) {
+  const int G = C >> 3;
+  const long long total = (long long)N * H * W * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % G);
+    long long p = e / G;
+    const int ix = (int)(p % W); p /= W;
+    const int iy = (int)(p % H);
+    const int n = (int)(p / H);
+    V8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ty = iy - (r - 1) * dil;
+      if (ty < 0 || ty % stride) continue;
+      const int oy = ty / stride;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int tx = ix - (s2 - 1) * dil;
+        if (tx < 0 || tx % stride) continue;
+        const int ox = tx / stride;
+        if (ox >= Wo) continue;
+        const V8 v = unpack8(ldg16(dy + (((size_t)n * Ho + oy) * Wo + ox) * lddy + g * 8));
+        const V8 wv = ld8f(wgt + (r * 3 + s2) * C + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wv.v[i], v.v[i], acc.v[i]);
+      }
+    }
+    st8(dx + (((size_t)n * H + iy) * W + ix) * lddx + g * 8, acc);
+  }
+}
+// weight gradient: dw[t][c] += sum over output pixels of dy[o][c] * x[o*stride + off_t][c]; block (TX groups, TY lanes)
+__global__ void __launch_bounds__(256) dw3x3_strided_wgrad_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int ldx,
+                                                                  const bf16* __restrict__ dy, int Ho, int Wo, int lddy,
+                                                                  int dil, int stride, float* dw) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int r = blockIdx.y;                      // filter row
+  const long long P = (long long)N * Ho * Wo;
+  float acc[3][8] = {};
+  if (tx < (C >> 3))
+    for (long long p = (long long)blockIdx.x * blockDim.y + ty; p < P; p += (long long)gridDim.x * blockDim.y) {
+      const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), n = (int)(p / ((long long)Wo * Ho));
+      const int iy = oy * stride + (r - 1) * dil;
+      if (iy < 0 || iy >= H) continue;
+      const V8 d = unpack8(ldg16(dy + (size_t)p * lddy + tx * 8));
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int ix = ox * stride + (s2 - 1) * dil;
+        if (ix < 0 || ix >= W) continue;
+        const V8 v = unpack8(ldg16(x + (((size_t)n * H + iy) * W + ix) * ldx + tx * 8));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[s2][i] = fmaf(d.v[i], v.v[i], acc[s2][i]);
+      }
+    }
+  // fold the three taps of this filter row: reuse the two-array block reduction twice
+  float z[8] = {};
+  block_channel_sum<2>(C, acc[0], acc[1], dw + (size_t)(r * 3 + 0) * C, dw + (size_t)(r * 3 + 1) * C);
+  __syncthreads();
+  block_channel_sum<1>(C, acc[2], z, dw + (size_t)(r * 3 + 2) * C, nullptr);
+}
+
 // dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]; blockIdx.y = filter row r (3 taps, 24 register accumulators),
 // the three launches' dy reads overlap in L2; block reduction in shared memory [3][C], then atomics
 __global__ void __launch_bounds__(256, 3) dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
@@ -906,6 +1013,27 @@ int dwconv3x3_wgrad_generic(const void* x, int n, int h, int w, int c, int ldx, 
   dim3 grid(std::max(blocks, 1), 3);
   dw3x3_wgrad_kernel<<<grid, blk, smem, st>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, lddy, dil, dw);
   return check_launch("dwconv3x3 wgrad");
+}
+
+int dwconv3x3_strided(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int stride, int direction,
+                      void* y, int ho, int wo, int ldy, cudaStream_t st) {
+  if (direction == 0)
+    dw3x3_strided_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), 256, 0, st>>>(
+        (const bf16*)x, n, h, w, c, ldx, wgt, dil, stride, (bf16*)y, ho, wo, ldy);
+  else      // x = dy [n,ho,wo], y = dx [n,h,w]
+    dw3x3_strided_dgrad_kernel<<<grid_for((long long)n * h * w * (c / 8)), 256, 0, st>>>(
+        (const bf16*)x, n, ho, wo, c, ldx, wgt, dil, stride, (bf16*)y, h, w, ldy);
+  return check_launch("dwconv3x3 strided");
+}
+int dwconv3x3_strided_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int ho, int wo, int lddy,
+                            int dil, int stride, float* dw, cudaStream_t st) {
+  const long long pixels = (long long)n * ho * wo;
+  const dim3 blk = reduce_block(c);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((pixels + blk.y * 16 - 1) / (blk.y * 16), 148 * 4));
+  dim3 grid(blocks, 3);
+  dw3x3_strided_wgrad_kernel<<<grid, blk, 0, st>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy, ho, wo, lddy, dil, stride,
+                                                  dw);
+  return check_launch("dwconv3x3 strided wgrad");
 }
 
 }  // namespace nn

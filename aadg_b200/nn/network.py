@@ -164,7 +164,8 @@ class BatchNorm:
         and bn_finalize(reset_sums=True) zeroes them again after reading"""
         return self.buf[0], self.buf[1]
 
-    def forward(self, x, y, training, res=None, relu=True, dropout_seed=None, relu_bits=None, have_stats=False):
+    def forward(self, x, y, training, res=None, relu=True, dropout_seed=None, relu_bits=None, have_stats=False,
+                relu6=False):
         s = self.buf
         if training:
             if not have_stats:
@@ -179,16 +180,18 @@ class BatchNorm:
             s[2].copy_(self.running_mean)
             torch.mul(self.gamma.data, s[3], out=s[4])
             torch.sub(self.beta.data, s[2] * s[4], out=s[5])
-        K.bn_apply(x, s[4], s[5], y, res=res, relu=relu, dropout_seed=dropout_seed, relu_bits=relu_bits)
+        K.bn_apply(x, s[4], s[5], y, res=res, relu=relu, dropout_seed=dropout_seed, relu_bits=relu_bits, relu6=relu6)
         self.saved = s[2:6] if training else None       # mean, invstd, scale, shift (this layer's own buffer)
 
-    def backward(self, dy, x, y, dx, relu=True, dropout_seed=None, dres=None, dres_accumulate=False, dy2=None):
+    def backward(self, dy, x, y, dx, relu=True, dropout_seed=None, dres=None, dres_accumulate=False, dy2=None,
+                 relu6=False):
         """y=None: no residual was added in forward, the ReLU mask is recomputed from x (saves reading y).
         dy2: second gradient branch, added to dy on load."""
         sv = self.saved
         K.bn_backward(dy, x, y, sv[0], sv[1], self.gamma.data, self.gamma.grad, self.beta.grad, dx, relu=relu,
                       dropout_seed=dropout_seed, dres=dres, dres_accumulate=dres_accumulate, shift=sv[3], dy2=dy2,
-                      grads_zeroed=True)       # gamma.grad / beta.grad: slices of the flat buffer zero_grad() cleared
+                      grads_zeroed=True,       # gamma.grad / beta.grad: slices of the flat buffer zero_grad() cleared
+                      relu6=relu6)
         self.saved = None
 
 
@@ -197,7 +200,8 @@ class ConvBN:
 
     def __init__(self, store, conv_name, bn_name, cin, cout, k=1, stride=1, pad=0, dil=1, relu=True, init=None,
                  need_dgrad=True):
-        self.cin, self.cout, self.k, self.stride, self.pad, self.dil, self.relu = cin, cout, k, stride, pad, dil, relu
+        self.cin, self.cout, self.k, self.stride, self.pad, self.dil = cin, cout, k, stride, pad, dil
+        self.relu, self.relu6 = bool(relu), relu == "relu6"
         init = init or kaiming_fan_out
         self.w = store.add(conv_name + ".weight", (k * k, cout, cin), "conv" if need_dgrad else "conv_nt",
                            lambda s: to_taps(init((cout, cin, k, k))))
@@ -221,7 +225,7 @@ class ConvBN:
         if training and res is not None and self.relu:
             bits = torch.empty((pre.numel() // 8,), dtype=torch.uint8, device=x.device)
         self.bn.forward(pre, out, training, res=res, relu=self.relu, dropout_seed=dropout_seed, relu_bits=bits,
-                        have_stats=fused)
+                        have_stats=fused, relu6=self.relu6)
         self.ctx = (x, pre, bits, dropout_seed) if training else None
         return out
 
@@ -234,7 +238,7 @@ class ConvBN:
         if want_dres and dres is None:
             dres = torch.empty(pre.shape, dtype=BF16, device=pre.device)
         self.bn.backward(dy, pre, y, dpre, relu=self.relu, dropout_seed=seed, dres=dres if want_dres else None,
-                         dres_accumulate=dres_accumulate, dy2=dy2)
+                         dres_accumulate=dres_accumulate, dy2=dy2, relu6=self.relu6)
         C.wgrad(x, dpre, self.k, self.k, self.stride, self.pad, self.dil, out=self.w.grad)
         if self.need_dgrad:
             dx = C.dgrad(dpre, self.w.bf16_t, self.k, self.k, self.stride, self.pad, self.dil, x.shape[1:3], out=dx,
@@ -245,23 +249,26 @@ class ConvBN:
 
 
 class Depthwise3x3:
-    def __init__(self, store, name, c, dil):
-        self.c, self.dil = c, dil
+    def __init__(self, store, name, c, dil, stride=1, init=None):
+        self.c, self.dil, self.stride = c, dil, stride
+        init = init or kaiming_uniform_default
         self.w = store.add(name + ".weight", (9, c), "f32",
-                           lambda s: kaiming_uniform_default((c, 1, 3, 3)).reshape(c, 9).t().contiguous())
+                           lambda s: init((c, 1, 3, 3)).reshape(c, 9).t().contiguous())
 
     def forward(self, x, training):
-        y = torch.empty(x.shape, dtype=BF16, device=x.device)
-        K.dwconv3x3(x, self.w.data, self.dil, y)
+        n, h, w, c = x.shape
+        ho, wo = (h - 1) // self.stride + 1, (w - 1) // self.stride + 1
+        y = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+        K.dwconv3x3(x, self.w.data, self.dil, y, stride=self.stride)
         self.ctx = x if training else None
         return y
 
     def backward(self, dy):
         x = self.ctx
         self.ctx = None
-        K.dwconv3x3_wgrad(x, dy, self.dil, self.w.grad)
+        K.dwconv3x3_wgrad(x, dy, self.dil, self.w.grad, stride=self.stride)
         dx = torch.empty(x.shape, dtype=BF16, device=x.device)
-        K.dwconv3x3(dy, self.w.data, self.dil, dx, backward_data=True)
+        K.dwconv3x3(dy, self.w.data, self.dil, dx, backward_data=True, stride=self.stride)
         return dx
 
 
@@ -411,6 +418,133 @@ class ResNetEncoder:
         C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad)
 
 
+class DepthwiseBN:
+    """Conv2d(c, c, 3, stride, padding=dil, dilation=dil, groups=c, bias=False) -> BatchNorm2d -> ReLU6 (torchvision
+    ConvBNActivation inside MobileNetV2's InvertedResidual)"""
+
+    def __init__(self, store, conv_name, bn_name, c, stride, dil):
+        self.dw = Depthwise3x3(store, conv_name, c, dil, stride, init=kaiming_fan_out)
+        self.bn = BatchNorm(store, bn_name, c)
+
+    def forward(self, x, training):
+        pre = self.dw.forward(x, training)
+        y = torch.empty_like(pre)
+        self.bn.forward(pre, y, training, relu=True, relu6=True)
+        self.ctx = pre if training else None
+        return y
+
+    def backward(self, dy):
+        pre = self.ctx
+        self.ctx = None
+        dpre = torch.empty_like(pre)
+        self.bn.backward(dy, pre, None, dpre, relu=True, relu6=True)
+        return self.dw.backward(dpre)
+
+
+class InvertedResidual:
+    """torchvision MobileNetV2 block: [1x1 expand + BN + ReLU6] -> depthwise 3x3 + BN + ReLU6 -> 1x1 project + BN (linear),
+    identity added when stride == 1 and cin == cout.  state_dict names: features.i.conv.{0.0,0.1,1.0,1.1,2,3}
+    (expand ratio 1: conv.{0.0,0.1,1,2})."""
+
+    def __init__(self, store, name, cin, cout, stride, expand, dil=1):
+        hid = cin * expand
+        n = name + ".conv."
+        self.expand = ConvBN(store, n + "0.0", n + "0.1", cin, hid, 1, relu="relu6") if expand != 1 else None
+        i = 1 if expand != 1 else 0
+        self.dw = DepthwiseBN(store, n + "%d.0" % i, n + "%d.1" % i, hid, stride, dil)
+        self.project = ConvBN(store, n + "%d" % (i + 1), n + "%d" % (i + 2), hid, cout, 1, relu=False)
+        self.use_res = stride == 1 and cin == cout
+
+    def forward(self, x, training):
+        h = self.expand.forward(x, training) if self.expand else x
+        return self.project.forward(self.dw.forward(h, training), training, res=x if self.use_res else None)
+
+    def backward(self, dy):
+        """the projection is linear, so the identity branch's gradient is dy itself: the conv branch accumulates into it
+        (dy is this block's private copy of the gradient: nothing else reads it afterwards)"""
+        d = self.dw.backward(self.project.backward(dy))
+        if self.expand is None:
+            if self.use_res:
+                K.add_(d, dy)
+            return d
+        if self.use_res:
+            return self.expand.backward(d, dx=dy, accumulate=True)
+        return self.expand.backward(d)
+
+
+MBV2_SETTING = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
+MBV2_STEM_RP = 16     # 3x3 stem patches: k = r*16 + s*3 + c (9 values + 7 zeros per filter row)
+
+
+def stem_pack_rows(w, rp):
+    """torch [Cout,3,R,S] -> [1,Cout,R*rp] in the row-pitched patch order of K.im2col_stem(row_pitch=rp)."""
+    co, _, r, s_ = w.shape
+    v = w.permute(0, 2, 3, 1).reshape(co, r, 3 * s_)
+    return torch.cat([v, torch.zeros(co, r, rp - 3 * s_, dtype=w.dtype, device=w.device)], 2).reshape(1, co, r * rp)
+
+
+def stem_unpack_rows(d, r, s_, rp):
+    co = d.shape[1]
+    return d[0].reshape(co, r, rp)[:, :, :3 * s_].reshape(co, r, s_, 3).permute(0, 3, 1, 2).contiguous()
+
+
+class MobileNetV2Encoder:
+    """torchvision mobilenet_v2 `features` (the reference's only reachable backbone, models/__init__.py:16) as smp wraps
+    it: stages features[:2], [2:4], [4:7], [7:14], [14:]; out_channels (3, 16, 24, 32, 96, 1280); output stride 16 =
+    every conv of the last stage at stride 1 / dilation 2 (smp make_dilated)."""
+
+    def __init__(self, store, in_channels=3, dilated=True):
+        assert in_channels == 3
+        f = "encoder.features."
+        self.stem_w = store.add(f + "0.0.weight", (1, 32, 3 * MBV2_STEM_RP), "conv_nt",
+                                lambda s: stem_pack_rows(kaiming_fan_out((32, 3, 3, 3)), MBV2_STEM_RP))
+        self.stem_bn = BatchNorm(store, f + "0.1", 32)
+        self.blocks = []          # (feature index, block)
+        cin, idx = 32, 1
+        for t, c, n, s_ in MBV2_SETTING:
+            for i in range(n):
+                stride = s_ if i == 0 else 1
+                dil = 1
+                if dilated and idx >= 14:
+                    stride, dil = 1, 2
+                self.blocks.append((idx, InvertedResidual(store, f + str(idx), cin, c, stride, t, dil)))
+                cin = c
+                idx += 1
+        self.last = ConvBN(store, f + "18.0", f + "18.1", cin, 1280, 1, relu="relu6")
+        self.out_channels = [3, 16, 24, 32, 96, 1280]
+        self.stage_ends = (1, 3, 6, 13)       # feature index after which a stage output is taken (then the last conv)
+
+    def forward(self, img, training):
+        col = K.im2col_stem(img, 3, 3, 2, 1, 3 * MBV2_STEM_RP, row_pitch=MBV2_STEM_RP)
+        fused = training and FUSE_BN_STATS
+        pre = C.fprop(col, self.stem_w.bf16, 1, 1, stats=self.stem_bn.stats_buffers() if fused else None)
+        x = torch.empty_like(pre)
+        self.stem_bn.forward(pre, x, training, relu=True, relu6=True, have_stats=fused)
+        feats = []
+        for idx, blk in self.blocks:
+            x = blk.forward(x, training)
+            if idx in self.stage_ends:
+                feats.append(x)
+        feats.append(self.last.forward(x, training))
+        self.ctx = (col, pre) if training else None
+        return feats            # strides 2, 4, 8, 16, 16
+
+    def backward(self, d_last, d_stride4=None, d_skips=None):
+        col, pre = self.ctx
+        self.ctx = None
+        skips = list(d_skips) if d_skips is not None else [None, d_stride4, None, None]
+        d = self.last.backward(d_last)
+        for idx, blk in reversed(self.blocks):
+            if idx in self.stage_ends:
+                sk = skips[self.stage_ends.index(idx)]
+                if sk is not None:
+                    K.add_(d, sk)
+            d = blk.backward(d)
+        dpre = torch.empty_like(pre)
+        self.stem_bn.backward(d, pre, None, dpre, relu=True, relu6=True)
+        C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad)
+
+
 class SeparableConvBN:
     """smp SeparableConv2d(depthwise 3x3 + pointwise 1x1, bias=False) -> BN -> ReLU"""
 
@@ -543,8 +677,12 @@ class SegNet:
         self.store = ParamStore(self.device)
         self.arch = arch
         self.classes = classes
+        def make_encoder(dilated):
+            if encoder_name == "mobilenet_v2":
+                return MobileNetV2Encoder(self.store, dilated=dilated)
+            return ResNetEncoder(self.store, encoder_name, dilated=dilated)
         if arch == "unet":
-            self.encoder = ResNetEncoder(self.store, encoder_name, dilated=False)
+            self.encoder = make_encoder(False)
             self.decoder = UnetDecoder(self.store, self.encoder.out_channels)
             hc = self.decoder.out_channels
             self.head_w = self.store.add(
@@ -552,7 +690,7 @@ class SegNet:
                 lambda s: kaiming_uniform_default((classes, hc, 3, 3)).permute(0, 2, 3, 1).reshape(classes, 9, hc))
             bound = 1.0 / math.sqrt(hc * 9)
         else:
-            self.encoder = ResNetEncoder(self.store, encoder_name)
+            self.encoder = make_encoder(True)
             self.decoder = DeepLabV3PlusDecoder(self.store, self.encoder.out_channels)
             self.head_w = self.store.add("segmentation_head.0.weight", (classes, 256), "f32",
                                          lambda s: kaiming_uniform_default((classes, 256, 1, 1)).reshape(classes, 256))
@@ -606,6 +744,8 @@ class SegNet:
             d = p.data.detach().clone()
             if p.name == "encoder.conv1.weight":
                 d = stem_unpack(d)
+            elif p.name == "encoder.features.0.0.weight":
+                d = stem_unpack_rows(d, 3, 3, MBV2_STEM_RP)
             elif p.kind in ("conv", "conv_nt"):
                 k = int(round(math.sqrt(p.shape[0])))
                 d = from_taps(d, k, k)
@@ -632,6 +772,8 @@ class SegNet:
             w = sd[name].detach().to(self.device, torch.float32)
             if name == "encoder.conv1.weight":
                 w = stem_pack(w)
+            elif name == "encoder.features.0.0.weight":
+                w = stem_pack_rows(w, MBV2_STEM_RP)
             elif p.kind in ("conv", "conv_nt"):
                 w = to_taps(w)
             elif name == "segmentation_head.0.weight":
@@ -721,8 +863,8 @@ def DeepLabV3Plus(encoder_name="resnet50", encoder_depth=5, encoder_weights=None
                   upsampling=4, aux_params=None, device="cuda", seed=0):
     """smp.DeepLabV3Plus constructor shape (models/__init__.py:17-23).  `encoder_weights` must be None
     (no network for ImageNet checkpoints: load_state_dict() accepts smp-named weights instead)."""
-    if encoder_name not in RESNETS:
-        raise NotImplementedError("encoder %r: resnet18/34/50 are implemented" % encoder_name)
+    if encoder_name not in RESNETS and encoder_name != "mobilenet_v2":
+        raise NotImplementedError("encoder %r: mobilenet_v2 and resnet18/34/50 are implemented" % encoder_name)
     if encoder_weights not in (None, "none"):
         raise NotImplementedError("pretrained encoder weights cannot be downloaded here; use load_state_dict()")
     if (encoder_depth, encoder_output_stride, decoder_channels, tuple(decoder_atrous_rates), in_channels, upsampling,

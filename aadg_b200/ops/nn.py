@@ -37,19 +37,19 @@ def bn_finalize(sum_, sumsq, gamma, beta, count, eps, momentum, mean, invstd, sc
           p(mean), p(invstd), p(scale), p(shift), p(run_mean), p(run_var), int(reset_sums))
 
 
-def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None, relu_bits=None):
-    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0)
+def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None, relu_bits=None, relu6=False):
+    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (32 if (relu and relu6) else 0)
     _call("aadg_bn_apply", p(x), _ld(x), p(scale), p(shift), p(res), _ld(res) if res is not None else 0, p(y), _ld(y),
           _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(relu_bits))
 
 
 def bn_backward(dy, x, y, mean, invstd, gamma, dgamma, dbeta, dx, relu=True, dropout_seed=None, dres=None,
-                dres_accumulate=False, shift=None, dy2=None, grads_zeroed=False):
+                dres_accumulate=False, shift=None, dy2=None, grads_zeroed=False, relu6=False):
     """y=None with relu=True recomputes the ReLU mask from x and the forward `shift` (no residual case).
     dy2: a second gradient tensor added to dy on load."""
     bits = y is not None and y.dtype == torch.uint8        # relu bit mask written by bn_apply(relu_bits=...)
     flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (4 if (relu and y is None) else 0) | \
-        (8 if bits else 0) | (16 if grads_zeroed else 0)
+        (8 if bits else 0) | (16 if grads_zeroed else 0) | (32 if (relu and relu6) else 0)
     tail = (p(x), _ld(x), p(y), _ld(y) if (y is not None and not bits) else 0, p(mean), p(invstd),
             p(gamma), p(shift), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
             p(dres), _ld(dres) if dres is not None else 0, int(dres_accumulate))
@@ -108,14 +108,25 @@ def f32_to_bf16(x, scale=1.0):
     return y
 
 
-def dwconv3x3(x, w, dil, y, backward_data=False):
-    n, h, wd, c = x.shape
-    _call("aadg_dwconv3x3", p(x), n, h, wd, c, _ld(x), p(w), dil, int(backward_data), p(y), _ld(y))
+def dwconv3x3(x, w, dil, y, backward_data=False, stride=1):
+    """forward: x [n,h,w,c] -> y [n,ho,wo,c]; backward_data: x is dy [n,ho,wo,c], y is dx [n,h,w,c]."""
+    if stride == 1:
+        n, h, wd, c = x.shape
+        _call("aadg_dwconv3x3", p(x), n, h, wd, c, _ld(x), p(w), dil, int(backward_data), p(y), _ld(y))
+        return
+    big, small = (y, x) if backward_data else (x, y)
+    n, h, wd, c = big.shape
+    _call("aadg_dwconv3x3_strided", p(x), n, h, wd, c, _ld(x), p(w), dil, stride, int(backward_data), p(y), small.shape[1],
+          small.shape[2], _ld(y))
 
 
-def dwconv3x3_wgrad(x, dy, dil, dw):
+def dwconv3x3_wgrad(x, dy, dil, dw, stride=1):
     n, h, wd, c = x.shape
-    _call("aadg_dwconv3x3_wgrad", p(x), n, h, wd, c, _ld(x), p(dy), _ld(dy), dil, p(dw))
+    if stride == 1:
+        _call("aadg_dwconv3x3_wgrad", p(x), n, h, wd, c, _ld(x), p(dy), _ld(dy), dil, p(dw))
+    else:
+        _call("aadg_dwconv3x3_strided_wgrad", p(x), n, h, wd, c, _ld(x), p(dy), dy.shape[1], dy.shape[2], _ld(dy), dil,
+              stride, p(dw))
 
 
 def im2col_stem(img, r, s, stride, pad, kp, row_pitch=None):

@@ -201,7 +201,8 @@ int aadg_bn_stats(const void* x, long long pixels, int c, int ld, float* sum, fl
 int aadg_bn_finalize(float* sum, float* sumsq, const float* gamma, const float* beta, int c, float count,
                      float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
                      float* run_mean, float* run_var, int reset_sums, void* stream);
-/* y = act(x*scale + shift (+ res)) ; flags bit0 = ReLU, bit1 = Dropout(0.5) keyed by (seed, element);
+/* y = act(x*scale + shift (+ res)) ; flags bit0 = ReLU, bit5 (32) = ReLU6 (with bit0), bit1 = Dropout(0.5) keyed by
+ * (seed, element);
  * relu_bits (may be NULL): uint8 [pixels][c/8], bit i of byte g = (pre-activation of channel 8g+i > 0) */
 int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr, void* y,
                   int ldy, long long pixels, int c, int flags, unsigned long long seed, void* relu_bits,
@@ -244,6 +245,12 @@ int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const flo
                    int ldy, void* stream);
 int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil, float* dw,
                          void* stream);
+/* strided depthwise 3x3 (padding = dilation; ho = (h-1)/stride + 1): MobileNetV2's down-sampling blocks.  direction 1:
+ * `x` is dy [n,ho,wo,ldx] and `y` is dx [n,h,w,ldy].  stride 1 forwards to the kernels above. */
+int aadg_dwconv3x3_strided(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int stride,
+                           int direction, void* y, int ho, int wo, int ldy, void* stream);
+int aadg_dwconv3x3_strided_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int ho, int wo, int lddy,
+                                 int dil, int stride, float* dw, void* stream);
 /* img fp32 [n,3,h,w] -> col bf16 [n*ho*wo][kp], k = (r*S+s)*3 + c, zero padded to kp */
 int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int kp, void* col,
                      void* stream);

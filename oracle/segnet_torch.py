@@ -7,7 +7,8 @@ classes, aux_params=dict(pooling='avg'))) with the patched classification head o
 not vendored under /root/reference, so the module structure follows its published source
 (smp/deeplabv3/{model,decoder}.py, smp/encoders/{resnet,_utils}.py, smp/base/{model,heads}.py) and keeps
 its state_dict key names; every layer is a stock torch layer, which pins the numerics of each op.
-Encoders: torchvision resnet18/34/50 without the classifier, stage 5 dilated (output stride 16).
+Encoders: torchvision mobilenet_v2 (the reference's only reachable backbone, models/__init__.py:16) and
+resnet18/34/50 without the classifier, stage 5 dilated (output stride 16).
 """
 import torch
 import torch.nn as nn
@@ -101,10 +102,33 @@ class ResNetEncoder(nn.Module):
         return [f0, f1, f2, f3, f4, f5]
 
 
+class MobileNetV2Encoder(nn.Module):
+    """smp MobileNetV2Encoder: torchvision mobilenet_v2 `features` (keys features.0 .. features.18), stages
+    [:2], [2:4], [4:7], [7:14], [14:]; make_dilated(stage_list=[5], dilation_list=[2]) on the last stage."""
+
+    def __init__(self, dilated=True):
+        super().__init__()
+        self.features = torchvision.models.mobilenet_v2(weights=None).features
+        for m in (self.features[14:].modules() if dilated else []):
+            if isinstance(m, nn.Conv2d):
+                m.stride = (1, 1)
+                m.dilation = (2, 2)
+                kh, kw = m.kernel_size
+                m.padding = ((kh // 2) * 2, (kw // 2) * 2)
+        self.out_channels = (3, 16, 24, 32, 96, 1280)
+
+    def forward(self, x):
+        feats = [x]
+        for lo, hi in ((0, 2), (2, 4), (4, 7), (7, 14), (14, 19)):
+            x = self.features[lo:hi](x)
+            feats.append(x)
+        return feats
+
+
 class DeepLabV3PlusTorch(nn.Module):
     def __init__(self, encoder_name="resnet50", classes=2):
         super().__init__()
-        self.encoder = ResNetEncoder(encoder_name)
+        self.encoder = MobileNetV2Encoder() if encoder_name == "mobilenet_v2" else ResNetEncoder(encoder_name)
         self.decoder = Decoder(self.encoder.out_channels)
         self.segmentation_head = nn.Sequential(nn.Conv2d(256, classes, 1), nn.UpsamplingBilinear2d(scale_factor=4),
                                                nn.Identity())

@@ -274,6 +274,9 @@ def _my_grad_as_torch(name, p):
     if name == "encoder.conv1.weight":
         from aadg_b200.nn.network import stem_unpack
         return stem_unpack(g)
+    if name == "encoder.features.0.0.weight":
+        from aadg_b200.nn.network import stem_unpack_rows, MBV2_STEM_RP
+        return stem_unpack_rows(g, 3, 3, MBV2_STEM_RP)
     if p.kind in ("conv", "conv_nt"):
         k = int(round(p.shape[0] ** 0.5))
         return g.reshape(k, k, p.shape[1], p.shape[2]).permute(2, 3, 0, 1)
@@ -514,3 +517,159 @@ def test_unet_resnet34_vs_oracle():
         out = net.loss_step(x, target)
         net.store.adam_step(1e-3)
     assert out["loss"].item() < first
+
+
+@pytest.mark.parametrize("stride,dil", [(2, 1), (2, 2)])
+def test_depthwise_strided(K, stride, dil):
+    """MobileNetV2's down-sampling depthwise convolutions (odd sizes included)"""
+    torch.manual_seed(11)
+    n, h, w, c = 2, 33, 30, 144
+    x = torch.randn(n, h, w, c, device="cuda").to(BF)
+    wt = torch.randn(c, 1, 3, 3, device="cuda") * 0.3
+    w9 = wt.reshape(c, 9).t().contiguous()
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    y = torch.empty(n, ho, wo, c, device="cuda", dtype=BF)
+    K.dwconv3x3(x, w9, dil, y, stride=stride)
+    xr, wr = nchw(x).requires_grad_(True), wt.clone().requires_grad_(True)
+    o = F.conv2d(xr, wr, stride=stride, padding=dil, dilation=dil, groups=c)
+    assert o.shape[2:] == (ho, wo)
+    rel_close(nchw(y), o, 1e-2, "dw strided fwd")
+    dy = torch.randn(n, ho, wo, c, device="cuda").to(BF)
+    o.backward(nchw(dy))
+    dx = torch.empty_like(x)
+    K.dwconv3x3(dy, w9, dil, dx, backward_data=True, stride=stride)
+    rel_close(nchw(dx), xr.grad, 1e-2, "dw strided dgrad")
+    dw = torch.zeros(9, c, device="cuda")
+    K.dwconv3x3_wgrad(x, dy, dil, dw, stride=stride)
+    rel_close(dw, wr.grad.reshape(c, 9).t(), 2e-3, "dw strided wgrad")
+
+
+def test_batchnorm_relu6(K):
+    torch.manual_seed(12)
+    n, h, w, c = 3, 9, 11, 96
+    x = (torch.randn(n, h, w, c, device="cuda") * 3).to(BF)
+    gamma, beta = torch.rand(c, device="cuda") * 3 + 0.5, torch.randn(c, device="cuda") * 2
+    buf = torch.zeros(6, c, device="cuda")
+    K.bn_stats(x, buf[0], buf[1])
+    K.bn_finalize(buf[0], buf[1], gamma, beta, n * h * w, 1e-5, 0.1, buf[2], buf[3], buf[4], buf[5], None, None)
+    y = torch.empty_like(x)
+    K.bn_apply(x, buf[4], buf[5], y, relu=True, relu6=True)
+    bn = torch.nn.BatchNorm2d(c).cuda().train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    xr = nchw(x).requires_grad_(True)
+    pre = bn(xr)
+    o = F.relu6(pre)
+    rel_close(nchw(y), o, 1e-2, "relu6 fwd")
+    assert y.max().item() == 6.0 and (y == 0).any()
+    dy = torch.randn(n, h, w, c, device="cuda").to(BF)
+    # the gradient mask is decided on the kernel's own pre-activation (bf16 x, fp32 affine): same formula on both sides
+    t = nchw(x).float() * buf[4].view(1, c, 1, 1) + buf[5].view(1, c, 1, 1)
+    mask = ((t > 0) & (t < 6)).float()
+    (pre * mask * nchw(dy)).sum().backward()
+    dx = torch.empty_like(x)
+    dg, db = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    K.bn_backward(dy, x, None, buf[2].clone(), buf[3].clone(), gamma, dg, db, dx, relu=True, shift=buf[5].clone(), relu6=True)
+    rel_close(nchw(dx), xr.grad, 2e-2, "relu6 dx")
+    dx2 = torch.empty_like(x)
+    K.bn_backward(dy, x, y, buf[2].clone(), buf[3].clone(), gamma, dg, db, dx2, relu=True, relu6=True)
+    # mask read from the bf16 output instead: identical except where the pre-activation rounds onto 0 or 6
+    differs = ((dx2.float() - dx.float()).abs() > 2e-2 * dx.float().abs().max()).float().mean().item()
+    assert differs < 0.01, differs
+
+
+def test_network_end_to_end_mobilenet_v2():
+    """the reference's own backbone (models/__init__.py:16): DeepLabV3+/MobileNetV2 step vs the torch oracle with
+    identical weights: loss, pooled feature, logits, gradients, state_dict key set."""
+    from aadg_b200.nn.network import dice_from_counts
+    ref, net, x, target = _pair("mobilenet_v2", 2, 128, 8)
+    assert set(ref.state_dict()) == set(net.state_dict())
+    masks, pooled = ref(x)
+    loss = F.binary_cross_entropy(torch.sigmoid(masks), target)
+    loss.backward()
+    net.store.zero_grad()
+    out = net.loss_step(x, target, want_logits=True)
+    assert out["pooled"].shape == (8, 1280)
+    # 52 randomly initialised layers with linear bottlenecks amplify bf16 rounding far more than the ResNets do (the
+    # blocks themselves are checked to 2 % in test_mobilenet_blocks_teacher_forced): statistical bounds here
+    e_pool, e_logit = l2err(out["pooled"], pooled), l2err(out["logits"], masks)
+    print("MBV2 e2e:", e_pool, e_logit, out["loss"].item(), loss.item(), _grad_report(net, ref, "decoder.", 0.7)[:12])
+    # (measured at random init, batch 8 @128^2: pooled 11 %, logits 65 % relative L2 -- the logits of an untrained net
+    # are small differences of large noisy terms; the loss still agrees to 1 %)
+    assert e_pool < 0.2, (e_pool, e_logit)
+    assert abs(out["loss"].item() - loss.item()) <= 2e-2 * abs(loss.item()), (out["loss"].item(), loss.item())
+    assert torch.isfinite(dice_from_counts(out["counts"])).all()
+    # a few optimiser steps learn
+    first = out["loss"].item()
+    for _ in range(8):
+        net.store.zero_grad()
+        o2 = net.loss_step(x, target)
+        net.store.adam_step(1e-3)
+    assert o2["loss"].item() < first
+
+
+def test_mobilenet_blocks_teacher_forced():
+    """every MobileNetV2 feature block, forward and backward, fed the torch oracle's own activations (bf16-rounded):
+    isolates each block's numerics (strides, dilation of the last stage, linear bottleneck + identity) from the
+    noise amplification of a randomly initialised 52-layer net."""
+    ref, net, x, target = _pair("mobilenet_v2", 2, 128, 4)
+    feats = ref.encoder.features
+    with torch.no_grad():
+        acts, h = [], x
+        for m in feats:
+            h = m(h)
+            acts.append(h)
+    report = []
+    for idx, blk in net.encoder.blocks:
+        xin = nhwc(acts[idx - 1]).to(BF)
+        ref.zero_grad()
+        net.store.zero_grad()
+        xr = nchw(xin).float().requires_grad_(True)
+        want = feats[idx](xr)
+        y = blk.forward(xin, True)
+        ef = l2err(nchw(y), want)
+        dy = torch.randn_like(want).to(BF)
+        want.backward(dy.float())
+        d = blk.backward(nhwc(dy).to(BF).contiguous())
+        eb = l2err(nchw(d), xr.grad)
+        bad = _grad_report(net, ref, "encoder.features.%d." % idx, 0.95)
+        report.append((idx, round(ef, 4), round(eb, 4), bad[:3]))
+    print("MBV2 blocks:", report)
+    worst_f = max(r[1] for r in report)
+    worst_b = max(r[2] for r in report)
+    assert worst_f < 2e-2 and worst_b < 8e-2 and not any(r[3] for r in report), report
+    # last 1x1 conv (features.18)
+    xin = nhwc(acts[17]).to(BF)
+    y = net.encoder.last.forward(xin, True)
+    assert l2err(nchw(y), feats[18](nchw(xin).float())) < 2e-2
+
+
+def test_mobilenet_decoder_and_stem_teacher_forced():
+    """DeepLabV3+ decoder on MobileNetV2's feature maps (1280 / 24 channels) and the 3x3 stride-2 stem, fed the
+    oracle's activations"""
+    ref, net, x, target = _pair("mobilenet_v2", 2, 128, 4)
+    with torch.no_grad():
+        feats = ref.encoder(x)
+    fb = [None] + [nhwc(f).to(BF) for f in feats[1:]]
+    ref.zero_grad()
+    net.store.zero_grad()
+    fr = [None] + [nchw(f).requires_grad_(True) for f in fb[1:]]
+    want = ref.decoder(*fr)
+    got = net.decoder.forward(fb[1:], True, None)
+    e_fwd = l2err(nchw(got), want)
+    dy = torch.randn_like(want).to(BF)
+    want.backward(dy.float())
+    d_last, d_high = net.decoder.backward(nhwc(dy).to(BF))
+    e_last, e_high = l2err(nchw(d_last), fr[5].grad), l2err(nchw(d_high), fr[2].grad)
+    bad = _grad_report(net, ref, "decoder.", 0.9)
+    # stem: features[0]
+    f0 = ref.encoder.features[0](x)
+    col = K_mod().im2col_stem(x, 3, 3, 2, 1, 48, row_pitch=16)
+    from aadg_b200.ops import conv as C
+    pre = C.fprop(col, net.encoder.stem_w.bf16, 1, 1)
+    y = torch.empty_like(pre)
+    net.encoder.stem_bn.forward(pre, y, True, relu=True, relu6=True)
+    e_stem = l2err(nchw(y), f0)
+    print("MBV2 decoder:", e_fwd, e_last, e_high, bad[:6], "stem", e_stem)
+    assert e_fwd < 3e-2 and e_last < 0.3 and e_high < 0.3 and not bad and e_stem < 1e-2
