@@ -23,7 +23,7 @@ def _ctype(decl):
         return ctypes.c_char_p if d.replace(" ", "") == "char*" else c_void_p
     d = " ".join(d.split())
     return {"int": c_int, "float": c_float, "size_t": c_size_t, "long long": ctypes.c_longlong,
-            "unsigned long long": ctypes.c_ulonglong, "void": None}[d]
+            "unsigned long long": ctypes.c_ulonglong, "double": ctypes.c_double, "void": None}[d]
 
 
 def _parse_header(path=HEADER):

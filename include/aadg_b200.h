@@ -285,6 +285,18 @@ int aadg_seg_head3x3_fwd(const void* a, int n, int h, int w, int c, int lda, con
 int aadg_seg_head3x3_bwd(const float* dz, const void* a, int n, int h, int w, int c, int lda, const float* wgt,
                          int classes, void* da, int ldda, float* dw, float* db, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Validation metric — replaces medpy.metric.binary.hd95 as validate() calls it per image and class on
+ * the CPU (search_dg.py:246-260, train_dg.py): surfaces = mask xor 4-neighbour erosion, exact Euclidean
+ * distances to the other surface, numpy.percentile(.., 95) of the union of both directed sets.
+ * ---------------------------------------------------------------------------------------------- */
+size_t aadg_hd95_workspace_bytes(int n_pairs, int h, int w);
+/* result, reference: uint8 [n_pairs][h][w] (non-zero = foreground); out float64 [n_pairs] in pixels;
+ * status int32 [n_pairs]: 0 ok, 1 = `result` empty, 2 = `reference` empty (medpy raises; out = NaN).
+ * `percentile` in [0,100] (95 for hd95, 100 = the Hausdorff distance). */
+int aadg_hd95(const unsigned char* result, const unsigned char* reference, int n_pairs, int h, int w, double percentile,
+              double* out, int* status, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
