@@ -125,3 +125,32 @@ def test_world_size_2_exchange_gloo():
     assert (d0[:6] == 0).all() and (d0[6:] == 1).all()
     assert np.allclose(g0, 1.5) and np.allclose(g1, 1.5)
     assert s0 == list(range(12)) and s1 == list(range(12, 24))
+
+
+def test_resident_pools_replay_reference_sampling():
+    """ResidentPools draws exactly what the reference dataset's __getitem__ draws (data/optic.py:81-84) and orders a
+    batch item-major / domain-minor like train_dg_collate_fn."""
+    import numpy as np
+    from aadg_b200.data.pool import ResidentPools
+    rng = np.random.RandomState(0)
+    sizes = {"DGS": 5, "RIM": 9, "REF": 3}
+    imgs = {k: rng.randint(0, 256, (n, 8, 8, 3)).astype(np.uint8) for k, n in sizes.items()}
+    msks = {k: rng.randint(0, 3, (n, 8, 8)).astype(np.uint8) * 127 for k, n in sizes.items()}
+    pools = ResidentPools(imgs, msks, device="cpu")
+    assert len(pools) == 9 and pools.steps_per_epoch(4) == 2 and pools.n_domains == 3
+    np.random.seed(123)
+    want = [[np.random.choice(n, 1)[0] for n in sizes.values()] for _ in range(4)]      # the reference's draws
+    np.random.seed(123)
+    idx = pools.sample_indices(4)
+    assert idx.tolist() == want
+    x, m, dom = pools.gather(idx)
+    assert x.shape == (12, 8, 8, 3) and m.shape == (12, 8, 8) and dom == [0, 1, 2] * 4
+    keys = list(sizes)
+    for b in range(4):
+        for d in range(3):
+            assert np.array_equal(x[b * 3 + d].numpy(), imgs[keys[d]][want[b][d]])
+            assert np.array_equal(m[b * 3 + d].numpy(), msks[keys[d]][want[b][d]])
+    assert sum(1 for _ in pools.epoch(4, np.random.RandomState(1))) == 2
+    import pytest
+    with pytest.raises(IndexError):
+        pools.gather(np.array([[5, 0, 0]]))
