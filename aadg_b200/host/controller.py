@@ -76,3 +76,100 @@ class Controller(nn.Module):
             return action
         self._walk(batch_size, choose)
         return torch.stack(logps, -1).sum(-1)
+
+
+class _WalkEvaluate(torch.autograd.Function):
+    """sum_t log pi(a_t) for given policies: forward = one aadg_controller_walk launch (mode 1), backward = one
+    aadg_controller_backward launch producing the gradients of all nine parameter tensors."""
+
+    @staticmethod
+    def forward(ctx, ctl, policies, *params):
+        step_logp, _, _, saved, _ = ctl._walk(policies, mode=1, want_saved=True)
+        ctx.ctl, ctx.policies, ctx.saved = ctl, policies, saved
+        ctx.save_for_backward(*params)
+        return step_logp.sum(-1)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ctl = ctx.ctl
+        grads = [torch.zeros_like(p) for p in ctx.saved_tensors]
+        ctl._backward(ctx.policies, ctx.saved, grad_out.contiguous().float(), grads)
+        return (None, None) + tuple(grads)
+
+
+class FusedController(Controller):
+    """Same module, parameters, state_dict and call shapes as `Controller` (models/controller.py), but `sample` and
+    `evaluate` are one kernel launch each (csrc/controller.cu) and `evaluate` back-propagates through one more, so the
+    reference's PPO loop (losses.py:127-157: five evaluate / backward / Adam rounds per epoch) needs 10 launches of
+    this library instead of ~1 000 small ATen ones.  Sampling is counter based (Philox keyed by `seed` and the call
+    number) instead of torch's multinomial stream.  CUDA only."""
+
+    def __init__(self, cfg, n_subpolicies=5, embedding_dim=32, hidden_dim=100, seed=0):
+        super().__init__(cfg, n_subpolicies, embedding_dim, hidden_dim)
+        self.seed, self.calls = int(seed), 0
+
+    def _params(self):
+        return [self.embedding.weight, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih, self.lstm.bias_hh,
+                self.outop.weight, self.outop.bias, self.outmag.weight, self.outmag.bias]
+
+    @staticmethod
+    def _ptr_array(tensors):
+        import ctypes
+        arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return arr, ctypes.addressof(arr)
+
+    def _check(self):
+        from .. import _lib
+        ps = self._params()
+        if not all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in ps):
+            raise RuntimeError("FusedController needs contiguous float32 CUDA parameters (no CPU path)")
+        return _lib, ps
+
+    def _walk(self, policies, mode, want_saved=False, want_probs=False, batch=None):
+        _lib, ps = self._check()
+        dev = ps[0].device
+        steps = self.Q * self.L * 2
+        m = policies.shape[0] if policies is not None else batch
+        if policies is None:
+            policies = torch.empty((m, steps), dtype=torch.int64, device=dev)
+        elif not (policies.is_cuda and policies.dtype == torch.int64 and policies.is_contiguous()
+                  and policies.shape == (m, steps)):
+            raise ValueError("policies must be a contiguous CUDA int64 [batch, %d] tensor" % steps)
+        logp = torch.empty((m, steps), dtype=torch.float32, device=dev)
+        ent = torch.empty((m, steps), dtype=torch.float32, device=dev)
+        vm = max(self.NUM_OPS, self.NUM_MAGS)
+        probs = torch.empty((m, steps, vm), dtype=torch.float32, device=dev) if want_probs else None
+        saved = torch.empty((m, steps, 6 * self.hidden_dim), dtype=torch.float32, device=dev) if want_saved else None
+        arr, addr = self._ptr_array([p.detach() for p in ps])
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().aadg_controller_walk(
+                addr, self.NUM_OPS, self.NUM_MAGS, self.Q, self.L, self.embedding_dim, self.hidden_dim, float(self.C),
+                float(self.T), m, mode, self.seed, self.calls, policies.data_ptr(), logp.data_ptr(), ent.data_ptr(),
+                None if probs is None else probs.data_ptr(), None if saved is None else saved.data_ptr(),
+                _lib.stream_ptr()))
+        del arr
+        return logp, ent, probs, saved, policies
+
+    def _backward(self, policies, saved, grad, grads):
+        _lib, ps = self._check()
+        parr, paddr = self._ptr_array([p.detach() for p in ps])
+        garr, gaddr = self._ptr_array(grads)
+        with torch.cuda.device(ps[0].device):
+            _lib.check(_lib.lib().aadg_controller_backward(
+                paddr, self.NUM_OPS, self.NUM_MAGS, self.Q, self.L, self.embedding_dim, self.hidden_dim, float(self.C),
+                float(self.T), policies.shape[0], policies.data_ptr(), saved.data_ptr(), grad.data_ptr(), gaddr,
+                _lib.stream_ptr()))
+        del parr, garr
+
+    def sample(self, batch_size=1):
+        """(policies int64 [M, Q*L*2], op_probs [NUM_OPS], mag_probs [NUM_MAGS], log_probs [M], entropies [M]):
+        the reference's return tuple (controller.py:118-119); log_probs carries no graph (the PPO loss detaches it)."""
+        logp, ent, probs, _, policies = self._walk(None, mode=0, want_probs=True, batch=batch_size)
+        self.calls += 1
+        op_probs = probs[:, 0::2, :self.NUM_OPS].reshape(-1, self.NUM_OPS).mean(0)
+        mag_probs = probs[:, 1::2, :self.NUM_MAGS].reshape(-1, self.NUM_MAGS).mean(0)
+        return policies, op_probs, mag_probs, logp.sum(-1), ent.sum(-1)
+
+    def evaluate(self, policies, batch_size):
+        policies = policies.long().contiguous()
+        return _WalkEvaluate.apply(self, policies, *self._params())

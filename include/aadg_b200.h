@@ -297,6 +297,25 @@ size_t aadg_hd95_workspace_bytes(int n_pairs, int h, int w);
 int aadg_hd95(const unsigned char* result, const unsigned char* reference, int n_pairs, int h, int w, double percentile,
               double* out, int* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Policy controller — replaces the per-decision LSTMCell / Linear / softmax / multinomial launches of
+ * models/controller.py:73-145 (sample, evaluate) and the autograd backward of the PPO update
+ * (losses.py:127-157) with one launch each.  `params` / `grads`: HOST arrays of nine device pointers in module
+ * order: embedding.weight [n_ops+n_mags, e], lstm.weight_ih [4h, e], lstm.weight_hh [4h, h], lstm.bias_ih [4h],
+ * lstm.bias_hh [4h], outop.weight [n_ops, h], outop.bias, outmag.weight [n_mags, h], outmag.bias.
+ * ---------------------------------------------------------------------------------------------- */
+/* mode 0 = sample (policies int64 [batch, q*l*2] written; decision t of row m draws from Philox4x32-10 keyed by
+ * `seed` with counter (m, t, call)), mode 1 = evaluate (policies read).  step_log_prob, step_entropy float32
+ * [batch, q*l*2]; step_probs float32 [batch, q*l*2, max(n_ops, n_mags)] or NULL; saved float32 [batch, q*l*2, 6h]
+ * (activations for the backward) or NULL. */
+int aadg_controller_walk(const float* const* params, int n_ops, int n_mags, int q, int l, int e, int h, float c, float t,
+                         int batch, int mode, unsigned long long seed, unsigned long long call, long long* policies,
+                         float* step_log_prob, float* step_entropy, float* step_probs, float* saved, void* stream);
+/* grads[i] += d( sum_m grad_log_prob[m] * sum_t log pi(a_t | m) ) / d params[i] (fp32, accumulated) */
+int aadg_controller_backward(const float* const* params, int n_ops, int n_mags, int q, int l, int e, int h, float c,
+                             float t, int batch, const long long* policies, const float* saved,
+                             const float* grad_log_prob, float* const* grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
