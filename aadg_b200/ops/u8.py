@@ -67,6 +67,15 @@ def policy_normalize(src_images, src_masks, rows, dataset="optic", want_images=T
     return out_images, out_labels
 
 
+def normalize_to_tensor(src_images, src_masks, dataset="optic"):
+    """The test-time transform (Normalize_dg + ToTensor, data/transform.py:138-236 without any policy): images
+    float32 [S,3,H,W] in [-1,1] and labels float32 [S,C,H,W], one row per source image with zero operations."""
+    from ..data.decisions import ROW_DTYPE
+    rows = np.zeros(src_images.shape[0], ROW_DTYPE)
+    rows["src"] = np.arange(src_images.shape[0])
+    return policy_normalize(src_images, src_masks, rows, dataset=dataset)
+
+
 def scale_crop_normalize(images, masks, rows, crop, dataset="optic", image_by_row=True, want_labels=True):
     """DGRandomScaleCrop + Normalize_dg + ToTensor for every row (data/transform.py:97-236): images uint8
     [n,H,W,3] (post-policy, one per row) or the sources (image_by_row=False); masks = ORIGINAL masks [S,H,W].

@@ -33,6 +33,8 @@ for kind, h, cin, cout, k, stride, dil in CASES:
     for _ in range(1 + reps):
         if kind == "fprop":
             C.fprop(x, w, k, k, stride, pad, dil)
+            ssum, ssq = torch.zeros(cout, device="cuda"), torch.zeros(cout, device="cuda")
+            C.fprop(x, w, k, k, stride, pad, dil, stats=(ssum, ssq))      # fused batch-norm statistics variant
         elif kind == "dgrad":
             C.dgrad(dy, wt, k, k, stride, pad, dil, (h, h))
         else:
