@@ -235,10 +235,12 @@ struct IgemmPArgs {
 constexpr int SLOT_BYTES = 128 * 128;     // 128 rows x 64 bf16
 template <int BN, int STAGES>
 constexpr int igemm_p_smem_bytes(int stat_channels) {
-  return STAGES * (A_BYTES + BN * 128) + 2 * SLOT_BYTES + 2 * stat_channels * 4 + 1024 + 256;
+  return STAGES * (A_BYTES + BN * 128) + 2 * SLOT_BYTES + 4 * stat_channels * 4 + 1024 + 256;
 }
 
-constexpr int IGP_THREADS_STATS = IG_THREADS + 128;    // + four warps that only accumulate the statistics
+constexpr int STAT_THREADS = 256;                      // eight warps that only accumulate the statistics
+constexpr int IGP_THREADS_STATS = IG_THREADS + STAT_THREADS;
+constexpr int STAT_BAR = 128 + STAT_THREADS;           // epilogue + statistics threads on the slot barriers
 template <int BN, int STAGES, bool STATS>
 __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) igemm_p_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
@@ -251,9 +253,9 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem + STAGES * STAGE_BYTES;
   const int stat_c = STATS ? ((a.Cout + 63) & ~63) : 0;
-  float* s_sum = (float*)(ring + 2 * SLOT_BYTES);
-  float* s_sq = s_sum + stat_c;
-  uint64_t* full = (uint64_t*)(s_sq + stat_c);
+  float* s_sum = (float*)(ring + 2 * SLOT_BYTES);       // [2 row halves][stat_c] sums, then the same for the squares
+  float* s_sq = s_sum + 2 * stat_c;
+  uint64_t* full = (uint64_t*)(s_sq + 2 * stat_c);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
     fence_mbar_init();
   }
   if (STATS)
-    for (int i = threadIdx.x; i < 2 * stat_c; i += blockDim.x) s_sum[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * stat_c; i += blockDim.x) s_sum[i] = 0.f;
   if (warp == 0 && lane == 0) { prefetch_map(&tmA); prefetch_map(&tmB); prefetch_map(&tmC); }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
         // STATS, the statistics warps must be done with it: barrier 4 + slot, 256 threads)
         if (leader) tma_store_wait_read<1>();
         named_bar_sync(1, 128);
-        if (STATS && slot >= 2) named_bar_sync(4 + (slot & 1), 256);
+        if (STATS && slot >= 2) named_bar_sync(4 + (slot & 1), STAT_BAR);
         uint32_t r[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + h * 64;
         tmem_ld32(taddr, r);
@@ -382,19 +384,22 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
           else tma_store_4d(&tmC, so, n0 + h * 64, sx0, sy0, img0);
           tma_store_commit();
         }
-        if (STATS) named_bar_arrive(2 + (slot & 1), 256);      // slot staged: the statistics warps may read it
+        if (STATS) named_bar_arrive(2 + (slot & 1), STAT_BAR);  // slot staged: the statistics warps may read it
       }
     }
     if (leader) tma_store_wait<0>();
   } else if (STATS) {
-    // statistics warps: warp w owns channels [16w, 16w + 16) of every staged 64-channel slot (bf16 values exactly
-    // as stored).  Lane = (column pair cp8, row quarter rsub): 32 rows x 2 channels each, the four row quarters
-    // folded with two shuffle steps, then lanes 0..7 add into the CTA's shared accumulators -- always the same
-    // thread for a given channel, so no atomics.  The quarters walk their rows with a stagger of two so that the
-    // 128-byte swizzle sends the four concurrent rows to different banks.
+    // statistics warps: warp w owns channels [16(w&3), +16) and rows [64(w>>2), +64) of every staged 64-channel slot
+    // (bf16 values exactly as stored).  Lane = (column pair cp8, row group rsub): 16 rows x 2 channels each, the four
+    // row groups folded with two shuffle steps, then lanes 0..7 add into the CTA's shared accumulators of their row
+    // half -- always the same thread for a given (half, channel), so no atomics.  The groups walk their rows with a
+    // stagger of two so that the 128-byte swizzle sends the four concurrent rows to different banks.
     // Barriers 2/3 = slot 0/1 staged, 4/5 = slot 0/1 consumed.
     const int et = threadIdx.x - IG_THREADS;
-    const int cpair = (et >> 5) * 8 + (lane & 7), rsub = lane >> 3;
+    const int sw = et >> 5;
+    const int cpair = (sw & 3) * 8 + (lane & 7), rsub = lane >> 3, half = sw >> 2;
+    float* my_sum = s_sum + half * stat_c;
+    float* my_sq = s_sq + half * stat_c;
     const int total_slots = (int)(BN / 64) * ((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
     int slot = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -403,18 +408,18 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
 #pragma unroll 1
       for (int h = 0; h < BN / 64; ++h, ++slot) {
         const uint8_t* so = ring + (slot & 1) * SLOT_BYTES + (cpair & 3) * 4;
-        named_bar_sync(2 + (slot & 1), 256);
+        named_bar_sync(2 + (slot & 1), STAT_BAR);
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const int rr = rsub * 32 + ((i + 2 * rsub) & 31);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int rr = half * 64 + rsub * 16 + ((i + 2 * rsub) & 15);
           const uint32_t u = *reinterpret_cast<const uint32_t*>(so + rr * 128 + (((cpair >> 2) ^ (rr & 7)) << 4));
           const float v0 = __uint_as_float(u << 16), v1 = __uint_as_float(u & 0xffff0000u);
           s0 += v0; s1 += v1;
           q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
         }
         // done reading: the epilogue warps may overwrite the slot (only waited for when the slot is used again)
-        if (slot + 2 < total_slots) named_bar_arrive(4 + (slot & 1), 256);
+        if (slot + 2 < total_slots) named_bar_arrive(4 + (slot & 1), STAT_BAR);
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {
           s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -422,8 +427,8 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
         }
         const int c = n0 + h * 64 + cpair * 2;
         if (rsub == 0 && c < a.Cout) {
-          s_sum[c] += s0; s_sum[c + 1] += s1;
-          s_sq[c] += q0; s_sq[c + 1] += q1;
+          my_sum[c] += s0; my_sum[c + 1] += s1;
+          my_sq[c] += q0; my_sq[c + 1] += q1;
         }
       }
     }
@@ -433,8 +438,8 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
   if (STATS) {
     for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) {
-      atomicAdd(&a.stat_sum[i], s_sum[i]);
-      atomicAdd(&a.stat_sq[i], s_sq[i]);
+      atomicAdd(&a.stat_sum[i], s_sum[i] + s_sum[stat_c + i]);
+      atomicAdd(&a.stat_sq[i], s_sq[i] + s_sq[stat_c + i]);
     }
   }
 }
