@@ -67,6 +67,7 @@ struct Args {
   int dil;
   const float* w;       // [9][C] fp32
   int flip;             // data gradient: filter rotated by 180 degrees
+  int accumulate;       // y += result (gradient fan-in of parallel branches)
   bf16* y; int ldy;     // output (forward / data gradient)
   const bf16* dy; int lddy;   // weight gradient: output gradient
   float* dwgt;          // weight gradient accumulator [9][C]
@@ -114,8 +115,16 @@ __global__ void __launch_bounds__(256, 2) roll_kernel(const __grid_constant__ CU
       for (int e = 0; e < 8; ++e)
         old[e] = fmaf(wt[8][e], xr[e], fmaf(wt[7][e], xc[e], fmaf(wt[6][e], xl[e], old[e])));
       const int oy = y0 + i - 2;
-      if (col_ok && oy < a.H)
-        *reinterpret_cast<uint4*>(a.y + (((size_t)n * a.H + oy) * a.W + ox) * a.ldy + c) = pack8(old);
+      if (col_ok && oy < a.H) {
+        uint4* dst = reinterpret_cast<uint4*>(a.y + (((size_t)n * a.H + oy) * a.W + ox) * a.ldy + c);
+        if (a.accumulate) {
+          float prev[8];
+          unpack8(*dst, prev);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) old[e] += prev[e];
+        }
+        *dst = pack8(old);
+      }
     }
     if (i >= 1 && i <= R_TH) {
 #pragma unroll
@@ -250,7 +259,16 @@ __global__ void __launch_bounds__(256) direct_kernel(const __grid_constant__ CUt
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(wt[r * 3 + s][e], v[e], acc[e]);
       }
     }
-    if (c < a.C) *reinterpret_cast<uint4*>(a.y + ((size_t)n * HW + p) * a.ldy + c) = pack8(acc);
+    if (c < a.C) {
+      uint4* dst = reinterpret_cast<uint4*>(a.y + ((size_t)n * HW + p) * a.ldy + c);
+      if (a.accumulate) {
+        float prev[8];
+        unpack8(*dst, prev);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += prev[e];
+      }
+      *dst = pack8(acc);
+    }
   }
 }
 
@@ -357,7 +375,8 @@ using namespace aadg::dw;
 
 extern "C" {
 
-/* depthwise 3x3, stride 1, padding = dilation. direction 0: forward, 1: data gradient. w fp32 [9][c] */
+/* depthwise 3x3, stride 1, padding = dilation. direction bit 0: 0 = forward, 1 = data gradient; bit 1 (2): y += result.
+ * w fp32 [9][c] */
 int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int direction, void* y,
                    int ldy, void* stream) {
   DW_REQ_C(c);
@@ -367,7 +386,8 @@ int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const flo
                "depthwise tensors must be 16-byte aligned with channel strides that are multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
   Args a{};
-  a.N = n; a.H = h; a.W = w; a.C = c; a.dil = dil; a.w = wgt; a.flip = direction ? 1 : 0;
+  a.N = n; a.H = h; a.W = w; a.C = c; a.dil = dil; a.w = wgt; a.flip = (direction & 1) ? 1 : 0;
+  a.accumulate = (direction & 2) ? 1 : 0;
   a.y = (bf16*)y; a.ldy = ldy;
   if (tuning_tma() && dil == 1) {
     CUtensorMap m;

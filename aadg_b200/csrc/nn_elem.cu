@@ -679,6 +679,21 @@ __global__ void broadcast_kernel(const bf16* v, int C, bf16* y, int HW, int ldy,
     *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = *reinterpret_cast<const uint4*>(v + n * C + g * 8);
   }
 }
+// y[n, p, :] += scale * v[n, :]  (gradient of a global average pool joining a feature map's gradient); v fp32 [N, C]
+__global__ void broadcast_add_kernel(const float* v, int C, bf16* y, int HW, int ldy, long long total_pix, float scale) {
+  const int G = C >> 3;
+  const long long total = total_pix * G;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / G;
+    const int g = (int)(e - p * G);
+    const long long n = p / HW;
+    V8 a = ld8(y + p * ldy + g * 8);
+    const V8 b = ld8f(v + n * C + g * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.v[i] = fmaf(scale, b.v[i], a.v[i]);
+    st8(y + p * ldy + g * 8, a);
+  }
+}
 // fp32 [N, C] -> bf16 [N, C] (optionally scaled)
 __global__ void f32_to_bf16_kernel(const float* x, bf16* y, long long n, float scale) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -689,7 +704,7 @@ __global__ void f32_to_bf16_kernel(const float* x, bf16* y, long long n, float s
 // y[n,oy,ox,c] = sum_t w[t][c] * x[n, oy + (r-1)*dil*sign, ox + (s-1)*dil*sign, c]; sign = -1 gives the data gradient
 // generic (dilated) form: one output pixel x 8 channels per thread (filter taps come from L1)
 __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx, const float* s_w, int dil, int sign,
-                             bf16* y, int ldy) {
+                             bf16* y, int ldy, int accumulate) {
   const int G = C >> 3;
   const int oy = blockIdx.y, n = blockIdx.z;
   const bf16* xn = x + (size_t)n * H * W * ldx;
@@ -712,6 +727,11 @@ __global__ void dw3x3_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wv.v[i], v.v[i], acc.v[i]);
       }
+    }
+    if (accumulate) {
+      const V8 prev = ld8(yrow + (size_t)ox * ldy + g * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc.v[i] += prev.v[i];
     }
     st8(yrow + (size_t)ox * ldy + g * 8, acc);
   }
@@ -1001,7 +1021,8 @@ static inline int stream_blocks(long long pixels, dim3 blk, int per_sm) {
 int dwconv3x3_generic(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int direction,
                       void* y, int ldy, cudaStream_t st) {
   dim3 grid(std::max(1, std::min((w * (c / 8) + 255) / 256, 64)), h, n);
-  dw3x3_kernel<<<grid, 256, 0, st>>>((const bf16*)x, n, h, w, c, ldx, wgt, dil, direction ? -1 : 1, (bf16*)y, ldy);
+  dw3x3_kernel<<<grid, 256, 0, st>>>((const bf16*)x, n, h, w, c, ldx, wgt, dil, (direction & 1) ? -1 : 1, (bf16*)y, ldy,
+                                     (direction & 2) ? 1 : 0);
   return check_launch("dwconv3x3");
 }
 int dwconv3x3_wgrad_generic(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil,
@@ -1197,6 +1218,13 @@ int aadg_broadcast_pixels(const void* v, int n, int c, void* y, int hw, int ldy,
   broadcast_kernel<<<grid_for((long long)n * hw * (c / 8)), 256, 0, (cudaStream_t)stream>>>((const bf16*)v, c, (bf16*)y, hw, ldy,
                                                                                           (long long)n * hw);
   return check_launch("broadcast");
+}
+/* y bf16 [n, hw, ldy] (c channels) += scale * v fp32 [n, c] broadcast over the hw pixels */
+int aadg_broadcast_add_pixels(const float* v, int n, int c, void* y, int hw, int ldy, float scale, void* stream) {
+  NN_REQ_C(c);
+  broadcast_add_kernel<<<grid_for((long long)n * hw * (c / 8)), 256, 0, (cudaStream_t)stream>>>(v, c, (bf16*)y, hw, ldy,
+                                                                                              (long long)n * hw, scale);
+  return check_launch("broadcast add");
 }
 int aadg_f32_to_bf16(const float* x, void* y, long long count, float scale, void* stream) {
   f32_to_bf16_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, count, scale);

@@ -263,12 +263,14 @@ class Depthwise3x3:
         self.ctx = x if training else None
         return y
 
-    def backward(self, dy):
+    def backward(self, dy, dx=None, accumulate=False):
+        """dx given with accumulate: the data gradient is added to it (fan-in of parallel branches, no separate add)"""
         x = self.ctx
         self.ctx = None
         K.dwconv3x3_wgrad(x, dy, self.dil, self.w.grad, stride=self.stride)
-        dx = torch.empty(x.shape, dtype=BF16, device=x.device)
-        K.dwconv3x3(dy, self.w.data, self.dil, dx, backward_data=True, stride=self.stride)
+        if dx is None:
+            dx, accumulate = torch.empty(x.shape, dtype=BF16, device=x.device), False
+        K.dwconv3x3(dy, self.w.data, self.dil, dx, backward_data=True, stride=self.stride, accumulate=accumulate)
         return dx
 
 
@@ -282,6 +284,18 @@ def fold_pair(d):
     if b is not None:
         K.add_(a, b)
     return a
+
+
+def _identity_grad(ds, dres, extra):
+    """gradient of a residual block's input through its identity / downsample branch, plus an optional extra input
+    gradient: the downsample convolution's data gradient accumulates straight into `extra`"""
+    if ds is not None:
+        if extra is not None:
+            return ds.backward(dres, dx=extra, accumulate=True)
+        return ds.backward(dres)
+    if extra is not None:
+        K.add_(dres, extra)
+    return dres
 
 
 class Bottleneck:
@@ -298,15 +312,19 @@ class Bottleneck:
         idt = self.ds.forward(x, training) if self.ds else x
         return self.c3.forward(self.c2.forward(self.c1.forward(x, training), training), training, res=idt)
 
-    def backward(self, dy):
-        """dy: tensor or pair of tensors whose sum is the gradient of the block output; returns the gradient of the
-        block input as a pair (identity / downsample branch, conv branch) that the next consumer adds on load."""
+    def _identity_grad(self, dres, extra):
+        return _identity_grad(self.ds, dres, extra)
+
+    def backward(self, dy, extra=None):
+        """dy: tensor or pair of tensors whose sum is the gradient of the block output; `extra`: another gradient of
+        the block INPUT (a decoder skip) that is merged here instead of by a separate add pass.  Returns the gradient
+        of the block input (a pair (identity / downsample branch, conv branch) with AADG_GRAD_PAIRS=1)."""
         dy, dy2 = as_pair(dy)
         d2, dres = self.c3.backward(dy, want_dres=True, dy2=dy2)
         d1 = self.c2.backward(d2)
         if not GRAD_PAIRS:      # the conv branch accumulates into the identity branch (TMA reduce-add epilogue)
-            return self.c1.backward(d1, dx=self.ds.backward(dres) if self.ds else dres, accumulate=True)
-        return (self.ds.backward(dres) if self.ds else dres), self.c1.backward(d1)
+            return self.c1.backward(d1, dx=self._identity_grad(dres, extra), accumulate=True)
+        return self._identity_grad(dres, extra), self.c1.backward(d1)
 
 
 class BasicBlock:
@@ -322,13 +340,16 @@ class BasicBlock:
         idt = self.ds.forward(x, training) if self.ds else x
         return self.c2.forward(self.c1.forward(x, training), training, res=idt)
 
-    def backward(self, dy):
+    def _identity_grad(self, dres, extra):
+        return _identity_grad(self.ds, dres, extra)
+
+    def backward(self, dy, extra=None):
         """see Bottleneck.backward"""
         dy, dy2 = as_pair(dy)
         d1, dres = self.c2.backward(dy, want_dres=True, dy2=dy2)
         if not GRAD_PAIRS:
-            return self.c1.backward(d1, dx=self.ds.backward(dres) if self.ds else dres, accumulate=True)
-        return (self.ds.backward(dres) if self.ds else dres), self.c1.backward(d1)
+            return self.c1.backward(d1, dx=self._identity_grad(dres, extra), accumulate=True)
+        return self._identity_grad(dres, extra), self.c1.backward(d1)
 
 
 RESNETS = {
@@ -406,10 +427,11 @@ class ResNetEncoder:
         skips = list(d_skips) if d_skips is not None else [None, d_stride4, None, None]
         d = d_last
         for li in (3, 2, 1, 0):
-            if li < 3 and skips[li + 1] is not None:
-                K.add_(as_pair(d)[0], skips[li + 1])          # extra gradient of stage li's output (= feats[li + 1])
-            for blk in reversed(self.blocks[li]):
-                d = blk.backward(d)                 # (identity branch, conv branch): summed by the next consumer
+            blocks = self.blocks[li]
+            for bi in range(len(blocks) - 1, -1, -1):
+                # the gradient of feats[li] (a decoder skip) joins the gradient of stage li's first block's input
+                extra = skips[li] if (bi == 0 and li > 0) else None
+                d = blocks[bi].backward(d, extra=extra)
         d = K.maxpool_bwd(fold_pair(d), arg, f1.shape)
         if skips[0] is not None:
             K.add_(d, skips[0])
@@ -555,8 +577,8 @@ class SeparableConvBN:
     def forward(self, x, training, out=None):
         return self.pw.forward(self.dw.forward(x, training), training, out=out)
 
-    def backward(self, dy):
-        return self.dw.backward(self.pw.backward(dy))
+    def backward(self, dy, dx=None, accumulate=False):
+        return self.dw.backward(self.pw.backward(dy), dx=dx, accumulate=accumulate)
 
 
 class DeepLabV3PlusDecoder:
@@ -610,13 +632,11 @@ class DeepLabV3PlusDecoder:
         dpj = self.sep.backward(da)
         dcat = self.project.backward(dpj)                                 # [n, h, w, 5*oc]
         dx = self.b0.backward(dcat[..., 0:oc])
-        for i, br in enumerate(self.br):
-            K.add_(dx, br.backward(dcat[..., (i + 1) * oc:(i + 2) * oc]))
+        for i, br in enumerate(self.br):       # each branch's depthwise data gradient lands on dx directly
+            br.backward(dcat[..., (i + 1) * oc:(i + 2) * oc], dx=dx, accumulate=True)
         dpv = K.f32_to_bf16(K.global_sum(dcat[..., 4 * oc:5 * oc], 1.0)).view(n, 1, 1, oc)
         dpooled = self.bp.backward(dpv)                                   # [n,1,1,cenc]
-        tmp = torch.empty(xs, dtype=BF16, device=dev)
-        K.broadcast_pixels((dpooled.float() / (h * w)).to(BF16), tmp)
-        K.add_(dx, tmp)
+        K.broadcast_add_pixels(dpooled.reshape(n, cenc).float().contiguous(), dx, 1.0 / (h * w))
         return dx, d_high
 
 

@@ -102,18 +102,27 @@ def broadcast_pixels(v, y):
     _call("aadg_broadcast_pixels", p(v), n, c, p(y), h * w, _ld(y))
 
 
+def broadcast_add_pixels(v, y, scale=1.0):
+    """y bf16 [n,h,w,c] += scale * v fp32 [n,c]"""
+    n, h, w, c = y.shape
+    assert v.dtype == torch.float32 and v.shape == (n, c) and v.is_contiguous()
+    _call("aadg_broadcast_add_pixels", p(v), n, c, p(y), h * w, _ld(y), float(scale))
+
+
 def f32_to_bf16(x, scale=1.0):
     y = torch.empty(x.shape, dtype=BF16, device=x.device)
     _call("aadg_f32_to_bf16", p(x), p(y), x.numel(), float(scale))
     return y
 
 
-def dwconv3x3(x, w, dil, y, backward_data=False, stride=1):
-    """forward: x [n,h,w,c] -> y [n,ho,wo,c]; backward_data: x is dy [n,ho,wo,c], y is dx [n,h,w,c]."""
+def dwconv3x3(x, w, dil, y, backward_data=False, stride=1, accumulate=False):
+    """forward: x [n,h,w,c] -> y [n,ho,wo,c]; backward_data: x is dy [n,ho,wo,c], y is dx [n,h,w,c];
+    accumulate (stride 1): y += result."""
     if stride == 1:
         n, h, wd, c = x.shape
-        _call("aadg_dwconv3x3", p(x), n, h, wd, c, _ld(x), p(w), dil, int(backward_data), p(y), _ld(y))
+        _call("aadg_dwconv3x3", p(x), n, h, wd, c, _ld(x), p(w), dil, int(backward_data) | (2 if accumulate else 0), p(y), _ld(y))
         return
+    assert not accumulate, "strided depthwise: accumulate is not implemented"
     big, small = (y, x) if backward_data else (x, y)
     n, h, wd, c = big.shape
     _call("aadg_dwconv3x3_strided", p(x), n, h, wd, c, _ld(x), p(w), dil, stride, int(backward_data), p(y), small.shape[1],

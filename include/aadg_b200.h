@@ -239,8 +239,11 @@ int aadg_copy_bf16(const void* x, int ldx, void* y, int ldy, long long pixels, i
 int aadg_global_sum(const void* x, int n, int hw, int c, int ld, float* out, float scale, void* stream);
 /* y[n, p, 0:c] = v[n, 0:c]  (bilinear resize of a 1x1 map) */
 int aadg_broadcast_pixels(const void* v, int n, int c, void* y, int hw, int ldy, void* stream);
+/* y bf16 [n, hw, ldy] (c channels) += scale * v fp32 [n, c] broadcast over the pixels (backward of the pooled branch) */
+int aadg_broadcast_add_pixels(const float* v, int n, int c, void* y, int hw, int ldy, float scale, void* stream);
 int aadg_f32_to_bf16(const float* x, void* y, long long count, float scale, void* stream);
 /* depthwise 3x3, stride 1, padding = dilation; w fp32 [9][c]; direction 0 forward, 1 data gradient */
+/* (direction bit 1 (value 2): y += result) */
 int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int direction, void* y,
                    int ldy, void* stream);
 int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int lddy, int dil, float* dw,
