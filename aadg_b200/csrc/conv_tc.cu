@@ -230,6 +230,11 @@ struct IgemmPArgs {
   int accumulate;
   int Wout, Hout, Nimg, Cout;
   float* stat_sum; float* stat_sq;
+  // HALO variant (k_blocks == 1): the distinct input rows of the filter are staged once per tile with their
+  // horizontal halo and every tap reads its shifted window out of them
+  int halo_rows, halo_row_bytes, halo_tx_bytes, halo_dx0, halo_k16, halo_base_offset_mode;
+  short halo_dy[4];
+  short halo_row_of_tap[MAX_TAPS];
   Taps taps;
 };
 constexpr int SLOT_BYTES = 128 * 128;     // 128 rows x 64 bf16
@@ -241,16 +246,25 @@ constexpr int igemm_p_smem_bytes(int stat_channels) {
 constexpr int STAT_THREADS = 256;                      // eight warps that only accumulate the statistics
 constexpr int IGP_THREADS_STATS = IG_THREADS + STAT_THREADS;
 constexpr int STAT_BAR = 128 + STAT_THREADS;           // epilogue + statistics threads on the slot barriers
-template <int BN, int STAGES, bool STATS>
+// HALO (3x3-style filters on maps at least 65 pixels wide, Cin <= 64, BN = 64): a tile is 128 consecutive pixels of
+// one image row.  Instead of one shifted A tile per tap (R*S re-reads of the input through L2), the R distinct input
+// rows are staged once per tile as (128 + span) x 64-channel boxes and tap (r, s) is the 128-row window that starts s
+// pixels into row r: a UMMA descriptor whose start address is 128*s bytes into the swizzled box (the 128-byte swizzle
+// is a function of the shared-memory address, so TMA and MMA agree on any 128-byte-aligned window).  The R*S weight
+// tiles of the CTA's output-channel block stay resident in shared memory; blockIdx.y = output-channel block.
+template <int BN, int STAGES, bool STATS, bool HALO = false>
 __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) igemm_p_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmC,
                                                                 const IgemmPArgs a) {
   constexpr int B_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // HALO: [resident weights: taps x BN x 128 B][stages: rows x row_bytes]; otherwise [stages: A tile + B tile]
+  const int STAGE_BYTES = HALO ? a.halo_rows * a.halo_row_bytes : A_BYTES + B_BYTES;
+  uint8_t* wres = smem_base;
+  uint8_t* smem = smem_base + (HALO ? a.taps.n * B_BYTES : 0);
   uint8_t* ring = smem + STAGES * STAGE_BYTES;
   const int stat_c = STATS ? ((a.Cout + 63) & ~63) : 0;
   float* s_sum = (float*)(ring + 2 * SLOT_BYTES);       // [2 row halves][stat_c] sums, then the same for the squares
@@ -259,12 +273,14 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  uint64_t* wbar = acc_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(wbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(wbar, 1);
     fence_mbar_init();
   }
   if (STATS)
@@ -277,11 +293,12 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
   const uint32_t tmem_base = *tmem_slot;
 
   const int lg_tn = 7 - a.lg_tw - a.lg_th;
-  const int n_tiles = a.tiles_x * a.tiles_y * a.tiles_n * a.cout_tiles;
+  const int n_tiles = a.tiles_x * a.tiles_y * a.tiles_n * (HALO ? 1 : a.cout_tiles);
   const int total_k = a.taps.n * a.k_blocks;
 
   auto decode = [&](int t, int& sx0, int& sy0, int& img0, int& n0) {
-    n0 = (t % a.cout_tiles) * BN; t /= a.cout_tiles;
+    if (HALO) n0 = blockIdx.y * BN;
+    else { n0 = (t % a.cout_tiles) * BN; t /= a.cout_tiles; }
     sx0 = (t % a.tiles_x) << a.lg_tw; t /= a.tiles_x;
     sy0 = (t % a.tiles_y) << a.lg_th; t /= a.tiles_y;
     img0 = t << lg_tn;
@@ -290,9 +307,23 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0, phase = 0;
+      if (HALO) {       // the CTA's weight tiles, once
+        mbar_arrive_expect_tx(wbar, (uint32_t)(a.taps.n * B_BYTES));
+        for (int tap = 0; tap < a.taps.n; ++tap)
+          tma_load_3d(wres + tap * B_BYTES, &tmB, wbar, 0, blockIdx.y * BN, a.taps.w[tap]);
+      }
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         int sx0, sy0, img0, n0;
         decode(t, sx0, sy0, img0, n0);
+        if (HALO) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)a.halo_tx_bytes);     // boxes are (128 + span) rows, slots are padded
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          for (int r = 0; r < a.halo_rows; ++r)
+            tma_load_4d(sa + r * a.halo_row_bytes, &tmA, &full[stage], 0, sx0 + a.halo_dx0, sy0 + a.halo_dy[r], img0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         for (int tap = 0; tap < a.taps.n; ++tap) {
           const int ix = sx0 * a.in_step + a.taps.dx[tap], iy = sy0 * a.in_step + a.taps.dy[tap];
           const int wi = a.taps.w[tap];
@@ -311,11 +342,29 @@ __global__ void __launch_bounds__(STATS ? IGP_THREADS_STATS : IG_THREADS, 1) ige
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       int stage = 0, phase = 0, it = 0;
+      if (HALO) { mbar_wait(wbar, 0); tc_fence_after(); }
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * BN;
+        if (HALO) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t wa = smem_u32(wres);
+          for (int tap = 0; tap < a.taps.n; ++tap) {
+            const uint32_t start = sa + a.halo_row_of_tap[tap] * a.halo_row_bytes + (a.taps.dx[tap] - a.halo_dx0) * 128;
+            const uint64_t adesc = make_sdesc(start, 16, 1024, a.halo_base_offset_mode ? (start >> 7) : 0);
+            const uint64_t bdesc = make_sdesc(wa + tap * B_BYTES, 16, 1024);
+            for (int kk = 0; kk < a.halo_k16; ++kk)
+              umma_bf16(acc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (tap | kk) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&acc_full[buf]);
+          continue;
+        }
         for (int k = 0; k < total_k; ++k) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -782,6 +831,27 @@ static int launch_igemm_p_t(const CUtensorMap& mA, const CUtensorMap& mB, const 
   return check_launch("igemm persistent kernel");
 }
 
+static int tuning_halo() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AADG_CONV_HALO");      // 0 = off, 1 = on (descriptor base offset 0), 2 = on with base offset
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+template <bool STATS>
+static int launch_igemm_halo_t(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, const IgemmPArgs& pa,
+                               dim3 grid, int smem, cudaStream_t st) {
+  static int attr_bytes = 0;
+  if (smem > attr_bytes) {
+    AADG_CUDA_TRY(cudaFuncSetAttribute(igemm_p_kernel<64, 2, STATS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_bytes = smem;
+  }
+  igemm_p_kernel<64, 2, STATS, true><<<grid, STATS ? IGP_THREADS_STATS : IG_THREADS, smem, st>>>(mA, mB, mC, pa);
+  return check_launch("igemm halo kernel");
+}
+
 // One implicit-GEMM launch.  in: bf16 [Nimg, Hin, Win, ld_in] (Cin channels used); wgt: bf16 [n_w_taps][Cn][Cin];
 // logical output grid Wsub x Hsub mapped to physical pixels by (o_step, o_y0, o_x0).
 static int launch_igemm(const void* in, int Nimg, int Hin, int Win, int Cin, int ld_in, int in_step,
@@ -836,6 +906,63 @@ static int launch_igemm(const void* in, int Nimg, int Hin, int Win, int Cin, int
     if (rc) return rc;
   }
   const int cout_tiles = (Cn + bn - 1) / bn;
+  // HALO variant: several taps, one 64-channel k-block, tiles = 128 pixels of one image row
+  if (persistent && tuning_halo() && taps.n > 1 && a.k_blocks == 1 && in_step == 1 && a.lg_tw == 7 && a.lg_th == 0) {
+    IgemmPArgs pa{};
+    int dx0 = 1 << 20, dx1 = -(1 << 20);
+    for (int t = 0; t < taps.n; ++t) {
+      dx0 = std::min<int>(dx0, taps.dx[t]); dx1 = std::max<int>(dx1, taps.dx[t]);
+      int r = 0;
+      while (r < pa.halo_rows && pa.halo_dy[r] != taps.dy[t]) ++r;
+      if (r == pa.halo_rows) {
+        if (pa.halo_rows == 4) { pa.halo_rows = 99; break; }
+        pa.halo_dy[pa.halo_rows++] = taps.dy[t];
+      }
+      pa.halo_row_of_tap[t] = (short)r;
+    }
+    const int span = dx1 - dx0;
+    const int row_bytes = (int)align_up((size_t)(128 + span) * 128, 1024);
+    const int halo_cout_tiles = (Cn + 63) / 64;
+    const int stat_c = stat_sum ? ((Cn + 63) & ~63) : 0;
+    const int smem = taps.n * 64 * 128 + 2 * pa.halo_rows * row_bytes + 2 * SLOT_BYTES + 4 * stat_c * 4 + 1024 + 256;
+    if (pa.halo_rows <= 4 && 128 + span <= 256 && smem <= 227 * 1024) {
+      CUtensorMap hA, hB, mC;
+      {
+        const long long dims[4] = {Cin, Win, Hin, Nimg};
+        const long long strides[3] = {ld_in, (long long)Win * ld_in, (long long)Hin * Win * ld_in};
+        const int box[4] = {64, 128 + span, 1, 1};
+        int rc = make_map_bf16(&hA, in, 4, dims, strides, box, nullptr);
+        if (rc) return rc;
+      }
+      {
+        const long long dims[3] = {Cin, Cn, n_w_taps};
+        const long long strides[2] = {Cin, (long long)Cn * Cin};
+        const int box[3] = {64, 64, 1};
+        int rc = make_map_bf16(&hB, wgt, 3, dims, strides, box, nullptr);
+        if (rc) return rc;
+      }
+      {
+        const long long dims[4] = {Cn, Wout, Hout, Nimg};
+        const long long strides[3] = {ldc, (long long)Wout * ldc, (long long)Hout * Wout * ldc};
+        const int box[4] = {64, 128, 1, 1};
+        int rc = make_map_bf16(&mC, (const __nv_bfloat16*)out + c_off, 4, dims, strides, box, nullptr);
+        if (rc) return rc;
+      }
+      pa.lg_tw = 7; pa.lg_th = 0;
+      pa.tiles_x = a.tiles_x; pa.tiles_y = a.tiles_y; pa.tiles_n = a.tiles_n; pa.cout_tiles = halo_cout_tiles;
+      pa.in_step = 1; pa.k_blocks = 1; pa.accumulate = accumulate;
+      pa.Wout = Wout; pa.Hout = Hout; pa.Nimg = Nimg; pa.Cout = Cn;
+      pa.stat_sum = stat_sum; pa.stat_sq = stat_sq;
+      pa.halo_row_bytes = row_bytes; pa.halo_dx0 = dx0; pa.halo_k16 = (Cin + 15) / 16;
+      pa.halo_tx_bytes = pa.halo_rows * (128 + span) * 128;
+      pa.halo_base_offset_mode = tuning_halo() == 2 ? 1 : 0;
+      pa.taps = taps;
+      const long long n_tiles = (long long)pa.tiles_x * pa.tiles_y * pa.tiles_n;
+      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(n_tiles, num_sms() / halo_cout_tiles)), halo_cout_tiles);
+      if (stat_sum) return launch_igemm_halo_t<true>(hA, hB, mC, pa, grid, smem, st);
+      return launch_igemm_halo_t<false>(hA, hB, mC, pa, grid, smem, st);
+    }
+  }
   if (persistent) {
     // persistent kernel with TMA-store epilogue: output = channel slice [c_off, c_off + Cn) of the NHWC tensor
     CUtensorMap mC;

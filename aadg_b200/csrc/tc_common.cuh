@@ -119,8 +119,9 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
 //   K-major : rows of 128 bytes (64 bf16 along K), 8-row groups every `sbo` bytes; lbo unused (1)
 //   MN-major: 128-byte rows along MN (64 bf16), 8 K-rows per 1024-byte atom; `lbo` = bytes between
 //             64-element MN blocks, `sbo` = bytes between 8-row K groups
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                               uint32_t base_offset = 0) {
+  uint64_t d = (uint64_t)(base_offset & 7) << 49;       // start address inside a 1024-byte swizzle atom (row & 7)
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;

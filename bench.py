@@ -38,6 +38,9 @@ def parse_args():
     ap.add_argument("--items", type=int, default=8, help="TRAIN.BATCH_SIZE: items per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scale-crop", action="store_true", help="skip DGRandomScaleCrop (fused policy+normalise pass)")
+    ap.add_argument("--arch", default="deeplabv3plus", choices=["deeplabv3plus", "unet"])
+    ap.add_argument("--dataset", default="optic", choices=["optic", "vessel"],
+                    help="optic: 3 source domains, 2 classes (config 2); vessel: 4 domains, 1 class (config 4)")
     return ap.parse_args()
 
 
@@ -50,10 +53,16 @@ class Cfg:
     SEED = 0
 
 
+def n_source_domains(a):
+    return 3 if a.dataset == "optic" else 4
+
+
 def workload_config(a, n_gpus):
-    d, m = 3, 6
-    return {"workload": "config2: OD/OC 3-source-domain %dx%d fundus, DeepLabV3+/%s, Sinkhorn diversity reward, "
-                        "search step (augment->fwd->rewards->bwd->Adam)" % (a.size, a.size, a.backbone),
+    d, m = n_source_domains(a), 6
+    name = "config2: OD/OC 3-source-domain %dx%d fundus, DeepLabV3+/%s" if (a.dataset, a.arch) == ("optic", "deeplabv3plus") \
+        else ("config4-style: " + a.dataset + " %d-source-domain" % d + " %dx%d, " + a.arch + "/%s")
+    return {"workload": (name + ", Sinkhorn diversity reward, search step (augment->fwd->rewards->bwd->Adam)") %
+                        (a.size, a.size, a.backbone),
             "items_per_gpu": a.items, "domains": d, "policies_M": m, "images_per_step_per_gpu": a.items * d * m,
             "global_images_per_step": a.items * d * m * n_gpus, "image_size": a.size, "sub_policy_ops_L": 2,
             "scale_crop": "none" if a.no_scale_crop else
@@ -212,21 +221,23 @@ def run_ours(a):
     from aadg_b200 import _lib
     from aadg_b200.data.policy import parse_policies
     from aadg_b200.host.search import SearchEngine
-    from aadg_b200.nn import DeepLabV3Plus
+    from aadg_b200.nn import DeepLabV3Plus, Unet
     from aadg_b200.ops import conv as C
-    from aadg_b200.synth import fundus_batch, random_policies
+    from aadg_b200.synth import fundus_batch, random_policies, vessel_batch
 
-    d, m = 3, 6
+    d, m = n_source_domains(a), 6
     s = a.items * d
-    imgs, masks = fundus_batch(s, a.size, a.size, seed=1023 + rank)
+    make = fundus_batch if a.dataset == "optic" else vessel_batch
+    imgs, masks = make(s, a.size, a.size, seed=1023 + rank)
     h_imgs = torch.from_numpy(imgs).pin_memory()
     h_masks = torch.from_numpy(masks).pin_memory()
     d_imgs, d_masks = h_imgs.to(dev), h_masks.to(dev)
     domains = [i % d for i in range(s)]                     # row order b*D + d
 
-    model = DeepLabV3Plus(encoder_name=a.backbone, encoder_weights=None, in_channels=3, classes=2,
-                          aux_params=dict(pooling="avg"), device=dev, seed=1023)
-    eng = SearchEngine(model, n_domains=d, M=m, lr=1e-3, dataset="optic", seed=1023,
+    ctor = DeepLabV3Plus if a.arch == "deeplabv3plus" else Unet
+    model = ctor(encoder_name=a.backbone, encoder_weights=None, in_channels=3, classes=2 if a.dataset == "optic" else 1,
+                 aux_params=dict(pooling="avg"), device=dev, seed=1023)
+    eng = SearchEngine(model, n_domains=d, M=m, lr=1e-3, dataset=a.dataset, seed=1023,
                        crop=None if a.no_scale_crop else a.size, scale_range=(1, 1.5))
     eng.set_policies(parse_policies(random_policies(m=m, seed=1023), Cfg), epoch=0)
 
@@ -255,7 +266,7 @@ def run_ours(a):
     def step_resident():
         return eng.step(d_imgs, d_masks, domains)
 
-    result_host = torch.empty(4, dtype=torch.float32).pin_memory()
+    result_host = torch.empty(2 + (2 if a.dataset == "optic" else 1), dtype=torch.float32).pin_memory()
 
     def step_e2e():
         xi = h_imgs.to(dev, non_blocking=True)
@@ -320,7 +331,7 @@ def run_ours(a):
             "dtype": "bf16", "data": "synthetic", "config": workload_config(a, world), "clocks": clk,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                     "h2d_bytes_per_step": int(h_imgs.numel() + h_masks.numel()) + 160 * n_img + 4 * d * n_img,
-                    "d2h_bytes_per_step": 16},
+                    "d2h_bytes_per_step": int(result_host.numel()) * 4},
             "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "roofline": roof}
     if world == 1 and not a.no_cpu_baseline:
         try:

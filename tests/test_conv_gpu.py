@@ -54,6 +54,11 @@ CASES = [
     (5, 64, 64, 64, 256, 3, 3, 1, 1, 1),
     (6, 60, 50, 320, 256, 1, 1, 1, 0, 1),
     (4, 32, 32, 256, 128, 3, 3, 1, 1, 1),       # 256-wide weight-gradient tiles
+    # halo-reuse kernel (Cin <= 64, rows of 128 pixels): partial tiles, dilation, small / several channel blocks
+    (2, 40, 200, 64, 64, 3, 3, 1, 1, 1),
+    (1, 20, 128, 32, 48, 3, 3, 1, 2, 2),
+    (1, 16, 256, 16, 128, 3, 3, 1, 1, 1),
+    (3, 9, 130, 64, 64, 3, 3, 1, 1, 1),
 ]
 
 
