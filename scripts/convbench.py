@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from aadg_b200.nn import DeepLabV3Plus  # noqa: E402
+from aadg_b200.nn import DeepLabV3Plus, Unet  # noqa: E402
 from aadg_b200.ops import conv as C  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -19,14 +19,16 @@ ap.add_argument("--backbone", default="resnet50")
 ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--n", type=int, default=144)
 ap.add_argument("--top", type=int, default=40)
+ap.add_argument("--arch", default="deeplabv3plus", choices=["deeplabv3plus", "unet"])
+ap.add_argument("--classes", type=int, default=2)
 a = ap.parse_args()
 pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
 TF, BW = pk["bf16_tflops_sustained"] * 1e12, pk["hbm_gbs"] * 1e9
 
-model = DeepLabV3Plus(encoder_name=a.backbone, encoder_weights=None, in_channels=3, classes=2,
-                      aux_params=dict(pooling="avg"), seed=1)
+model = (DeepLabV3Plus if a.arch == "deeplabv3plus" else Unet)(
+    encoder_name=a.backbone, encoder_weights=None, in_channels=3, classes=a.classes, aux_params=dict(pooling="avg"), seed=1)
 x = torch.randn(a.n, 3, a.size, a.size, device="cuda")
-t = (torch.rand(a.n, 2, a.size, a.size, device="cuda") > 0.5).float()
+t = (torch.rand(a.n, a.classes, a.size, a.size, device="cuda") > 0.5).float()
 for _ in range(2):
     model.store.zero_grad()
     model.loss_step(x, t)
