@@ -760,6 +760,136 @@ __global__ void __launch_bounds__(IG_THREADS) wgrad_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ---- wgrad, halo-reuse variant ---------------------------------------------------------------------------
+// For 3x3-style filters with Cin <= 64 on maps wider than 64 pixels (stride 1): a K tile is 128 consecutive pixels of one
+// image row.  dY is staged once per tile and the distinct input rows of the filter once each with their horizontal
+// halo; tap (r, s) is the MN-major B window that starts s pixels into row r (same address-based swizzle argument as
+// the forward halo kernel), accumulated into its own 64 TMEM columns.  512 columns hold 8 taps, so a 3x3 filter
+// takes two passes (blockIdx.y) of 5 + 4 taps; every pass stages only the rows its taps touch.  Compared with one
+// CTA per tap this cuts the TMA boxes per 128 pixels from 4 per tap to 1 + rows per pass.
+struct WgradHaloArgs {
+  int tiles_x, H, N, ksplit;
+  int Cout, Cin;
+  float* dw;
+  int row_bytes, box_bytes, dx0, taps_per_pass;
+  short row_of_tap[MAX_TAPS];
+  short row_dy[4];
+  Taps taps;
+};
+constexpr int WH_PIX = 128;
+constexpr int WH_A_BYTES = 2 * WH_PIX * 128;
+constexpr int WH_STAGES = 2;
+
+__global__ void __launch_bounds__(IG_THREADS, 1) wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                                   const __grid_constant__ CUtensorMap tmX,
+                                                                   const WgradHaloArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int STAGE_BYTES = WH_A_BYTES + 3 * a.row_bytes;
+  uint64_t* full = (uint64_t*)(smem + WH_STAGES * STAGE_BYTES);
+  uint64_t* empty = full + WH_STAGES;
+  uint64_t* acc_full = empty + WH_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * 128;
+  const int tap0 = blockIdx.y * a.taps_per_pass, tap1 = min(a.taps.n, tap0 + a.taps_per_pass);
+  const int r_lo = a.row_of_tap[tap0], n_rows = a.row_of_tap[tap1 - 1] - r_lo + 1;
+  const int split = blockIdx.z;
+  const int n_tiles = a.tiles_x * a.H * a.N;
+  const int my_tiles = split < n_tiles ? (n_tiles - split + a.ksplit - 1) / a.ksplit : 0;
+  const bool half_a = a.Cout - co0 <= 64;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WH_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (half_a) {      // the second 64-channel half of dY is padding: zero it once
+    for (int i = threadIdx.x; i < WH_STAGES * (WH_PIX * 128 / 16); i += IG_THREADS) {
+      const int st = i / (WH_PIX * 128 / 16), o = i % (WH_PIX * 128 / 16);
+      reinterpret_cast<uint4*>(smem + st * STAGE_BYTES + WH_PIX * 128)[o] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) { prefetch_map(&tmDY); prefetch_map(&tmX); }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0, phase = 0;
+      const uint32_t tx_bytes = (uint32_t)((half_a ? WH_PIX * 128 : WH_A_BYTES) + n_rows * a.box_bytes);
+      for (int i = 0; i < my_tiles; ++i) {
+        int t = split + i * a.ksplit;
+        const int ox = (t % a.tiles_x) * WH_PIX; t /= a.tiles_x;
+        const int oy = t % a.H, img = t / a.H;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], tx_bytes);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        tma_load_4d(sa, &tmDY, &full[stage], co0, ox, oy, img);
+        if (!half_a) tma_load_4d(sa + WH_PIX * 128, &tmDY, &full[stage], co0 + 64, ox, oy, img);
+        for (int r = 0; r < n_rows; ++r)
+          tma_load_4d(sa + WH_A_BYTES + r * a.row_bytes, &tmX, &full[stage], 0, ox + a.dx0, oy + a.row_dy[r_lo + r], img);
+        if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      int stage = 0, phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        for (int tap = tap0; tap < tap1; ++tap) {
+          const uint32_t xb = sa + WH_A_BYTES + (a.row_of_tap[tap] - r_lo) * a.row_bytes + (a.taps.dx[tap] - a.dx0) * 128;
+#pragma unroll
+          for (int kk = 0; kk < WH_PIX / 16; ++kk) {
+            const uint64_t adesc = make_sdesc(sa + kk * 2048, WH_PIX * 128, 1024);
+            const uint64_t bdesc = make_sdesc(xb + kk * 2048, WH_PIX * 128, 1024);
+            umma_bf16(tmem_base + (tap - tap0) * 64, adesc, bdesc, idesc, (i | kk) != 0);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (my_tiles > 0) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int tap = tap0; tap < tap1; ++tap) {
+      float* drow = a.dw + ((size_t)a.taps.w[tap] * a.Cout + co) * a.Cin;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (tap - tap0) * 64 + c, r);
+        tmem_ld_wait();
+        if (co < a.Cout) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (c + g * 4 < a.Cin) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c + g * 4),
+                           "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
+                           "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                           : "memory");
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- host ---------------------------------------------------------------------------------------------
 static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -1162,6 +1292,68 @@ int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, c
       a.taps.dx[i * s + j] = (short)(j * dil - pad);
       a.taps.w[i * s + j] = (short)(i * s + j);
     }
+  // halo-reuse variant: several taps, Cin <= 64, stride 1, rows of 128 pixels
+  {
+    static int halo_mode = -1;
+    if (halo_mode < 0) { const char* e = getenv("AADG_WGRAD_HALO"); halo_mode = e ? atoi(e) : 1; }
+    if (halo_mode && stride == 1 && r * s > 1 && cin <= 64 && wo >= 65) {
+      WgradHaloArgs ha{};
+      int n_rows = 0, dx0 = 1 << 20, dx1 = -(1 << 20);
+      bool ok = true;
+      for (int t = 0; t < a.taps.n; ++t) {
+        dx0 = std::min<int>(dx0, a.taps.dx[t]); dx1 = std::max<int>(dx1, a.taps.dx[t]);
+        int q = 0;
+        while (q < n_rows && ha.row_dy[q] != a.taps.dy[t]) ++q;
+        if (q == n_rows) {
+          if (n_rows == 4) { ok = false; break; }
+          ha.row_dy[n_rows++] = a.taps.dy[t];
+        }
+        ha.row_of_tap[t] = (short)q;
+      }
+      const int span = dx1 - dx0;
+      const int passes = (a.taps.n + 7) / 8;                     // 512 TMEM columns = 8 taps x 64
+      const int tpp = (a.taps.n + passes - 1) / passes;          // balanced: 3x3 -> 5 + 4
+      // a pass may touch at most 3 distinct rows (its shared-memory stage holds three)
+      for (int p = 0; ok && p < passes; ++p) {
+        const int t0 = p * tpp, t1 = std::min(a.taps.n, t0 + tpp);
+        if (ha.row_of_tap[t1 - 1] - ha.row_of_tap[t0] + 1 > 3 || ha.row_of_tap[t1 - 1] < ha.row_of_tap[t0]) ok = false;
+      }
+      const int row_bytes = (int)align_up((size_t)(WH_PIX + span) * 128, 1024);
+      const int smem = WH_STAGES * (WH_A_BYTES + 3 * row_bytes) + 1024 + 256;
+      if (ok && WH_PIX + span <= 256 && smem <= 227 * 1024) {
+        CUtensorMap hDY, hX;
+        {
+          const long long dims[4] = {cout, wo, ho, n};
+          const long long strides[3] = {lddy, (long long)wo * lddy, (long long)ho * wo * lddy};
+          const int box[4] = {64, WH_PIX, 1, 1};
+          rc = make_map_bf16(&hDY, dy, 4, dims, strides, box, nullptr);
+          if (rc) return rc;
+        }
+        {
+          const long long dims[4] = {cin, w, h, n};
+          const long long strides[3] = {ldx, (long long)w * ldx, (long long)h * w * ldx};
+          const int box[4] = {64, WH_PIX + span, 1, 1};
+          rc = make_map_bf16(&hX, x, 4, dims, strides, box, nullptr);
+          if (rc) return rc;
+        }
+        ha.tiles_x = (wo + WH_PIX - 1) / WH_PIX; ha.H = ho; ha.N = n;
+        ha.Cout = cout; ha.Cin = cin; ha.dw = dw;
+        ha.row_bytes = row_bytes; ha.box_bytes = (WH_PIX + span) * 128; ha.dx0 = dx0; ha.taps_per_pass = tpp;
+        ha.taps = a.taps;
+        const long long tiles = (long long)ha.tiles_x * ho * n;
+        const int base = ((cout + 127) / 128) * passes;
+        ha.ksplit = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(tiles, 65535), (148 + base - 1) / base));
+        static int attr = 0;
+        if (smem > attr) {
+          AADG_CUDA_TRY(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          attr = smem;
+        }
+        dim3 grid((cout + 127) / 128, passes, ha.ksplit);
+        wgrad_halo_kernel<<<grid, IG_THREADS, smem, (cudaStream_t)stream>>>(hDY, hX, ha);
+        return check_launch("wgrad halo kernel");
+      }
+    }
+  }
   // 256-wide Cin tiles halve the dY traffic per flop (one CTA per SM pair of stages in flight instead of four small ones)
   static int wide_mode = -1;
   if (wide_mode < 0) { const char* e = getenv("AADG_WGRAD_BN256"); wide_mode = e ? atoi(e) : 0; }   // measured neutral on the ResNet-50 step: off by default
