@@ -842,6 +842,18 @@ class SegNet:
 
     forward = __call__
 
+    def evaluate_batch(self, x, target, thr=0.75):
+        """Inference + metrics in one pass (validate(), search_dg.py:236-245): logits float32 [N,classes,H,W], the BCE
+        of sigmoid(logits) vs target (mean) and the TP/FP/FN counts of (sigmoid(logits) > thr) per sample and class."""
+        dec, pooled = self.features(x)
+        z = self._head(dec)
+        n, _, hh, ww = x.shape
+        logits = torch.empty((n, self.classes, hh, ww), dtype=torch.float32, device=x.device)
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=x.device)
+        counts = torch.zeros((n, self.classes, 3), dtype=torch.int32, device=x.device)
+        K.seg_loss_fwd(z, target, thr, loss_sum, counts, logits)
+        return dict(logits=logits, counts=counts, pooled=pooled, loss=(loss_sum / float(logits.numel())).float())
+
     def loss_step(self, x, target, thr=0.5, want_logits=False):
         """Forward + BCELoss(sigmoid(logits), target) (mean) + Dice counts, then the whole backward.
         Gradients are left in store.grads (call store.zero_grad() before, store.adam_step() after).
@@ -899,8 +911,8 @@ def Unet(encoder_name="resnet34", encoder_depth=5, encoder_weights=None, decoder
          decoder_channels=(256, 128, 64, 32, 16), decoder_attention_type=None, in_channels=3, classes=1,
          activation=None, aux_params=None, device="cuda", seed=0):
     """smp.Unet constructor shape (the north star's UNet / RVS configuration)."""
-    if encoder_name not in RESNETS:
-        raise NotImplementedError("encoder %r: resnet18/34/50 are implemented" % encoder_name)
+    if encoder_name not in RESNETS and encoder_name != "mobilenet_v2":
+        raise NotImplementedError("encoder %r: mobilenet_v2 and resnet18/34/50 are implemented" % encoder_name)
     if encoder_weights not in (None, "none"):
         raise NotImplementedError("pretrained encoder weights cannot be downloaded here; use load_state_dict()")
     if (encoder_depth, decoder_use_batchnorm, tuple(decoder_channels), decoder_attention_type, in_channels,

@@ -179,7 +179,8 @@ class UnetTorch(nn.Module):
 
     def __init__(self, encoder_name="resnet34", classes=1):
         super().__init__()
-        self.encoder = ResNetEncoder(encoder_name, dilated=False)
+        self.encoder = MobileNetV2Encoder(dilated=False) if encoder_name == "mobilenet_v2" else \
+            ResNetEncoder(encoder_name, dilated=False)
         self.decoder = UnetDecoder(self.encoder.out_channels)
         self.segmentation_head = nn.Sequential(nn.Conv2d(16, classes, 3, padding=1), nn.Identity(), nn.Identity())
         self.pool = nn.AdaptiveAvgPool2d(1)

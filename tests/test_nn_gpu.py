@@ -675,3 +675,83 @@ def test_mobilenet_decoder_and_stem_teacher_forced():
     e_stem = l2err(nchw(y), f0)
     print("MBV2 decoder:", e_fwd, e_last, e_high, bad[:6], "stem", e_stem)
     assert e_fwd < 3e-2 and e_last < 0.3 and e_high < 0.3 and not bad and e_stem < 1e-2
+
+
+def test_unet_mobilenet_v2_vs_oracle():
+    """smp.Unet over the MobileNetV2 encoder (stride-32 last stage, five skip levels): decoder teacher-forced, key set,
+    whole-step loss and learning."""
+    from aadg_b200.nn import Unet
+    from aadg_b200.synth import vessel_batch
+    from oracle.segnet_torch import UnetTorch
+    torch.manual_seed(4)
+    ref = UnetTorch("mobilenet_v2", 1).cuda().train()
+    net = Unet(encoder_name="mobilenet_v2", encoder_weights=None, in_channels=3, classes=1)
+    net.load_state_dict(ref.state_dict())
+    assert set(net.state_dict()) == set(ref.state_dict())
+    imgs, masks = vessel_batch(4, 128, 128, seed=10)
+    x = (torch.from_numpy(imgs).cuda().permute(0, 3, 1, 2).float() / 127.5 - 1.0).contiguous()
+    target = (torch.from_numpy(masks).cuda() != 0).float().unsqueeze(1).contiguous()
+    with torch.no_grad():
+        feats = ref.encoder(x)
+    assert [f.shape[1] for f in feats] == [3, 16, 24, 32, 96, 1280] and feats[-1].shape[-1] == 4
+    fb = [nhwc(f).to(BF) for f in feats[1:]]
+    fr = [None] + [nchw(f).requires_grad_(True) for f in fb]
+    want = ref.decoder(*fr)
+    got = net.decoder.forward(fb, True)
+    assert l2err(nchw(got), want) < 3e-2, l2err(nchw(got), want)
+    dy = torch.randn_like(want).to(BF)
+    want.backward(dy.float())
+    net.store.zero_grad()
+    d_last, d_skips = net.decoder.backward(nhwc(dy).to(BF))
+    assert l2err(nchw(d_last), fr[5].grad) < 0.3
+    for i, ds in enumerate(d_skips):
+        assert l2err(nchw(ds), fr[i + 1].grad) < 0.3, i
+    ref.zero_grad()
+    masks_r, pooled = ref(x)
+    loss = F.binary_cross_entropy(torch.sigmoid(masks_r), target)
+    net.store.zero_grad()
+    out = net.loss_step(x, target)
+    assert abs(out["loss"].item() - loss.item()) <= 2e-2 * abs(loss.item()), (out["loss"].item(), loss.item())
+    first = out["loss"].item()
+    for _ in range(8):
+        net.store.zero_grad()
+        out = net.loss_step(x, target)
+        net.store.adam_step(1e-3)
+    assert out["loss"].item() < first
+
+
+def test_validate_matches_reference_formulas():
+    """host/validate.py (search_dg.py:219-275): Dice and HD95 meters equal the oracle formulas evaluated on the engine's
+    own logits (torchmetrics samplewise F1, medpy hd95 with the 100-for-empty rule)."""
+    from aadg_b200.host.validate import validate
+    from oracle import hd95 as OH
+    from oracle.segnet_torch import f1_samplewise
+    ref, net, x, target = _pair("resnet18", 2, 64, 6, seed=7)
+    for _ in range(12):                           # a few steps so that some predictions cross the 0.75 threshold
+        net.store.zero_grad()
+        net.loss_step(x, target)
+        net.store.adam_step(3e-3)
+    batches = [(x[:4], target[:4]), (x[4:], target[4:])]
+    got = validate(net, batches)
+    assert net.training
+    net.eval()
+    dsc = [[], []]
+    hd = [[], []]
+    weights = []
+    for xb, tb in batches:
+        logits, _ = net(xb)
+        prob = torch.sigmoid(logits)
+        hard = (logits > np.log(3.0)).cpu().numpy()
+        weights.append(len(xb))
+        for k in range(2):
+            dsc[k].append(f1_samplewise(prob[:, k], tb[:, k], thr=0.75).item())
+            tot = 0.0
+            for i in range(len(xb)):
+                tot += 100.0 if hard[i, k].sum() == 0 else OH.hd95(hard[i, k], tb[i, k].cpu().numpy() > 0.5)
+            hd[k].append(tot / len(xb))
+    net.train()
+    for k in range(2):
+        want_d = np.average(dsc[k], weights=weights)
+        want_h = np.average(hd[k], weights=weights)
+        assert abs(got["dsc"][k] - want_d) <= 1e-6, (k, got["dsc"], want_d)
+        assert abs(got["hd"][k] - want_h) <= 1e-9 * max(1.0, want_h), (k, got["hd"], want_h)
