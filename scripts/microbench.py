@@ -50,12 +50,12 @@ def timeit(fn, iters, flush=None):
     return float(np.median(ms))
 
 
-def bench_aug():
+def bench_aug(batches=(8, 16, 32, 64, 128, 256, 512)):
     pk = peak()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     parsed = parse_policies(random_policies(seed=1023), Cfg)
     h = w = 512
-    for n_out in (8, 16, 32, 64, 128, 256, 512):
+    for n_out in batches:
         s = max(1, n_out // 6)
         imgs, masks = fundus_batch(s, h, w, seed=7)
         rows, _ = D.philox_rows(parsed, s, w, h, w, (1, 1.5), seed=1, scale_crop=False)
@@ -104,6 +104,7 @@ if __name__ == "__main__":
     args = sys.argv[1:]
     max_n = int(args[args.index("--max-n") + 1]) if "--max-n" in args else 65536
     if not args or "aug" in args:
-        bench_aug()
+        bench_aug(tuple(int(v) for v in args[args.index("--batches") + 1].split(",")) if "--batches" in args
+                  else (8, 16, 32, 64, 128, 256, 512))
     if not args or "sinkhorn" in args:
         bench_sinkhorn(max_n)
