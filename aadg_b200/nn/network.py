@@ -195,6 +195,56 @@ class BatchNorm:
         self.saved = None
 
 
+# ---------------------------------------------------------------------------------------------------
+# pixel packing for 16 / 32-channel 3x3 convolutions on wide maps
+# ---------------------------------------------------------------------------------------------------
+# A [N,H,W,16] tensor has 32-byte pixel rows: the TMA moves one short row per pixel and the tensor cores see K = 16.
+# Viewing P = 64 / Cin consecutive pixels as ONE 64-"channel" pixel ([N,H,W/P,64], the same memory) turns the layer
+# into a 64 -> P*Cout 3x3 convolution on a W/P-wide map whose weights are the original taps scattered into P x P
+# blocks: macro tap (dy, T) holds w[dy, dx] at block (b, a) iff dx = P*T + a - b is a real tap (-1, 0, 1).  Full
+# 128-byte rows, the halo-reuse kernels apply, and the 16x arithmetic inflation is free on idle tensor cores.
+PACK_MIN_W = int(os.environ.get("AADG_PACK_MIN_W", "65"))    # packed width from which the halo kernels pay off
+
+
+class PackedTaps:
+    """index maps between w [9, Co, Ci] and its packed expansion W4 [9, P*Co, P*Ci] (built once per layer)"""
+
+    def __init__(self, cout, cin, P, device):
+        src = np.full((3, 3, P, cout, P, cin), -1, np.int64)          # [dy, T, b, co, a, ci] -> flat index into w
+        base = np.arange(9 * cout * cin, dtype=np.int64).reshape(3, 3, cout, cin)   # [dy, dx, co, ci]
+        for T in (-1, 0, 1):
+            for a in range(P):
+                for b in range(P):
+                    dx = P * T + a - b
+                    if -1 <= dx <= 1:
+                        src[:, T + 1, b, :, a, :] = base[:, dx + 1]
+        src = src.reshape(-1)
+        self.P, self.cout, self.cin = P, cout, cin
+        self.shape = (9, P * cout, P * cin)
+        valid = np.nonzero(src >= 0)[0]
+        self.valid = torch.from_numpy(valid).to(device)                # positions of W4 that hold a real tap
+        self.src = torch.from_numpy(src[valid]).to(device)             # ... and the w element each one copies
+        # transposed expansion for the data gradient: [9, P*Ci, P*Co]
+        perm = np.arange(src.size, dtype=np.int64).reshape(9, P * cout, P * cin).transpose(0, 2, 1).reshape(-1)
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(perm.size)
+        self.valid_t = torch.from_numpy(inv[valid]).to(device)
+
+    def expand(self, w_bf16):
+        out = torch.zeros(self.shape, dtype=BF16, device=w_bf16.device)
+        out.view(-1)[self.valid] = w_bf16.reshape(-1)[self.src]
+        return out
+
+    def expand_t(self, w_bf16):
+        out = torch.zeros((9, self.shape[2], self.shape[1]), dtype=BF16, device=w_bf16.device)
+        out.view(-1)[self.valid_t] = w_bf16.reshape(-1)[self.src]
+        return out
+
+    def fold_grad(self, dw4, dw):
+        """dw [9, Co, Ci] (fp32, accumulated) += the real taps scattered over dW4"""
+        dw.view(-1).index_add_(0, self.src, dw4.reshape(-1)[self.valid])
+
+
 class ConvBN:
     """Conv2d(bias=False) -> BatchNorm2d -> [+ residual] -> [ReLU] -> [Dropout(0.5)]"""
 
@@ -207,16 +257,48 @@ class ConvBN:
                            lambda s: to_taps(init((cout, cin, k, k))))
         self.bn = BatchNorm(store, bn_name, cout)
         self.need_dgrad = need_dgrad
+        self.packed = None        # PackedTaps when the layer qualifies (decided at the first forward)
 
     def out_hw(self, h, w):
         return C.out_size(h, w, self.k, self.k, self.stride, self.pad, self.dil)
+
+    def _pack_factor(self, x):
+        """P > 1 when this call runs pixel-packed: 3x3 / stride 1 / pad 1 / dilation 1, 16 or 32 dense input channels"""
+        if (self.k, self.stride, self.pad, self.dil) != (3, 1, 1, 1) or self.cin not in (16, 32):
+            return 0
+        P = 64 // self.cin
+        w = x.shape[2]
+        if x.stride(2) != self.cin or not x.is_contiguous() or w % P or w // P < PACK_MIN_W or P * self.cout > 64:
+            return 0
+        return P
+
+    def _fprop_packed(self, x, P, fused):
+        n, h, w, _ = x.shape
+        if self.packed is None:
+            self.packed = PackedTaps(self.cout, self.cin, P, x.device)
+        pre = torch.empty((n, h, w, self.cout), dtype=BF16, device=x.device)
+        stats = None
+        if fused:
+            stats = (torch.zeros(P * self.cout, device=x.device), torch.zeros(P * self.cout, device=x.device))
+        C.fprop(x.view(n, h, w // P, 64), self.packed.expand(self.w.bf16), 3, 3, 1, 1, 1,
+                out=pre.view(n, h, w // P, P * self.cout), stats=stats,
+                flops=2.0 * n * h * w * self.cout * self.cin * 9)      # the layer's own FLOPs, not the packed problem's
+        if fused:      # packed channel (b, co) -> co
+            s0, s1 = self.bn.stats_buffers()
+            s0.add_(stats[0].view(P, self.cout).sum(0))
+            s1.add_(stats[1].view(P, self.cout).sum(0))
+        return pre
 
     def forward(self, x, training, out=None, res=None, dropout_seed=None):
         n, h, w, _ = x.shape
         ho, wo = self.out_hw(h, w)
         fused = training and FUSE_BN_STATS
-        pre = C.fprop(x, self.w.bf16, self.k, self.k, self.stride, self.pad, self.dil,
-                      stats=self.bn.stats_buffers() if fused else None)
+        P = self._pack_factor(x)
+        if P:
+            pre = self._fprop_packed(x, P, fused)
+        else:
+            pre = C.fprop(x, self.w.bf16, self.k, self.k, self.stride, self.pad, self.dil,
+                          stats=self.bn.stats_buffers() if fused else None)
         if out is None:
             out = torch.empty((n, ho, wo, self.cout), dtype=BF16, device=x.device)
         # backward needs the ReLU mask: recomputed from `pre` when there is no residual, otherwise kept as one
@@ -226,19 +308,33 @@ class ConvBN:
             bits = torch.empty((pre.numel() // 8,), dtype=torch.uint8, device=x.device)
         self.bn.forward(pre, out, training, res=res, relu=self.relu, dropout_seed=dropout_seed, relu_bits=bits,
                         have_stats=fused, relu6=self.relu6)
-        self.ctx = (x, pre, bits, dropout_seed) if training else None
+        self.ctx = (x, pre, bits, dropout_seed, P) if training else None
         return out
 
     def backward(self, dy, dx=None, accumulate=False, want_dres=False, dres=None, dres_accumulate=False, dy2=None):
         """returns dx (or None when the input needs no gradient); with want_dres also the residual gradient.
         The incoming gradient is dy (+ dy2 when given)."""
-        x, pre, y, seed = self.ctx
+        x, pre, y, seed, P = self.ctx
         self.ctx = None
         dpre = torch.empty_like(pre)
         if want_dres and dres is None:
             dres = torch.empty(pre.shape, dtype=BF16, device=pre.device)
         self.bn.backward(dy, pre, y, dpre, relu=self.relu, dropout_seed=seed, dres=dres if want_dres else None,
                          dres_accumulate=dres_accumulate, dy2=dy2, relu6=self.relu6)
+        if P and (dx is None or (dx.stride(2) == self.cin and not accumulate)):
+            n, h, w, _ = x.shape
+            x4, d4 = x.view(n, h, w // P, 64), dpre.view(n, h, w // P, P * self.cout)
+            real_flops = 2.0 * n * h * w * self.cout * self.cin * 9
+            dw4 = C.wgrad(x4, d4, 3, 3, 1, 1, 1, flops=real_flops)
+            self.packed.fold_grad(dw4, self.w.grad)
+            if self.need_dgrad:
+                if dx is None:
+                    dx = torch.empty(x.shape, dtype=BF16, device=x.device)
+                C.dgrad(d4, self.packed.expand_t(self.w.bf16), 3, 3, 1, 1, 1, (h, w // P), out=dx.view(n, h, w // P, 64),
+                        flops=real_flops)
+            else:
+                dx = None
+            return (dx, dres) if want_dres else dx
         C.wgrad(x, dpre, self.k, self.k, self.stride, self.pad, self.dil, out=self.w.grad)
         if self.need_dgrad:
             dx = C.dgrad(dpre, self.w.bf16_t, self.k, self.k, self.stride, self.pad, self.dil, x.shape[1:3], out=dx,

@@ -8,7 +8,8 @@ import torch
 from .. import _lib
 
 
-# bench.py sets TIMING = [] to bracket every launch with CUDA events: (kind, algorithmic flops, start, end)
+# bench.py sets TIMING = [] to bracket every launch with CUDA events: (kind, algorithmic flops, start, end, geometry);
+# `flops=` lets a caller that runs a reformulated problem (pixel packing) report the ORIGINAL layer's FLOPs
 TIMING = None
 
 
@@ -42,7 +43,7 @@ def out_size(h, w, r, s, stride, pad, dil):
     return ((h + 2 * pad - dil * (r - 1) - 1) // stride + 1, (w + 2 * pad - dil * (s - 1) - 1) // stride + 1)
 
 
-def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False, stats=None):
+def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False, stats=None, flops=None):
     """x [N,H,W,Cin] bf16, wgt [R*S,Cout,Cin] bf16 -> y [N,Ho,Wo,Cout] bf16 (or written into `out`).
     stats = (sum, sumsq) fp32 [Cout] tensors (zeroed by the caller): the batch-norm statistics of y are accumulated
     in the convolution's epilogue instead of a separate pass over y."""
@@ -54,7 +55,7 @@ def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False, stat
         out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
     _, oh, ow, oc, ldy = _nhwc(out, "out")
     assert (oh, ow, oc) == (ho, wo, cout)
-    with torch.cuda.device(x.device), _timed("fprop", 2.0 * n * ho * wo * cout * cin * r * s,
+    with torch.cuda.device(x.device), _timed("fprop", flops or 2.0 * n * ho * wo * cout * cin * r * s,
                                               (n, h, w, cin, ho, wo, cout, r, stride, dil)):
         if stats is not None:
             assert not accumulate
@@ -70,7 +71,7 @@ def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False, stat
     return out
 
 
-def dgrad(dy, wgt_t, r, s, stride, pad, dil, in_hw, out=None, accumulate=False):
+def dgrad(dy, wgt_t, r, s, stride, pad, dil, in_hw, out=None, accumulate=False, flops=None):
     """dy [N,Ho,Wo,Cout] bf16, wgt_t [R*S,Cin,Cout] bf16 -> dx [N,H,W,Cin] bf16."""
     n, ho, wo, cout, lddy = _nhwc(dy, "dy")
     cin = wgt_t.shape[1]
@@ -80,7 +81,7 @@ def dgrad(dy, wgt_t, r, s, stride, pad, dil, in_hw, out=None, accumulate=False):
         out = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=dy.device)
     _, xh, xw, xc, lddx = _nhwc(out, "out")
     assert (xh, xw, xc) == (h, w, cin)
-    with torch.cuda.device(dy.device), _timed("dgrad", 2.0 * n * ho * wo * cout * cin * r * s,
+    with torch.cuda.device(dy.device), _timed("dgrad", flops or 2.0 * n * ho * wo * cout * cin * r * s,
                                                (n, h, w, cin, ho, wo, cout, r, stride, dil)):
         _lib.check(_lib.lib().aadg_conv_dgrad_bf16(dy.data_ptr(), n, ho, wo, cout, lddy, wgt_t.data_ptr(), cin, r, s,
                                                    stride, pad, dil, out.data_ptr(), h, w, lddx, 0, int(accumulate),
@@ -88,14 +89,14 @@ def dgrad(dy, wgt_t, r, s, stride, pad, dil, in_hw, out=None, accumulate=False):
     return out
 
 
-def wgrad(x, dy, r, s, stride, pad, dil, out=None):
+def wgrad(x, dy, r, s, stride, pad, dil, out=None, flops=None):
     """x [N,H,W,Cin], dy [N,Ho,Wo,Cout] bf16 -> dw [R*S,Cout,Cin] fp32 (accumulated into `out`)."""
     n, h, w, cin, ldx = _nhwc(x, "x")
     _, ho, wo, cout, lddy = _nhwc(dy, "dy")
     if out is None:
         out = torch.zeros((r * s, cout, cin), dtype=torch.float32, device=x.device)
     assert out.shape == (r * s, cout, cin) and out.dtype == torch.float32 and out.is_contiguous()
-    with torch.cuda.device(x.device), _timed("wgrad", 2.0 * n * ho * wo * cout * cin * r * s,
+    with torch.cuda.device(x.device), _timed("wgrad", flops or 2.0 * n * ho * wo * cout * cin * r * s,
                                               (n, h, w, cin, ho, wo, cout, r, stride, dil)):
         _lib.check(_lib.lib().aadg_conv_wgrad_bf16(x.data_ptr(), n, h, w, cin, ldx, dy.data_ptr(), ho, wo, cout, lddy,
                                                    r, s, stride, pad, dil, out.data_ptr(), _lib.stream_ptr()))

@@ -755,3 +755,37 @@ def test_validate_matches_reference_formulas():
         want_h = np.average(hd[k], weights=weights)
         assert abs(got["dsc"][k] - want_d) <= 1e-6, (k, got["dsc"], want_d)
         assert abs(got["hd"][k] - want_h) <= 1e-9 * max(1.0, want_h), (k, got["hd"], want_h)
+
+
+@pytest.mark.parametrize("cin,cout,w", [(16, 16, 512), (32, 16, 264), (32, 32, 64)])
+def test_pixel_packed_small_channel_conv_matches_plain(cin, cout, w):
+    """ConvBN runs 16/32-channel 3x3 layers pixel-packed (P pixels x Cin channels = one 64-channel row, block-scattered
+    weights): forward, batch-norm statistics, data and weight gradients equal the plain path on the same tensors."""
+    import aadg_b200.nn.network as NW
+    torch.manual_seed(cin + cout)
+    n, h = 2, 9
+    x = torch.randn(n, h, w, cin, device="cuda").to(BF)
+    dy = torch.randn(n, h, w, cout, device="cuda").to(BF)
+    results = []
+    for min_w in (1, 1 << 30):                      # packed, then plain
+        old = NW.PACK_MIN_W
+        NW.PACK_MIN_W = min_w
+        try:
+            torch.manual_seed(5)
+            store = NW.ParamStore(torch.device("cuda"))
+            layer = NW.ConvBN(store, "c", "b", cin, cout, 3, 1, 1, 1)
+            store.finalize()
+            y = layer.forward(x, True)
+            assert (layer.ctx[4] > 0) == (min_w == 1)
+            stats = layer.bn.saved.clone()
+            store.zero_grad()
+            dx = layer.backward(dy)
+            results.append((y.float(), stats, dx.float(), layer.w.grad.clone(), layer.bn.gamma.grad.clone()))
+        finally:
+            NW.PACK_MIN_W = old
+    (y1, s1, dx1, dw1, dg1), (y0, s0, dx0, dw0, dg0) = results
+    rel_close(y1, y0, 1e-2, "packed fwd")
+    assert torch.allclose(s1[:2], s0[:2], rtol=1e-3, atol=1e-3), "mean / invstd"
+    rel_close(dx1, dx0, 2e-2, "packed dgrad")
+    rel_close(dw1, dw0, 5e-3, "packed wgrad")
+    rel_close(dg1, dg0, 5e-3, "packed dgamma")
