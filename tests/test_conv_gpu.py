@@ -142,3 +142,26 @@ def test_fprop_fused_statistics(conv, case):
     tol = 1e-4 * (yf.abs().sum(0) + 1e-3)
     assert ((ssum.double() - want_sum).abs() <= tol).all(), (case, (ssum.double() - want_sum).abs().max().item())
     assert ((ssq.double() - want_sq).abs() <= 1e-4 * want_sq + 1e-6).all(), case
+
+
+def test_halo_kernel_channel_slices_and_accumulate(conv):
+    """the halo-reuse kernels (rows of 128 pixels, Cin <= 64) with strided channel slices on both sides and the
+    reduce-add epilogue; data gradient accumulated into an existing tensor"""
+    x_full = torch.randn(2, 12, 200, 96, device="cuda").bfloat16()
+    x = x_full[..., 32:96]
+    _, wt = rand_case(1, 1, 1, 64, 48, 3, 3, seed=6)
+    out_full = torch.zeros(2, 12, 200, 128, device="cuda", dtype=torch.bfloat16)
+    out = out_full[..., 64:112]
+    conv.fprop(x, to_taps(wt), 3, 3, 1, 1, 1, out=out)
+    want = ref_conv(x.contiguous(), wt, 1, 1, 1)
+    close(out, want, "halo slice")
+    assert out_full[..., :64].abs().max() == 0 and out_full[..., 112:].abs().max() == 0
+    conv.fprop(x, to_taps(wt), 3, 3, 1, 1, 1, out=out, accumulate=True)
+    close(out, 2 * want, "halo accumulate")
+    dy = torch.randn(2, 12, 200, 48, device="cuda").bfloat16()
+    xr = x.contiguous().float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.conv2d(xr, wt.float(), padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    base = torch.randn(2, 12, 200, 64, device="cuda").bfloat16()
+    got = base.clone()
+    conv.dgrad(dy, to_taps_t(wt), 3, 3, 1, 1, 1, (12, 200), out=got, accumulate=True)
+    close(got, base.float() + xr.grad.permute(0, 2, 3, 1), "halo dgrad accumulate")
