@@ -128,6 +128,37 @@ class SearchEngine:
         return dict(seg_loss=out["loss"], dis_loss=dis_loss.detach(), dice=dice_from_counts(out["counts"]),
                     n_images=images.shape[0])
 
+    def pretrain_step(self, src_images, src_masks, src_domains):
+        """One step of the warm-up phase (`pretrain`, search_dg.py:22-100): the un-augmented `sample['image']` (only
+        DGRandomScaleCrop / Normalize_dg / ToTensor), segmentation step, live discriminator step on the detached pooled
+        features; no policies, no rewards.  Same argument / return shapes as `step`."""
+        s, h, w, _ = src_images.shape
+        _, raws = D.philox_rows([[[]]], s, w, h, self.crop or w, self.scale_range, self.seed + 1000003 * self.rank,
+                                self.epoch, self.step_idx, scale_crop=self.crop is not None)
+        dc = np.stack([D.soft_label(self._soft_rng, int(d), self.n_domains) for d in src_domains]).astype(np.float32)
+        dc_dev = torch.from_numpy(dc).to(src_images.device, non_blocking=True)
+        if self.crop is not None:
+            images, labels = U8.policy_scale_crop_normalize(src_images, src_masks, raws, self.crop, self.dataset)
+        else:
+            images, labels = U8.policy_normalize(src_images, src_masks, raws, dataset=self.dataset)
+        model = self.model
+        model.store.zero_grad()
+        out = model.loss_step(images, labels)
+        dis_loss = self.dis_criterion(self.discriminator(out["pooled"].detach(), momentum=False), dc_dev)
+        if self.world > 1:
+            average_(model.store.grads)
+        model.store.adam_step(self.lr, weight_decay=self.wd)
+        self.dis_optimizer.zero_grad()
+        dis_loss.backward()
+        if self.world > 1:
+            for p in self.discriminator.parameters():
+                if p.grad is not None:
+                    average_(p.grad)
+        self.dis_optimizer.step()
+        self.step_idx += 1
+        return dict(seg_loss=out["loss"], dis_loss=dis_loss.detach(), dice=dice_from_counts(out["counts"]),
+                    n_images=images.shape[0])
+
     def normalized_rewards(self):
         """search_dg.py:214"""
         return SK.normalize_rewards(self.rewards)

@@ -56,3 +56,22 @@ def test_step_rewards_match_oracle_on_the_same_features():
     want, _ = OS.diversity_rewards(captured["feat"], captured["dc"], 6)
     assert np.allclose(eng.rewards.cpu().numpy(), want, rtol=1e-4)
     assert captured["feat"].shape == (72, 128) and captured["dc"].shape == (72, 3)
+
+
+def test_pretrain_step_learns_without_policies():
+    """warm-up phase (search_dg.py pretrain): un-augmented images through scale/crop + normalise, segmentation and
+    discriminator steps; the loss falls over a few steps on one batch"""
+    from aadg_b200.host.search import SearchEngine
+    from aadg_b200.nn import DeepLabV3Plus
+    from aadg_b200.synth import fundus_batch
+    model = DeepLabV3Plus(encoder_name="resnet18", classes=2)
+    eng = SearchEngine(model, n_domains=3, M=6, crop=64)
+    imgs, masks = fundus_batch(6, 64, 64, seed=4)
+    x, m = torch.from_numpy(imgs).cuda(), torch.from_numpy(masks).cuda()
+    losses = []
+    for _ in range(8):
+        out = eng.pretrain_step(x, m, [0, 1, 2, 0, 1, 2])
+        assert out["n_images"] == 6
+        losses.append(float(out["seg_loss"]))
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    assert float(eng.rewards.abs().sum()) == 0.0
