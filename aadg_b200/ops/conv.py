@@ -55,7 +55,7 @@ def fprop(x, wgt, r, s, stride=1, pad=0, dil=1, out=None, accumulate=False, stat
         out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
     _, oh, ow, oc, ldy = _nhwc(out, "out")
     assert (oh, ow, oc) == (ho, wo, cout)
-    with torch.cuda.device(x.device), _timed("fprop", flops or 2.0 * n * ho * wo * cout * cin * r * s,
+    with _lib.on_device(x.device), _timed("fprop", flops or 2.0 * n * ho * wo * cout * cin * r * s,
                                               (n, h, w, cin, ho, wo, cout, r, stride, dil)):
         if stats is not None:
             assert not accumulate
@@ -81,7 +81,7 @@ def dgrad(dy, wgt_t, r, s, stride, pad, dil, in_hw, out=None, accumulate=False, 
         out = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=dy.device)
     _, xh, xw, xc, lddx = _nhwc(out, "out")
     assert (xh, xw, xc) == (h, w, cin)
-    with torch.cuda.device(dy.device), _timed("dgrad", flops or 2.0 * n * ho * wo * cout * cin * r * s,
+    with _lib.on_device(dy.device), _timed("dgrad", flops or 2.0 * n * ho * wo * cout * cin * r * s,
                                                (n, h, w, cin, ho, wo, cout, r, stride, dil)):
         _lib.check(_lib.lib().aadg_conv_dgrad_bf16(dy.data_ptr(), n, ho, wo, cout, lddy, wgt_t.data_ptr(), cin, r, s,
                                                    stride, pad, dil, out.data_ptr(), h, w, lddx, 0, int(accumulate),
@@ -96,7 +96,7 @@ def wgrad(x, dy, r, s, stride, pad, dil, out=None, flops=None):
     if out is None:
         out = torch.zeros((r * s, cout, cin), dtype=torch.float32, device=x.device)
     assert out.shape == (r * s, cout, cin) and out.dtype == torch.float32 and out.is_contiguous()
-    with torch.cuda.device(x.device), _timed("wgrad", flops or 2.0 * n * ho * wo * cout * cin * r * s,
+    with _lib.on_device(x.device), _timed("wgrad", flops or 2.0 * n * ho * wo * cout * cin * r * s,
                                               (n, h, w, cin, ho, wo, cout, r, stride, dil)):
         _lib.check(_lib.lib().aadg_conv_wgrad_bf16(x.data_ptr(), n, h, w, cin, ldx, dy.data_ptr(), ho, wo, cout, lddy,
                                                    r, s, stride, pad, dil, out.data_ptr(), _lib.stream_ptr()))
