@@ -154,3 +154,39 @@ def test_resident_pools_replay_reference_sampling():
     import pytest
     with pytest.raises(IndexError):
         pools.gather(np.array([[5, 0, 0]]))
+
+
+def test_packed_taps_index_maps_on_cpu():
+    """pixel packing (nn/network.py PackedTaps): a 3x3 convolution on [N,H,W,Cin] equals the 3x3 convolution with the
+    block-scattered weights on the packed view [N,H,W/P,P*Cin]; the transposed expansion and the gradient fold agree
+    with autograd.  Pure index logic: runs on CPU tensors."""
+    import torch
+    import torch.nn.functional as F
+    from aadg_b200.nn.network import PackedTaps
+    for co, ci, P in ((16, 16, 4), (16, 32, 2), (32, 32, 2)):
+        pt = PackedTaps(co, ci, P, "cpu")
+        torch.manual_seed(co + ci)
+        w = torch.randn(9, co, ci).bfloat16()
+        W4 = pt.expand(w).float()
+        x = torch.randn(2, ci, 5, 3 * P)
+        y = F.conv2d(x, w.float().view(3, 3, co, ci).permute(2, 3, 0, 1), padding=1)
+        xp = x.permute(0, 2, 3, 1).reshape(2, 5, 3, P * ci).permute(0, 3, 1, 2)
+        yp = F.conv2d(xp, W4.view(3, 3, P * co, P * ci).permute(2, 3, 0, 1), padding=1)
+        back = yp.permute(0, 2, 3, 1).reshape(2, 5, 3 * P, co).permute(0, 3, 1, 2)
+        assert torch.allclose(y, back, atol=1e-4), (co, ci, P)
+        assert torch.equal(pt.expand_t(w).float(), W4.transpose(1, 2).contiguous())
+        g = torch.randn(pt.shape)
+        dw = torch.zeros(9, co, ci)
+        pt.fold_grad(g, dw)
+        wr = w.float().clone().requires_grad_(True)
+        w4r = torch.zeros(pt.shape).view(-1).index_put((pt.valid,), wr.view(-1)[pt.src]).view(pt.shape)
+        (w4r * g).sum().backward()
+        assert torch.allclose(dw, wr.grad, atol=1e-5)
+
+
+def test_validate_average_meter():
+    from aadg_b200.host.validate import AverageMeter
+    m = AverageMeter()
+    m.update(2.0, 4)
+    m.update(5.0, 2)
+    assert abs(m.avg - 3.0) < 1e-12
