@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(const bf16* __restrict
                                                           unsigned long long seed, unsigned char* relu_bits) {
   const int G = C >> 3, g = threadIdx.x;
   if (g >= G) return;
+  if (flags & 64) seed = *reinterpret_cast<const unsigned long long*>(seed);   // seed kept in device memory (CUDA graphs)
   const V8 sc = ld8f(scale + g * 8), sh = ld8f(shift + g * 8);
   const long long step = (long long)gridDim.x * blockDim.y;
   for (long long p0 = (long long)blockIdx.x * blockDim.y + threadIdx.y; p0 < P; p0 += BN_U * step) {
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const bf16* __res
                                                                unsigned long long seed, float* dgamma, float* dbeta) {
   const int G = C >> 3, g = threadIdx.x;
   float a0[8] = {}, a1[8] = {};
+  if (flags & 64) seed = *reinterpret_cast<const unsigned long long*>(seed);
   if (g < G) {
     const V8 m = ld8f(mean + g * 8), is = ld8f(invstd + g * 8);
     V8 sc = {}, sh = {};
@@ -325,10 +327,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const bf16* __rest
                                                               const float* beta, const float* dgamma, const float* dbeta,
                                                               long long P, int C, int flags, unsigned long long seed,
                                                               bf16* __restrict__ dx, int lddx, bf16* dres, int lddr,
-                                                              int dres_accumulate) {
+                                                              int dres_accumulate, float inv_count) {
   const int G = C >> 3, g = threadIdx.x;
   if (g >= G) return;
-  const float invP = 1.f / (float)P;
+  if (flags & 64) seed = *reinterpret_cast<const unsigned long long*>(seed);
+  const float invP = inv_count;      // 1 / (pixels the statistics were taken over): local P, or the global count (SyncBN)
   // dx = sc*g + kk + bb*(x - mean):  sc = gamma*invstd, bb = -sc*invstd*dgamma/P, kk = -sc*dbeta/P
   const V8 m = ld8f(mean + g * 8);
   V8 sc, sh = {}, bb, kk;
@@ -971,6 +974,25 @@ __global__ void adam_kernel(float* p, const float* g, float* m, float* v, long l
     p[i] = pi - (lr / bc1) * (mi / denom);
   }
 }
+// the same update with (lr, beta1, beta2, eps, weight_decay, grad_scale) and the 1-based step count read from device
+// memory, so that a captured CUDA graph replays it unchanged while the host advances the counter / changes the rate;
+// grad_scale (1 / world size after a summing all-reduce) is folded into the gradient load
+__global__ void adam_dev_kernel(float* p, const float* g, float* m, float* v, long long n, const float* hyper,
+                                const long long* step_ptr) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gs = hyper[5];
+  const float step = (float)*step_ptr;
+  const float bc1 = 1.f - powf(b1, step), bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gs;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
 // fp32 master weights [taps][Cout][Cin] -> bf16 copy and bf16 transposed copy [taps][Cin][Cout]
 struct WeightDesc { long long off_master, off_bf16, off_bf16_t; int taps, cout, cin, pad_; };
 __global__ void weight_prep_kernel(const float* master, bf16* wb, bf16* wbt, const WeightDesc* descs) {
@@ -1095,17 +1117,20 @@ int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift
   return check_launch("bn_apply");
 }
 
+// phase bit 1 = reduce (dgamma / dbeta accumulate), bit 2 = apply; inv_count <= 0 -> 1 / pixels
 static int bn_backward_impl(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const void* y,
                             int ldy, const float* mean, const float* invstd, const float* gamma, const float* shift,
                             long long pixels, int c, int flags, unsigned long long seed, float* dgamma, float* dbeta,
-                            void* dx, int lddx, void* dres, int lddr, int dres_accumulate, void* stream) {
+                            void* dx, int lddx, void* dres, int lddr, int dres_accumulate, void* stream, int phase = 3,
+                            float inv_count = 0.f) {
   NN_REQ_C(c);
   AADG_REQUIRE(pixels > 0 && pixels < (1ll << 31), "bad pixel count");
   cudaStream_t st = (cudaStream_t)stream;
-  if (!(flags & 16)) {     // flag 16: dgamma / dbeta are accumulated into (the caller zeroed its gradient buffer)
+  if (!(flags & 16) && (phase & 1)) {     // flag 16: dgamma / dbeta are accumulated into (the caller zeroed its gradient buffer)
     AADG_CUDA_TRY(cudaMemsetAsync(dgamma, 0, sizeof(float) * c, st));
     AADG_CUDA_TRY(cudaMemsetAsync(dbeta, 0, sizeof(float) * c, st));
   }
+  if (!(inv_count > 0.f)) inv_count = 1.f / (float)pixels;
   const dim3 blk = reduce_block(c);
   AADG_REQUIRE(!(flags & 1) || (flags & 4) || y, "ReLU mask needs y / the bit mask (or flag 4 to recompute it from x)");
   AADG_REQUIRE(!(flags & 4) || shift, "flag 4 needs the forward shift vector");
@@ -1113,13 +1138,16 @@ static int bn_backward_impl(const void* dy, int lddy, const void* dy2, int lddy2
   const int grid = stream_blocks(pixels, blk, 2);
 #define AADG_BN_BWD(MASK, DY2)                                                                                         \
   {                                                                                                                    \
-    bn_bwd_reduce_kernel<MASK, DY2><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)dy2, lddy2, (const bf16*)x, \
-                                                          ldx, (const bf16*)y, ldy, mean, invstd, gamma, shift, pixels, c, \
-                                                          flags, seed, dgamma, dbeta);                                  \
-    bn_bwd_apply_kernel<MASK, DY2><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)dy2, lddy2, (const bf16*)x,  \
-                                                         ldx, (const bf16*)y, ldy, mean, invstd, gamma, shift, dgamma,   \
-                                                         dbeta, pixels, c, flags, seed, (bf16*)dx, lddx, (bf16*)dres,    \
-                                                         lddr, dres_accumulate);                                        \
+    if (phase & 1)                                                                                                     \
+      bn_bwd_reduce_kernel<MASK, DY2><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)dy2, lddy2,             \
+                                                            (const bf16*)x, ldx, (const bf16*)y, ldy, mean, invstd,     \
+                                                            gamma, shift, pixels, c, flags, seed, dgamma, dbeta);       \
+    if (phase & 2)                                                                                                     \
+      bn_bwd_apply_kernel<MASK, DY2><<<grid, blk, 0, st>>>((const bf16*)dy, lddy, (const bf16*)dy2, lddy2,              \
+                                                           (const bf16*)x, ldx, (const bf16*)y, ldy, mean, invstd,      \
+                                                           gamma, shift, dgamma, dbeta, pixels, c, flags, seed,         \
+                                                           (bf16*)dx, lddx, (bf16*)dres, lddr, dres_accumulate,         \
+                                                           inv_count);                                                  \
   }
   if (dy2) {
     if (mask == 4) AADG_BN_BWD(4, true) else if (mask == 8) AADG_BN_BWD(8, true) else if (mask == 1) AADG_BN_BWD(1, true) else AADG_BN_BWD(0, true)
@@ -1128,6 +1156,28 @@ static int bn_backward_impl(const void* dy, int lddy, const void* dy2, int lddy2
   }
 #undef AADG_BN_BWD
   return check_launch("bn_backward");
+}
+
+/* The two halves of the backward, for batch statistics shared across ranks (SyncBN): `reduce` ACCUMULATES this
+ * rank's sum(g * xhat) and sum(g) into dgamma_sum / dbeta_sum (zero them first); the caller all-reduces them; `apply`
+ * takes the global sums and inv_count = 1 / (global pixel count).  dy2 may be NULL. */
+int aadg_bn_backward_reduce(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const void* y,
+                            int ldy, const float* mean, const float* invstd, const float* gamma, const float* shift,
+                            long long pixels, int c, int flags, unsigned long long seed, float* dgamma_sum,
+                            float* dbeta_sum, void* stream) {
+  return bn_backward_impl(dy, lddy, dy2, dy2 ? lddy2 : 0, x, ldx, y, ldy, mean, invstd, gamma, shift, pixels, c, flags | 16,
+                          seed, dgamma_sum, dbeta_sum, nullptr, 0, nullptr, 0, 0, stream, 1);
+}
+
+int aadg_bn_backward_apply(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const void* y,
+                           int ldy, const float* mean, const float* invstd, const float* gamma, const float* shift,
+                           long long pixels, int c, int flags, unsigned long long seed, const float* dgamma_sum,
+                           const float* dbeta_sum, float inv_count, void* dx, int lddx, void* dres, int lddr,
+                           int dres_accumulate, void* stream) {
+  AADG_REQUIRE(inv_count > 0.f, "inv_count = 1 / (pixels behind the statistics) must be positive");
+  return bn_backward_impl(dy, lddy, dy2, dy2 ? lddy2 : 0, x, ldx, y, ldy, mean, invstd, gamma, shift, pixels, c, flags | 16,
+                          seed, (float*)dgamma_sum, (float*)dbeta_sum, dx, lddx, dres, lddr, dres_accumulate, stream, 2,
+                          inv_count);
 }
 
 int aadg_bn_backward(const void* dy, int lddy, const void* x, int ldx, const void* y, int ldy, const float* mean,
@@ -1278,6 +1328,13 @@ int aadg_adam_step(float* params, const float* grads, float* exp_avg, float* exp
   adam_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, count, lr, beta1,
                                                                 beta2, eps, bc1, bc2, weight_decay);
   return check_launch("adam");
+}
+
+int aadg_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count,
+                       const float* hyper, const long long* step, void* stream) {
+  AADG_REQUIRE(params && grads && exp_avg && exp_avg_sq && hyper && step, "null pointer");
+  adam_dev_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, count, hyper, step);
+  return check_launch("adam (device state)");
 }
 
 /* descs (device) int64x3 + int32x4 per weight: see WeightDesc */

@@ -110,6 +110,28 @@ class PolicyState:
         self.calls = [0] * m
 
 
+def replay_policy_call(row, policy, n_calls, src_index, width, height, py, npr):
+    """One `Policy.__call__` (data/policy.py:15-30) resolved into `row`: the CutMix-queue draw (only while the queue
+    holds <= 10 entries; `n_calls` = calls of this Policy object so far, this one included), the sub-policy choice and
+    the per-op draws, consumed from `py` (random.Random or the `random` module) and `npr` (RandomState or
+    `np.random`) in the reference's order."""
+    qlen = min(n_calls, 11)
+    if qlen <= 10:
+        py.choice(range(qlen))                        # pair = random.choice(self.queue)
+    sub = py.choice(policy)
+    row["src"] = src_index
+    row["n_ops"] = len(sub)
+    for k, (name, level) in enumerate(sub):
+        ux = uy = None
+        mirror = False
+        if name == "Cutout" and level_to_value(name, level) > 0.0:
+            ux = npr.uniform(width)
+            uy = npr.uniform(height)
+        elif name in GEOMETRIC:
+            mirror = py.random() > 0.5
+        resolve_op(row, k, name, level, width, height, ux, uy, mirror)
+
+
 def replay_sample(parsed_policies, src_index, width, height, crop, scale_range, py, npr, state,
                   scale_crop=True):
     """Rows for the M augmented copies of one source image, consuming `py` (random.Random) and
@@ -122,22 +144,7 @@ def replay_sample(parsed_policies, src_index, width, height, crop, scale_range, 
     tw = th = crop
     for j, policy in enumerate(parsed_policies):
         state.calls[j] += 1
-        qlen = min(state.calls[j], 11)
-        if qlen <= 10:
-            py.choice(range(qlen))                        # pair = random.choice(self.queue)
-        sub = py.choice(policy)
-        row = rows[j]
-        row["src"] = src_index
-        row["n_ops"] = len(sub)
-        for k, (name, level) in enumerate(sub):
-            ux = uy = None
-            mirror = False
-            if name == "Cutout" and level_to_value(name, level) > 0.0:
-                ux = npr.uniform(width)
-                uy = npr.uniform(height)
-            elif name in GEOMETRIC:
-                mirror = py.random() > 0.5
-            resolve_op(row, k, name, level, width, height, ux, uy, mirror)
+        replay_policy_call(rows[j], policy, state.calls[j], src_index, width, height, py, npr)
     raw = np.zeros(1, ROW_DTYPE)[0]
     raw["src"] = src_index
     if scale_crop:
@@ -168,6 +175,27 @@ def soft_label(py, domain, n_domains):
     return np.asarray(new, np.float32)
 
 
+class _UniformStream:
+    """`.random()` over a fixed array of uniforms (lets soft_label consume counter-based draws)"""
+
+    def __init__(self, values):
+        self.values, self.i = values, 0
+
+    def random(self):
+        v = float(self.values[self.i])
+        self.i += 1
+        return v
+
+
+def philox_soft_labels(domains, n_domains, seed, epoch=0, step=0, src_offset=0):
+    """ToTensor's random soft domain labels (data/transform.py:260-274) for source images src_offset.. of the global
+    batch, counter-based: keyed (seed, epoch, step, global source index), independent of how the batch is sharded."""
+    domains = [int(d) for d in domains]
+    ids = src_offset + np.arange(len(domains))
+    u = _uniforms((int(seed) ^ 0x50F7) & 0xFFFFFFFFFFFFFFFF, epoch, step, len(domains), (n_domains + 3) // 4, ids)
+    return np.stack([soft_label(_UniformStream(u[i]), d, n_domains) for i, d in enumerate(domains)])
+
+
 # ------------------------------------------------------------------------------------------------
 # production generator: Philox4x32-10, counter = (row, draw, step, epoch), key = seed
 # ------------------------------------------------------------------------------------------------
@@ -192,10 +220,12 @@ def philox4x32(counter, key):
     return np.stack(c, axis=-1).astype(np.uint32)
 
 
-def _uniforms(seed, epoch, step, n_rows, n_draws):
-    """float64 uniforms in [0,1) with 32 bits of entropy, shape [n_rows, n_draws*4]."""
+def _uniforms(seed, epoch, step, n_rows, n_draws, row_ids=None):
+    """float64 uniforms in [0,1) with 32 bits of entropy, shape [n_rows, n_draws*4]; row_ids = the counter value of
+    every row (default 0..n_rows-1)."""
     ctr = np.zeros((n_rows, n_draws, 4), np.uint32)
-    ctr[..., 0] = np.arange(n_rows, dtype=np.uint32)[:, None]
+    ids = np.arange(n_rows, dtype=np.uint32) if row_ids is None else np.asarray(row_ids, np.uint32)
+    ctr[..., 0] = ids[:, None]
     ctr[..., 1] = np.arange(n_draws, dtype=np.uint32)[None, :]
     ctr[..., 2] = np.uint32(step & 0xFFFFFFFF)
     ctr[..., 3] = np.uint32(epoch & 0xFFFFFFFF)
@@ -207,13 +237,20 @@ def _uniforms(seed, epoch, step, n_rows, n_draws):
 
 
 def philox_rows(parsed_policies, n_src, width, height, crop, scale_range, seed, epoch=0, step=0,
-                scale_crop=True):
+                scale_crop=True, src_offset=0, n_src_total=None):
     """Rows for n_src source images x M policies, row index = s*M + j (the reference's collate
     order, data/transform.py:323-340).  Same distributions as the reference's draws, different
-    (counter-based) stream.  Also returns the raw-image rows [n_src]."""
+    (counter-based) stream.  Also returns the raw-image rows [n_src].
+
+    src_offset / n_src_total: these n_src images are sources src_offset .. src_offset+n_src-1 of a GLOBAL batch of
+    n_src_total; the draws are keyed by the global row index, so a rank that owns a shard of the batch makes exactly the
+    decisions a single process holding the whole batch makes for those images (1-vs-N result parity)."""
     m = len(parsed_policies)
     n = n_src * m
-    u = _uniforms(seed, epoch, step, n + n_src, 5)        # 20 uniforms per row
+    total = n_src if n_src_total is None else int(n_src_total)
+    ids = np.concatenate([np.arange(src_offset * m, (src_offset + n_src) * m),
+                          total * m + np.arange(src_offset, src_offset + n_src)])
+    u = _uniforms(seed, epoch, step, n + n_src, 5, ids)   # 20 uniforms per row
     rows = np.zeros(n, ROW_DTYPE)
     raws = np.zeros(n_src, ROW_DTYPE)
     tw = th = crop

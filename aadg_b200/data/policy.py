@@ -52,17 +52,58 @@ def parse_policies(policies, config, logger=None):
     return parsed
 
 
-class Policy:
-    """One searched policy = Q sub-policies of L (op, mag) pairs (data/policy.py:7-30)."""
+def _apply_one_policy(policy_obj, img, mask, py, npr):
+    """the body of `Policy.__call__` on CUDA tensors: one row per image resolved through the reference's draws"""
+    import torch
+    from ..ops import u8 as _u8  # CUDA bank; fails loudly when the extension is missing
+    single = img.dim() == 3
+    imgs = img[None] if single else img
+    masks = None if mask is None else (mask[None] if single else mask)
+    s, h, w, _ = imgs.shape
+    rows = np.zeros(s, _dec.ROW_DTYPE)
+    for i in range(s):
+        policy_obj.calls += 1
+        _dec.replay_policy_call(rows[i], policy_obj.policy, policy_obj.calls, i, w, h, py, npr)
+        rows[i]["scale_w"], rows[i]["scale_h"] = w, h
+    if masks is None:
+        out, outm = _u8.apply_policy(imgs, None, rows), None
+    else:
+        out, outm = _u8.apply_policy(imgs, masks, rows, want_masks=True)
+    policy_obj.last_rows = rows
+    if single:
+        return out[0], (None if outm is None else outm[0])
+    return out, outm
 
-    def __init__(self, policy):
+
+class Policy:
+    """One searched policy = Q sub-policies of L (op, mag) pairs (data/policy.py:7-30).
+
+    `policy(img, mask)` keeps the reference's call shape on CUDA uint8 tensors (`[H,W,3]` + `[H,W]`, or a batch
+    `[S,H,W,3]` + `[S,H,W]`): one randomly chosen sub-policy is applied by the CUDA bank.  The draws come from `rng`
+    = (random.Random-like, RandomState-like); the default is the GLOBAL `random` / `np.random` state the reference
+    uses, consumed in its order (queue draw, sub-policy choice, Cutout centre / mirror sign), so that a seeded
+    reference `Policy` and this one make identical decisions."""
+
+    def __init__(self, policy, rng=None):
         self.policy = policy
         self.calls = 0  # stands in for the CutMix queue length (see decisions.PolicyState)
+        self.rng = rng
+        self.last_rows = None
+
+    def __call__(self, img, mask=None):
+        py, npr = self.rng if self.rng is not None else (_random, np.random)
+        return _apply_one_policy(self, img, mask, py, npr)
 
 
 class MultiPolicy:
-    def __init__(self, policies):
-        self.policies = [Policy(p) for p in policies]
+    """data/policy.py:33-43: `multi(img) -> [policy(img) for policy in policies]` (each entry an (img, mask) pair,
+    mask None: the reference's MultiPolicy passes no mask and would raise inside Policy.__call__)."""
+
+    def __init__(self, policies, rng=None):
+        self.policies = [Policy(p, rng) for p in policies]
+
+    def __call__(self, img, mask=None):
+        return [policy(img, mask) for policy in self.policies]
 
 
 class DGMultiPolicy:

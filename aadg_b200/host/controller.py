@@ -78,6 +78,21 @@ class Controller(nn.Module):
         return torch.stack(logps, -1).sum(-1)
 
 
+def evaluate_with_entropy(controller, policies, batch_size):
+    """(sum_t log pi(a_t), sum_t H_t) [M] WITH an autograd graph, through the torch mirror of the walk (what the
+    reference's `controller(M)` returns for the REINFORCE loss, losses.py:96-114).  Used when the sampled
+    log-probabilities carry no graph (FusedController.sample)."""
+    logps, ents = [], []
+
+    def choose(step, kind, logp):
+        action = policies[:, step].long()
+        logps.append(logp.gather(1, action[:, None])[:, 0])
+        ents.append(-(logp * logp.exp()).sum(1))
+        return action
+    Controller._walk(controller, batch_size, choose)
+    return torch.stack(logps, -1).sum(-1), torch.stack(ents, -1).sum(-1)
+
+
 class _WalkEvaluate(torch.autograd.Function):
     """sum_t log pi(a_t) for given policies: forward = one aadg_controller_walk launch (mode 1), backward = one
     aadg_controller_backward launch producing the gradients of all nine parameter tensors."""
@@ -107,6 +122,22 @@ class FusedController(Controller):
     def __init__(self, cfg, n_subpolicies=5, embedding_dim=32, hidden_dim=100, seed=0):
         super().__init__(cfg, n_subpolicies, embedding_dim, hidden_dim)
         self.seed, self.calls = int(seed), 0
+
+    # the Philox call counter travels with the state_dict (a resumed run must not replay the same sample stream); it
+    # is stored as module extra state so that the parameter / buffer key set stays the reference Controller's
+    def get_extra_state(self):
+        return {"calls": int(self.calls), "seed": int(self.seed)}
+
+    def set_extra_state(self, state):
+        self.calls = int(state.get("calls", 0))
+        self.seed = int(state.get("seed", self.seed))
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """accepts a reference `Controller` checkpoint (no `_extra_state` key) as well as its own"""
+        if "_extra_state" not in state_dict:
+            state_dict = dict(state_dict)
+            state_dict["_extra_state"] = self.get_extra_state()
+        return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def _params(self):
         return [self.embedding.weight, self.lstm.weight_ih, self.lstm.weight_hh, self.lstm.bias_ih, self.lstm.bias_hh,

@@ -20,6 +20,11 @@ class Reinforce(nn.Module):
         self.optimizer = optimizer
 
     def forward(self, controller, policies, log_probs, entropies, reward):
+        if not log_probs.requires_grad:
+            # FusedController.sample() returns graph-less values (one kernel launch): rebuild log-probabilities and
+            # entropies of the SAME policies with a graph through the torch mirror of the walk (once per epoch)
+            from .controller import evaluate_with_entropy
+            log_probs, entropies = evaluate_with_entropy(controller, policies, reward.size(0))
         score = torch.mean(-log_probs * reward)
         ent = torch.mean(entropies)
         loss = score - self.penalty * ent

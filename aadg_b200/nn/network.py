@@ -105,6 +105,10 @@ class ParamStore:
             p.data.copy_(p.init(p.shape).to(dev))
             p.init = None
         self.step = 0
+        # the optimiser's scalars in device memory (aadg_adam_step_dev): nothing is passed by value, so a captured CUDA
+        # graph replays the update while the host changes the rate / the step count advances on the device
+        self.hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0], dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.refresh()
 
     def refresh(self):
@@ -116,8 +120,21 @@ class ParamStore:
 
     def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.step += 1
+        self.step_dev += 1
         K.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, lr, betas[0], betas[1], eps,
                     weight_decay, self.step)
+        self.refresh()
+
+    def set_hyper(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+        """(host -> device copy; call it outside a captured region) grad_scale multiplies the gradients on load:
+        1/world after a summing all-reduce"""
+        self.hyper.copy_(torch.tensor([lr, betas[0], betas[1], eps, weight_decay, grad_scale], dtype=torch.float32))
+
+    def adam_step_dev(self):
+        """the same Adam step driven by `hyper` / `step_dev` in device memory (capturable)"""
+        self.step += 1
+        self.step_dev += 1
+        K.adam_step_dev(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.hyper, self.step_dev)
         self.refresh()
 
 
@@ -148,6 +165,31 @@ def from_taps(w, r, s):
 # ---------------------------------------------------------------------------------------------------
 # layers
 # ---------------------------------------------------------------------------------------------------
+# SyncBN option: a torch.distributed process group (or True for the default group) makes every
+# BatchNorm share its batch statistics across ranks -- forward sums and the two backward sums are all-reduced -- so that
+# N ranks holding shards of a batch compute what one GPU holding the whole batch computes.  None = per-rank statistics,
+# the reference's DDP behaviour (plain BatchNorm2d under DistributedDataParallel, models/__init__.py:39).
+SYNC_BN = None
+
+
+def set_sync_bn(group):
+    global SYNC_BN
+    SYNC_BN = group
+
+
+def _sync_world():
+    import torch.distributed as dist
+    if SYNC_BN is None or not (dist.is_available() and dist.is_initialized()):
+        return None, 1
+    g = None if SYNC_BN is True else SYNC_BN
+    return g, dist.get_world_size(g)
+
+
+def _all_reduce_sum(t, group):
+    import torch.distributed as dist
+    dist.all_reduce(t, group=group)
+
+
 class BatchNorm:
     def __init__(self, store, name, c):
         self.c, self.name = c, name
@@ -172,6 +214,11 @@ class BatchNorm:
                 s[:2].zero_()
                 K.bn_stats(x, s[0], s[1])
             count = x.numel() // x.shape[-1]
+            group, world = _sync_world()
+            if world > 1:
+                _all_reduce_sum(s[:2], group)
+                count *= world
+            self.count = count
             K.bn_finalize(s[0], s[1], self.gamma.data, self.beta.data, count, BN_EPS, BN_MOMENTUM, s[2], s[3], s[4],
                           s[5], self.running_mean, self.running_var, reset_sums=True)
             self.num_batches_tracked += 1
@@ -188,6 +235,21 @@ class BatchNorm:
         """y=None: no residual was added in forward, the ReLU mask is recomputed from x (saves reading y).
         dy2: second gradient branch, added to dy on load."""
         sv = self.saved
+        group, world = _sync_world()
+        if world > 1:
+            # local sums -> this rank's share of dgamma / dbeta (the gradient all-reduce sums the shares); the GLOBAL
+            # sums and the global pixel count give dx
+            sums = torch.zeros((2, self.c), dtype=torch.float32, device=x.device)
+            K.bn_backward_reduce(dy, x, y, sv[0], sv[1], self.gamma.data, sums, relu=relu, dropout_seed=dropout_seed,
+                                 shift=sv[3], dy2=dy2, relu6=relu6)
+            self.gamma.grad.add_(sums[0])
+            self.beta.grad.add_(sums[1])
+            _all_reduce_sum(sums, group)
+            K.bn_backward_apply(dy, x, y, sv[0], sv[1], self.gamma.data, sums, self.count, dx, relu=relu,
+                                dropout_seed=dropout_seed, dres=dres, dres_accumulate=dres_accumulate, shift=sv[3],
+                                dy2=dy2, relu6=relu6)
+            self.saved = None
+            return
         K.bn_backward(dy, x, y, sv[0], sv[1], self.gamma.data, self.gamma.grad, self.beta.grad, dx, relu=relu,
                       dropout_seed=dropout_seed, dres=dres, dres_accumulate=dres_accumulate, shift=sv[3], dy2=dy2,
                       grads_zeroed=True,       # gamma.grad / beta.grad: slices of the flat buffer zero_grad() cleared
@@ -370,6 +432,24 @@ class Depthwise3x3:
         return dx
 
 
+def first_offset(obj):
+    """smallest flat-buffer offset of the parameters under `obj` (layers register their parameters in forward order, so
+    everything from this offset to the next module's first offset belongs to `obj`)"""
+    best = [None]
+
+    def walk(o):
+        if isinstance(o, Param):
+            best[0] = o.offset if best[0] is None else min(best[0], o.offset)
+        elif isinstance(o, (list, tuple)):
+            for i in o:
+                walk(i)
+        elif hasattr(o, "__dict__") and not isinstance(o, (ParamStore, torch.Tensor)):
+            for v in vars(o).values():
+                walk(v)
+    walk(obj)
+    return best[0]
+
+
 def as_pair(d):
     return d if isinstance(d, tuple) else (d, None)
 
@@ -515,9 +595,10 @@ class ResNetEncoder:
         self.ctx = (col, pre, f1, arg) if training else None
         return feats            # strides 2, 4, 8, 16, 16
 
-    def backward(self, d_last, d_stride4=None, d_skips=None):
+    def backward(self, d_last, d_stride4=None, d_skips=None, on_ready=None):
         """d_last: gradient of the last feature map; d_stride4: gradient of the stride-4 map (DeepLab decoder
-        skip); d_skips: gradients of feats[0..3] as returned by forward (UNet skips, None entries allowed)."""
+        skip); d_skips: gradients of feats[0..3] as returned by forward (UNet skips, None entries allowed).
+        on_ready(offset): called when every parameter gradient at flat offset >= `offset` is final (a stage is done)."""
         col, pre, f1, arg = self.ctx
         self.ctx = None
         skips = list(d_skips) if d_skips is not None else [None, d_stride4, None, None]
@@ -528,6 +609,8 @@ class ResNetEncoder:
                 # the gradient of feats[li] (a decoder skip) joins the gradient of stage li's first block's input
                 extra = skips[li] if (bi == 0 and li > 0) else None
                 d = blocks[bi].backward(d, extra=extra)
+            if on_ready is not None and li > 0:
+                on_ready(first_offset(blocks))
         d = K.maxpool_bwd(fold_pair(d), arg, f1.shape)
         if skips[0] is not None:
             K.add_(d, skips[0])
@@ -647,7 +730,7 @@ class MobileNetV2Encoder:
         self.ctx = (col, pre) if training else None
         return feats            # strides 2, 4, 8, 16, 16
 
-    def backward(self, d_last, d_stride4=None, d_skips=None):
+    def backward(self, d_last, d_stride4=None, d_skips=None, on_ready=None):
         col, pre = self.ctx
         self.ctx = None
         skips = list(d_skips) if d_skips is not None else [None, d_stride4, None, None]
@@ -657,6 +740,8 @@ class MobileNetV2Encoder:
                 sk = skips[self.stage_ends.index(idx)]
                 if sk is not None:
                     K.add_(d, sk)
+                if on_ready is not None and idx == 13:      # features.14 .. 18 are done (most of the encoder's weights)
+                    on_ready(first_offset([b for i, b in self.blocks if i > idx]))
             d = blk.backward(d)
         dpre = torch.empty_like(pre)
         self.stem_bn.backward(d, pre, None, dpre, relu=True, relu6=True)
@@ -819,6 +904,9 @@ class SegNet:
         self.dropout_seed = 0x5EED0000 + seed
         self.dropout_enabled = True      # Dropout(0.5) of the ASPP projection (train mode)
         self.steps = 0
+        # the current dropout seed (dropout_seed + steps) in device memory: the kernels read it there (flag 64), so a
+        # captured CUDA graph draws a fresh mask on every replay
+        self.seed_dev = torch.full((1,), self.dropout_seed, dtype=torch.int64, device=self.device)
 
     # ---- torch.nn.Module-like surface ---------------------------------------------------------------
     def train(self, mode=True):
@@ -915,7 +1003,7 @@ class SegNet:
         if self.arch == "unet":
             dec = self.decoder.forward(feats, self.training)
         else:
-            seed = (self.dropout_seed + self.steps) if (self.training and self.dropout_enabled) else None
+            seed = self.seed_dev if (self.training and self.dropout_enabled) else None
             dec = self.decoder.forward(feats, self.training, seed)
         return dec, pooled
 
@@ -950,9 +1038,11 @@ class SegNet:
         K.seg_loss_fwd(z, target, thr, loss_sum, counts, logits)
         return dict(logits=logits, counts=counts, pooled=pooled, loss=(loss_sum / float(logits.numel())).float())
 
-    def loss_step(self, x, target, thr=0.5, want_logits=False):
+    def loss_step(self, x, target, thr=0.5, want_logits=False, on_ready=None):
         """Forward + BCELoss(sigmoid(logits), target) (mean) + Dice counts, then the whole backward.
         Gradients are left in store.grads (call store.zero_grad() before, store.adam_step() after).
+        on_ready(offset): called during the backward pass each time every gradient at flat offset >= `offset` is final
+        (head + decoder, then encoder stage by stage, finally 0) -- the hook a bucketed gradient all-reduce overlaps on.
         Returns dict(loss [1] fp32 tensor, counts int32 [N,classes,3], pooled fp32 [N,C], logits or None)."""
         assert self.training
         n, _, hh, ww = x.shape
@@ -968,13 +1058,62 @@ class SegNet:
         if self.arch == "unet":
             K.seg_head3x3_bwd(dz, dec, self.head_w.data, ddec, self.head_w.grad, self.head_b.grad)
             d_last, d_skips = self.decoder.backward(ddec)
-            self.encoder.backward(d_last, d_skips=d_skips)
+            if on_ready is not None:
+                on_ready(first_offset(self.decoder))
+            self.encoder.backward(d_last, d_skips=d_skips, on_ready=on_ready)
         else:
             K.seg_head_bwd(dz, dec, self.head_w.data, ddec, self.head_w.grad, self.head_b.grad)
             d_last, d_high = self.decoder.backward(ddec)
-            self.encoder.backward(d_last, d_high)
+            if on_ready is not None:
+                on_ready(first_offset(self.decoder))
+            self.encoder.backward(d_last, d_high, on_ready=on_ready)
+        if on_ready is not None:
+            on_ready(0)
         self.steps += 1
+        if self.dropout_enabled:
+            self.seed_dev += 1
         return dict(loss=(loss_sum / numel).float(), counts=counts, pooled=pooled, logits=logits)
+
+
+class GraphedTrainStep:
+    """zero_grad -> loss_step (forward, loss, backward, with the gradient-ready hooks) -> `before_update()` -> Adam from
+    device-resident scalars, captured ONCE into a CUDA graph and replayed: ~2 000 kernel launches become one
+    cudaGraphLaunch.  `images` / `labels` are the static input buffers the caller refills before every replay(); the
+    returned dict holds static output tensors (overwritten by the next replay).  Everything that changes from step to
+    step lives in device memory (dropout seed, Adam step count and rate), nothing is baked into the graph by value."""
+
+    def __init__(self, model, images, labels, on_ready=None, before_update=None, pool=None):
+        assert C.TIMING is None, "per-launch event timing cannot be captured"
+        self.model = model
+        store = model.store
+        bns = model._bns()
+        saved = (model.steps, store.step, [bn.num_batches_tracked for bn in bns])
+        torch.cuda.synchronize(model.device)
+        self.graph = torch.cuda.CUDAGraph()
+        from .. import _lib
+        calls0 = _lib.CALLS
+        with torch.cuda.graph(self.graph, pool=pool):
+            store.zero_grad()
+            self.out = model.loss_step(images, labels, on_ready=on_ready)
+            if before_update is not None:
+                before_update()
+            store.adam_step_dev()
+        self.launches = _lib.CALLS - calls0        # C-ABI launches inside the graph (replayed every step)
+        # capture executes nothing on the device: take back the host-side counters it advanced
+        model.steps, store.step = saved[0], saved[1]
+        for bn, nb in zip(bns, saved[2]):
+            bn.num_batches_tracked = nb
+        self._bns = bns
+
+    def replay(self):
+        from .. import _lib
+        self.graph.replay()
+        _lib.CALLS += self.launches
+        self.model.steps += 1
+        self.model.store.step += 1
+        for bn in self._bns:
+            bn.num_batches_tracked += 1
+        return self.out
 
 
 def dice_from_counts(counts):

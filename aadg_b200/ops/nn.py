@@ -37,27 +37,65 @@ def bn_finalize(sum_, sumsq, gamma, beta, count, eps, momentum, mean, invstd, sc
           p(mean), p(invstd), p(scale), p(shift), p(run_mean), p(run_var), int(reset_sums))
 
 
+def _seed(dropout_seed):
+    """(flag bits, value) of a dropout seed: None, an int (passed by value), or an int64 CUDA tensor holding it (flag
+    64: the kernel reads the seed from device memory, so a captured CUDA graph follows the host's seed updates)"""
+    if dropout_seed is None:
+        return 0, 0
+    if isinstance(dropout_seed, torch.Tensor):
+        assert dropout_seed.is_cuda and dropout_seed.dtype == torch.int64 and dropout_seed.numel() == 1
+        return 2 | 64, dropout_seed.data_ptr()
+    return 2, int(dropout_seed)
+
+
 def bn_apply(x, scale, shift, y, res=None, relu=True, dropout_seed=None, relu_bits=None, relu6=False):
-    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (32 if (relu and relu6) else 0)
+    sf, sv = _seed(dropout_seed)
+    flags = (1 if relu else 0) | sf | (32 if (relu and relu6) else 0)
     _call("aadg_bn_apply", p(x), _ld(x), p(scale), p(shift), p(res), _ld(res) if res is not None else 0, p(y), _ld(y),
-          _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(relu_bits))
+          _pix(x), x.shape[-1], flags, sv, p(relu_bits))
+
+
+def _bn_bwd_flags(y, relu, dropout_seed, grads_zeroed, relu6):
+    bits = y is not None and y.dtype == torch.uint8        # relu bit mask written by bn_apply(relu_bits=...)
+    sf, sv = _seed(dropout_seed)
+    flags = (1 if relu else 0) | sf | (4 if (relu and y is None) else 0) | \
+        (8 if bits else 0) | (16 if grads_zeroed else 0) | (32 if (relu and relu6) else 0)
+    return bits, flags, sv
 
 
 def bn_backward(dy, x, y, mean, invstd, gamma, dgamma, dbeta, dx, relu=True, dropout_seed=None, dres=None,
                 dres_accumulate=False, shift=None, dy2=None, grads_zeroed=False, relu6=False):
     """y=None with relu=True recomputes the ReLU mask from x and the forward `shift` (no residual case).
     dy2: a second gradient tensor added to dy on load."""
-    bits = y is not None and y.dtype == torch.uint8        # relu bit mask written by bn_apply(relu_bits=...)
-    flags = (1 if relu else 0) | (2 if dropout_seed is not None else 0) | (4 if (relu and y is None) else 0) | \
-        (8 if bits else 0) | (16 if grads_zeroed else 0) | (32 if (relu and relu6) else 0)
+    bits, flags, sv = _bn_bwd_flags(y, relu, dropout_seed, grads_zeroed, relu6)
     tail = (p(x), _ld(x), p(y), _ld(y) if (y is not None and not bits) else 0, p(mean), p(invstd),
-            p(gamma), p(shift), _pix(x), x.shape[-1], flags, int(dropout_seed or 0), p(dgamma), p(dbeta), p(dx), _ld(dx),
+            p(gamma), p(shift), _pix(x), x.shape[-1], flags, sv, p(dgamma), p(dbeta), p(dx), _ld(dx),
             p(dres), _ld(dres) if dres is not None else 0, int(dres_accumulate))
     if dy2 is None:
         _call("aadg_bn_backward", p(dy), _ld(dy), *tail)
     else:
         assert dy2.shape == dy.shape
         _call("aadg_bn_backward2", p(dy), _ld(dy), p(dy2), _ld(dy2), *tail)
+
+
+def bn_backward_reduce(dy, x, y, mean, invstd, gamma, sums, relu=True, dropout_seed=None, shift=None, dy2=None,
+                       relu6=False):
+    """first half of the backward (SyncBN): sums fp32 [2,C] += (sum g*xhat, sum g) of this rank's pixels"""
+    bits, flags, sv = _bn_bwd_flags(y, relu, dropout_seed, True, relu6)
+    assert sums.dtype == torch.float32 and sums.shape == (2, x.shape[-1]) and sums.is_contiguous()
+    _call("aadg_bn_backward_reduce", p(dy), _ld(dy), p(dy2), _ld(dy2) if dy2 is not None else 0, p(x), _ld(x), p(y),
+          _ld(y) if (y is not None and not bits) else 0, p(mean), p(invstd), p(gamma), p(shift), _pix(x), x.shape[-1],
+          flags, sv, p(sums[0]), p(sums[1]))
+
+
+def bn_backward_apply(dy, x, y, mean, invstd, gamma, sums, count, dx, relu=True, dropout_seed=None, dres=None,
+                      dres_accumulate=False, shift=None, dy2=None, relu6=False):
+    """second half: dx (and dres) from the GLOBAL sums [2,C] and the global pixel count"""
+    bits, flags, sv = _bn_bwd_flags(y, relu, dropout_seed, True, relu6)
+    _call("aadg_bn_backward_apply", p(dy), _ld(dy), p(dy2), _ld(dy2) if dy2 is not None else 0, p(x), _ld(x), p(y),
+          _ld(y) if (y is not None and not bits) else 0, p(mean), p(invstd), p(gamma), p(shift), _pix(x), x.shape[-1],
+          flags, sv, p(sums[0]), p(sums[1]), 1.0 / float(count), p(dx), _ld(dx), p(dres),
+          _ld(dres) if dres is not None else 0, int(dres_accumulate))
 
 
 def add_(a, b):
@@ -153,6 +191,13 @@ def im2col_stem(img, r, s, stride, pad, kp, row_pitch=None):
 
 def adam_step(params, grads, m, v, lr, beta1, beta2, eps, wd, step):
     _call("aadg_adam_step", p(params), p(grads), p(m), p(v), params.numel(), lr, beta1, beta2, eps, wd, step)
+
+
+def adam_step_dev(params, grads, m, v, hyper, step):
+    """Adam with its scalars in device memory: hyper float32 [6] = (lr, beta1, beta2, eps, weight_decay, grad_scale),
+    step int64 [1] (1-based)"""
+    assert hyper.dtype == torch.float32 and hyper.numel() == 6 and step.dtype == torch.int64 and step.numel() == 1
+    _call("aadg_adam_step_dev", p(params), p(grads), p(m), p(v), params.numel(), p(hyper), p(step))
 
 
 def weight_prep(master, wb, wbt, descs, n):

@@ -94,10 +94,49 @@ class SamplesLoss:
     forward = __call__
 
 
-def diversity_rewards(domain_feature, domain_code, M, rewards=None):
-    """search_dg.py:150-162 in one launch.  domain_feature float32 [n,d], domain_code float32 [n,D]
-    (soft one-hot), rows ordered (b*D+d)*M+j.  Adds (d12+d13)+d23 to rewards[j] (created if None);
-    returns (rewards [M], pair_values [M, pairs])."""
+def _pair_order(nd):
+    """the reference's call order for three domains is (1,2), (2,3), (1,3) (search_dg.py:158-160); otherwise lexicographic"""
+    if nd == 3:
+        return [(0, 1), (1, 2), (0, 2)]
+    return [(a, b) for a in range(nd) for b in range(a + 1, nd)]
+
+
+def _diversity_rewards_general(f, dc, M, rewards, pairs):
+    """clouds of any size: the `[j::M]` / argmax split on the host side of the ABI (one device->host read of the domain
+    ids), every pair through `divergence` (one-launch kernel up to small_max_points(), streamed large path above)."""
+    nd = dc.shape[1]
+    dom = torch.argmax(dc, dim=1).cpu().numpy()
+    order = _pair_order(nd)
+    for j in range(M):
+        rows = np.arange(j, f.shape[0], M)
+        clouds = []
+        for k in range(nd):
+            idx = rows[dom[rows] == k]
+            if idx.size == 0:
+                raise RuntimeError("diversity_rewards: policy %d has no sample of domain %d in this batch (the "
+                                   "reference's sinkhorn(empty, .) is undefined)" % (j, k))
+            clouds.append(f[torch.as_tensor(idx, device=f.device)])
+        vals = [divergence(clouds[a], clouds[b]) for a, b in order]
+        pairs[j] = torch.stack(vals)
+        if nd == 3:
+            rewards[j] += (vals[0] + vals[2]) + vals[1]        # (d12 + d13) + d23
+        else:
+            t = vals[0]
+            for v in vals[1:]:
+                t = t + v
+            rewards[j] += t
+    return rewards, pairs
+
+
+def diversity_rewards(domain_feature, domain_code, M, rewards=None, max_cloud=None):
+    """search_dg.py:150-162.  domain_feature float32 [n,d], domain_code float32 [n,D] (soft one-hot), rows ordered
+    (b*D+d)*M+j.  Adds (d12+d13)+d23 to rewards[j] (created if None); returns (rewards [M], pair_values [M, pairs]).
+
+    max_cloud = an upper bound on the number of rows of one (policy, domain) cloud, when the caller knows it (the
+    search engine does: it is the largest per-domain source-image count of the global batch); default n // M, the worst
+    case.  Up to small_max_points() everything is ONE launch without a host sync; above it the clouds go through the
+    general path (streamed large-N kernels).  An EMPTY cloud makes the fused kernel store NaN and flag its status word:
+    `check_rewards(rewards)` at the epoch boundary raises on it (a NaN reward must never reach the controller)."""
     f, dc = _check(domain_feature), _check(domain_code)
     n, d = f.shape
     nd = dc.shape[1]
@@ -106,15 +145,28 @@ def diversity_rewards(domain_feature, domain_code, M, rewards=None):
     if rewards is None:
         rewards = torch.zeros(M, dtype=torch.float32, device=f.device)
     pairs = torch.empty((M, nd * (nd - 1) // 2), dtype=torch.float32, device=f.device)
+    if max_cloud is None:
+        max_cloud = (n + M - 1) // M
+    if max_cloud > small_max_points():
+        return _diversity_rewards_general(f, dc, M, rewards, pairs)
     L = _lib.lib()
     ws = _lib.workspace(L.aadg_sinkhorn_rewards_workspace_bytes(M, nd), f.device)
-    with torch.cuda.device(f.device):
+    with _lib.on_device(f.device):
         _lib.check(L.aadg_sinkhorn_diversity_rewards(_lib.ptr(f), _lib.ptr(dc), n, d, nd, M, _lib.ptr(rewards),
                                                      _lib.ptr(pairs), _lib.ptr(ws), ws.numel(),
                                                      _lib.stream_ptr()))
     return rewards, pairs
 
 
+def check_rewards(rewards):
+    """raise if a reward is not finite (an empty or oversize domain cloud reached the fused kernel)"""
+    if not bool(torch.isfinite(rewards).all()):
+        raise RuntimeError("diversity rewards are not finite: a (policy, domain) cloud was empty or larger than %d "
+                           "points in some step; rewards=%s" % (small_max_points(), rewards.tolist()))
+    return rewards
+
+
 def normalize_rewards(rewards):
-    """search_dg.py:214."""
+    """search_dg.py:214 (raises instead of normalising NaN rewards into the controller update)."""
+    check_rewards(rewards)
     return (rewards - torch.mean(rewards)) / (torch.std(rewards) + 1e-5)

@@ -76,7 +76,8 @@ def normalize_to_tensor(src_images, src_masks, dataset="optic"):
     return policy_normalize(src_images, src_masks, rows, dataset=dataset)
 
 
-def scale_crop_normalize(images, masks, rows, crop, dataset="optic", image_by_row=True, want_labels=True):
+def scale_crop_normalize(images, masks, rows, crop, dataset="optic", image_by_row=True, want_labels=True,
+                         out_images=None, out_labels=None):
     """DGRandomScaleCrop + Normalize_dg + ToTensor for every row (data/transform.py:97-236): images uint8
     [n,H,W,3] (post-policy, one per row) or the sources (image_by_row=False); masks = ORIGINAL masks [S,H,W].
     Returns (float32 [n,3,crop,crop], float32 [n,C,crop,crop] or None)."""
@@ -88,8 +89,12 @@ def scale_crop_normalize(images, masks, rows, crop, dataset="optic", image_by_ro
     ds = DATASETS[dataset]
     c = 2 if ds == 0 else 1
     n_src = masks.shape[0] if masks is not None else images.shape[0]
-    out_i = torch.empty((n, 3, crop, crop), dtype=torch.float32, device=dev)
-    out_l = torch.empty((n, c, crop, crop), dtype=torch.float32, device=dev) if (want_labels and masks is not None) else None
+    out_i = out_images if out_images is not None else torch.empty((n, 3, crop, crop), dtype=torch.float32, device=dev)
+    assert out_i.shape == (n, 3, crop, crop) and out_i.dtype == torch.float32 and out_i.is_contiguous()
+    out_l = None
+    if want_labels and masks is not None:
+        out_l = out_labels if out_labels is not None else torch.empty((n, c, crop, crop), dtype=torch.float32, device=dev)
+        assert out_l.shape == (n, c, crop, crop) and out_l.dtype == torch.float32 and out_l.is_contiguous()
     mw = int(max([w] + [int(r["scale_w"]) for r in rows if r["do_scale"]]))
     mh = int(max([h] + [int(r["scale_h"]) for r in rows if r["do_scale"]]))
     L = _lib.lib()
@@ -101,11 +106,12 @@ def scale_crop_normalize(images, masks, rows, crop, dataset="optic", image_by_ro
     return out_i, out_l
 
 
-def policy_scale_crop_normalize(src_images, src_masks, rows, crop, dataset="optic"):
+def policy_scale_crop_normalize(src_images, src_masks, rows, crop, dataset="optic", out_images=None, out_labels=None):
     """The reference's whole train transform for the augmented copies: DGMultiPolicy -> DGRandomScaleCrop ->
     Normalize_dg -> ToTensor -> collate (data/policy.py:51-61, data/transform.py:97-236,323-340)."""
     post = apply_policy(src_images, src_masks, rows)
-    return scale_crop_normalize(post, src_masks, rows, crop, dataset, image_by_row=True)
+    return scale_crop_normalize(post, src_masks, rows, crop, dataset, image_by_row=True, out_images=out_images,
+                                out_labels=out_labels)
 
 
 def apply_dg_multipolicy(policy, sample):

@@ -202,7 +202,8 @@ int aadg_bn_finalize(float* sum, float* sumsq, const float* gamma, const float* 
                      float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
                      float* run_mean, float* run_var, int reset_sums, void* stream);
 /* y = act(x*scale + shift (+ res)) ; flags bit0 = ReLU, bit5 (32) = ReLU6 (with bit0), bit1 = Dropout(0.5) keyed by
- * (seed, element);
+ * (seed, element); bit6 (64, here and in the backward calls): `seed` is the DEVICE ADDRESS of the 64-bit seed, read by
+ * the kernel (a captured CUDA graph replays the launch while the host advances the seed in device memory);
  * relu_bits (may be NULL): uint8 [pixels][c/8], bit i of byte g = (pre-activation of channel 8g+i > 0) */
 int aadg_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr, void* y,
                   int ldy, long long pixels, int c, int flags, unsigned long long seed, void* relu_bits,
@@ -222,6 +223,19 @@ int aadg_bn_backward2(const void* dy, int lddy, const void* dy2, int lddy2, cons
                       const float* mean, const float* invstd, const float* gamma, const float* shift, long long pixels,
                       int c, int flags, unsigned long long seed, float* dgamma, float* dbeta, void* dx, int lddx,
                       void* dres, int lddr, int dres_accumulate, void* stream);
+/* The two halves of aadg_bn_backward / aadg_bn_backward2 for batch statistics shared across ranks (the SyncBN option
+ * of SURVEY.md §8e(3); torch.nn.SyncBatchNorm semantics): `reduce` ACCUMULATES this rank's sum(g*xhat) / sum(g) into
+ * dgamma_sum / dbeta_sum (fp32 [c], zero them first); the caller all-reduces them; `apply` takes the global sums and
+ * inv_count = 1 / (global pixel count) and writes dx (and dres).  dy2 may be NULL. */
+int aadg_bn_backward_reduce(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const void* y,
+                            int ldy, const float* mean, const float* invstd, const float* gamma, const float* shift,
+                            long long pixels, int c, int flags, unsigned long long seed, float* dgamma_sum,
+                            float* dbeta_sum, void* stream);
+int aadg_bn_backward_apply(const void* dy, int lddy, const void* dy2, int lddy2, const void* x, int ldx, const void* y,
+                           int ldy, const float* mean, const float* invstd, const float* gamma, const float* shift,
+                           long long pixels, int c, int flags, unsigned long long seed, const float* dgamma_sum,
+                           const float* dbeta_sum, float inv_count, void* dx, int lddx, void* dres, int lddr,
+                           int dres_accumulate, void* stream);
 int aadg_add_bf16(void* a, int lda, const void* b, int ldb, long long pixels, int c, void* stream);
 /* MaxPool2d(3, stride 2, padding 1): argmax uint8 [n,ho,wo,c] */
 int aadg_maxpool3x3s2_fwd(const void* x, int n, int h, int w, int c, void* y, void* argmax, void* stream);
@@ -264,6 +278,11 @@ int aadg_im2col_stem_rows(const float* img, int n, int h, int w, int r, int s, i
 /* torch.optim.Adam step `step` (1-based) over flat fp32 buffers */
 int aadg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+/* the same step with its scalars in device memory: hyper = float32 {lr, beta1, beta2, eps, weight_decay, grad_scale}
+ * (grad_scale multiplies the gradient on load: 1/world after a summing all-reduce, models/__init__.py:39 DDP averaging),
+ * step = int64 1-based step count.  Nothing is passed by value, so a captured CUDA graph replays it unchanged. */
+int aadg_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count,
+                       const float* hyper, const long long* step, void* stream);
 /* fp32 master weights [taps][cout][cin] -> bf16 copy (+ transposed [taps][cin][cout] copy); descs (device):
  * per weight { int64 off_master, off_bf16, off_bf16_t (-1: none); int32 taps, cout, cin, 0 } */
 int aadg_weight_prep(const float* master, void* w_bf16, void* w_bf16_t, const void* descs, int n_descs, void* stream);

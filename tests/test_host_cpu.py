@@ -93,7 +93,7 @@ def _free_port():
 
 def _exchange_worker(rank, world, port, q):
     import torch.distributed as dist
-    from aadg_b200.host.search import gather_rows, average_, shard_sources
+    from aadg_b200.host.search import BucketedAllReduce, gather_rows, average_, shard_sources
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -103,7 +103,17 @@ def _exchange_worker(rank, world, port, q):
     all_f, all_dc = gather_rows(feat, dc)
     grads = torch.full((5,), float(rank + 1))
     average_(grads)
-    q.put((rank, all_f.numpy(), all_dc.numpy(), grads.numpy(), shard_sources(24, rank, world)))
+    # the bucketed gradient exchange: slices are handed over from the END of the flat buffer as backward finishes stages
+    flat = torch.arange(40, dtype=torch.float32) * (rank + 1)
+    red = BucketedAllReduce(flat, min_elems=8)
+    red.ready(36)            # too small a slice: merged into the next one
+    assert not red.works and red.hi == 40
+    red.ready(25)
+    red.ready(10)
+    assert len(red.works) == 2 and red.hi == 10
+    red.wait()               # the rest ([0, 10)) goes out here
+    assert red.hi == 40 and not red.works
+    q.put((rank, all_f.numpy(), all_dc.numpy(), grads.numpy(), shard_sources(24, rank, world), flat.numpy()))
     dist.destroy_process_group()
 
 
@@ -120,7 +130,8 @@ def test_world_size_2_exchange_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, f0, d0, g0, s0), (r1, f1, d1, g1, s1) = res
+    (r0, f0, d0, g0, s0, b0), (r1, f1, d1, g1, s1, b1) = res
+    assert np.array_equal(b0, np.arange(40) * 3.0) and np.array_equal(b1, b0)        # summed over both ranks, every slice once
     assert np.array_equal(f0, f1) and np.array_equal(d0, d1) and f0.shape == (12, 8)
     assert (d0[:6] == 0).all() and (d0[6:] == 1).all()
     assert np.allclose(g0, 1.5) and np.allclose(g1, 1.5)
@@ -190,3 +201,68 @@ def test_validate_average_meter():
     m.update(2.0, 4)
     m.update(5.0, 2)
     assert abs(m.avg - 3.0) < 1e-12
+
+
+def test_decisions_are_keyed_by_the_global_source_index():
+    """a rank that owns sources [off, off+n) of a global batch draws what a single process draws for those images
+    (rows, raw rows and soft domain labels): the basis of 1-vs-N result parity"""
+    parsed = parse_policies(random_policies(seed=5), get_config())
+    full, fr = D.philox_rows(parsed, 6, 64, 64, 64, (1, 1.5), seed=9, epoch=2, step=3)
+    part, pr = D.philox_rows(parsed, 2, 64, 64, 64, (1, 1.5), seed=9, epoch=2, step=3, src_offset=2, n_src_total=6)
+    want, wr = full[12:24].copy(), fr[2:4].copy()
+    want["src"] -= 2
+    wr["src"] -= 2
+    assert part.tobytes() == want.tobytes() and pr.tobytes() == wr.tobytes()
+    sl = D.philox_soft_labels([0, 1, 2, 0, 1, 2], 3, 7, 1, 2)
+    assert np.array_equal(sl[2:4], D.philox_soft_labels([2, 0], 3, 7, 1, 2, src_offset=2))
+    assert (sl.argmax(1) == [0, 1, 2, 0, 1, 2]).all() and (sl.max(1) >= 0.8).all()
+    assert not np.array_equal(sl, D.philox_soft_labels([0, 1, 2, 0, 1, 2], 3, 7, 1, 3))
+
+
+def test_bf16_storage_oracle_rounds_where_the_engine_stores():
+    """oracle/segnet_bf16.py: conv outputs / activations are bf16-representable, the head stays fp32, gradients flow to
+    every parameter (straight-through rounding), and the twin differs from the fp32 oracle by a bf16-sized amount"""
+    import copy
+    from oracle import segnet_bf16
+    from oracle.segnet_torch import DeepLabV3PlusTorch
+    torch.manual_seed(0)
+    ref = DeepLabV3PlusTorch("resnet18", 2).train()
+    for m in ref.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    twin = segnet_bf16.install(copy.deepcopy(ref))
+    seen = {}
+    twin.encoder.layer2[0].conv1.register_forward_hook(lambda m, i, o: seen.__setitem__("conv", o.detach()))
+    twin.encoder.layer2[0].register_forward_hook(lambda m, i, o: seen.__setitem__("block", o.detach()))
+    twin.segmentation_head[0].register_forward_hook(lambda m, i, o: seen.__setitem__("head", o.detach()))
+    x = torch.randn(2, 3, 64, 64)
+    a, pa = ref(x)
+    b, pb = twin(x)
+    for k in ("conv", "block"):
+        assert torch.equal(seen[k], seen[k].bfloat16().float()), k
+    assert not torch.equal(seen["head"], seen["head"].bfloat16().float())
+    rel = ((a - b).norm() / a.norm()).item()
+    assert 1e-4 < rel < 0.5, rel
+    b.sum().backward()
+    assert all(p.grad is not None for p in twin.parameters())
+
+
+def test_reference_arm_times_real_steps():
+    """bench.py --impl reference: the timed region is what the line claims (ms_per_step x steps fits the run)"""
+    import json
+    import subprocess
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t0 = time.time()
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--size", "64", "--backbone", "resnet18", "--ref-sources", "2"], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    wall = time.time() - t0
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["cores"] == os.cpu_count()          # OMP_NUM_THREADS=1 (torchrun) is overridden
+    assert line["ms_per_step"] * line["steps"] / 1e3 <= wall
+    assert abs(line["value"] - line["images_per_timed_step"] / (line["ms_per_step"] / 1e3)) < 1e-6 * line["value"]
+    assert line["e2e"]["value"] == line["value"] and line["gpu_launches"] == 0

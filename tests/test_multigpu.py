@@ -1,5 +1,5 @@
 """GPU (>= 2 devices): the sharded search step under torchrun/NCCL — identical parameters and rewards on every
-rank.  Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`."""
+rank (eager and CUDA-graph steps), and 1-vs-2 result parity on the same global batch with SyncBN statistics.  Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`."""
 import os
 import subprocess
 import sys
@@ -16,4 +16,7 @@ def test_two_rank_search_step_in_lockstep():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "scripts", "multigpu_check.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0 and "MULTIGPU_CHECK OK" in p.stdout, (p.stdout[-2000:], p.stderr[-2000:])
+    print(p.stdout)
+    assert p.returncode == 0, (p.stdout[-3000:], p.stderr[-3000:])
+    for name in ("LOCKSTEP OK", "LOCKSTEP_GRAPH OK", "PARITY_1_vs_2 OK"):
+        assert "MULTIGPU_CHECK " + name in p.stdout, (name, p.stdout[-3000:])

@@ -1,0 +1,201 @@
+"""GPU: whole-network parity at the benchmarked shapes (search_dg.py:132,140-142,170-172).
+
+Two oracles (both stock torch fp32 layers, identical weights):
+  * `oracle/segnet_bf16.py` — the fp32 oracle with the engine's bf16 STORAGE points made explicit.  Same algorithm as
+    the engine, so the ReLU masks coincide ("teacher-forced" by construction) and the bounds are tight: this is the
+    implementation-parity test.
+  * `oracle/segnet_torch.py` — the plain fp32 oracle.  engine-vs-fp32 = implementation error + the precision cost of
+    bf16 activations.  At random initialisation a ResNet-50 amplifies a 2^-9 perturbation of its INPUT IMAGE to 3 % of
+    the pooled feature (measured, DESIGN.md "Precision"), so the fp32 comparison is made on conditioned weights (a few
+    fp32 Adam steps of the oracle) and over a 50-step training trajectory.
+Tolerances are written next to each assert; measured values are printed (pytest -s) and recorded in DESIGN.md.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_math():
+    assert torch.cuda.is_available()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def l2err(got, want):
+    return ((got.float() - want.float()).norm() / (want.float().norm() + 1e-20)).item()
+
+
+def make_data(n, size, classes, seed=0, dataset="optic"):
+    from aadg_b200.synth import fundus_batch, vessel_batch
+    rng = np.random.RandomState(seed)
+    if dataset == "optic":
+        imgs, masks = fundus_batch(n, size, size, seed=seed + 5)
+    else:
+        imgs, masks = vessel_batch(n, size, size, seed=seed + 5)
+    for i in range(n):                       # per-sample colour / contrast variety
+        imgs[i] = np.clip(imgs[i].astype(np.float32) * rng.uniform(0.5, 1.3) + rng.uniform(-40, 40, 3), 0, 255)
+    x = (torch.from_numpy(imgs).cuda().permute(0, 3, 1, 2).float() / 127.5 - 1.0).contiguous()
+    m = torch.from_numpy(masks).cuda()
+    if dataset == "optic":
+        target = torch.stack([(m <= 50).float(), (m <= 200).float()], 1)[:, :classes].contiguous()
+    else:
+        target = (m != 0).float().unsqueeze(1).contiguous()
+    return x, target
+
+
+def make_models(arch, encoder, classes, seed=0, presteps=0, x=None, target=None):
+    """(fp32 oracle, bf16-storage oracle, engine) with identical weights; `presteps` fp32 Adam steps of the oracle on
+    (x, target) first, so that the comparison is made on conditioned weights rather than on a random initialisation."""
+    from aadg_b200.nn import DeepLabV3Plus, Unet
+    from oracle import segnet_bf16
+    from oracle.segnet_torch import DeepLabV3PlusTorch, UnetTorch
+    torch.manual_seed(seed)
+    ref = (DeepLabV3PlusTorch if arch == "deeplabv3plus" else UnetTorch)(encoder, classes).cuda().train()
+    for m in ref.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    if presteps:
+        opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+        for _ in range(presteps):
+            logits, _ = ref(x)
+            loss = F.binary_cross_entropy(torch.sigmoid(logits), target)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        ref.zero_grad(set_to_none=True)
+    twin = segnet_bf16.install(copy.deepcopy(ref))
+    ctor = DeepLabV3Plus if arch == "deeplabv3plus" else Unet
+    net = ctor(encoder_name=encoder, encoder_weights=None, in_channels=3, classes=classes,
+               aux_params=dict(pooling="avg"))
+    net.load_state_dict(ref.state_dict())
+    net.dropout_enabled = False
+    return ref, twin, net
+
+
+def grad_table(net, ref):
+    """[(name, cosine, norm ratio)] of every parameter gradient of the engine against the oracle's"""
+    from test_nn_gpu import _my_grad_as_torch
+    rg = {k: v.grad for k, v in ref.named_parameters() if v.grad is not None}
+    rows = []
+    for name, p in net.named_params().items():
+        if name not in rg:
+            continue
+        g, w = _my_grad_as_torch(name, p).reshape(-1).double(), rg[name].reshape(-1).double()
+        if w.norm() < 1e-12:
+            continue
+        rows.append((name, (g @ w / (g.norm() * w.norm() + 1e-30)).item(), (g.norm() / w.norm()).item()))
+    return rows
+
+
+def oracle_step(model, x, target):
+    model.zero_grad(set_to_none=True)
+    logits, pooled = model(x)
+    loss = F.binary_cross_entropy(torch.sigmoid(logits), target)
+    loss.backward()
+    return logits.detach(), pooled.detach(), loss.item()
+
+
+CASES = [
+    # arch, encoder, classes, size, n, dataset
+    ("deeplabv3plus", "resnet18", 2, 128, 8, "optic"),
+    ("deeplabv3plus", "resnet50", 2, 512, 8, "optic"),          # BASELINE config 2 geometry (512^2, ResNet-50)
+    ("deeplabv3plus", "mobilenet_v2", 2, 256, 144, "optic"),    # the reference-native step: 144 x 256^2, MobileNetV2
+    ("unet", "resnet34", 1, 512, 4, "vessel"),                  # config 4 family at 512^2
+]
+
+
+@pytest.mark.parametrize("arch,encoder,classes,size,n,dataset", CASES)
+def test_engine_matches_bf16_storage_oracle(arch, encoder, classes, size, n, dataset):
+    """implementation parity: identical algorithm, identical rounding points => identical ReLU masks.
+    Bounds: loss 3e-4 relative, pooled feature 1e-2, every parameter-gradient cosine >= 0.99 with ZERO offenders and
+    norm ratio within 3 % (the engine rounds its gradient tensors to bf16, autograd keeps them in fp32)."""
+    x, target = make_data(n, size, classes, dataset=dataset)
+    ref, twin, net = make_models(arch, encoder, classes)
+    logits, pooled, loss = oracle_step(twin, x, target)
+    net.store.zero_grad()
+    out = net.loss_step(x, target, want_logits=True)
+    e_loss = abs(out["loss"].item() - loss) / abs(loss)
+    e_pool, e_logit = l2err(out["pooled"], pooled), l2err(out["logits"], logits)
+    rows = grad_table(net, twin)
+    worst = sorted(rows, key=lambda r: r[1])[:4]
+    off_ratio = [r for r in rows if not (0.97 < r[2] < 1.03)]
+    print("PARITY bf16-oracle %s/%s %d^2 n=%d: loss rel %.2e pooled %.2e logits %.2e | grads %d, min cos %.4f, "
+          "worst %s, ratio offenders %s" % (arch, encoder, size, n, e_loss, e_pool, e_logit, len(rows), worst[0][1],
+                                            [(w[0], round(w[1], 4)) for w in worst], off_ratio[:4]))
+    assert e_loss <= 3e-4, e_loss
+    assert e_pool <= 1e-2, e_pool
+    assert e_logit <= 5e-2, e_logit
+    assert worst[0][1] >= 0.99, worst
+    assert not off_ratio, off_ratio[:8]
+    del ref
+
+
+@pytest.mark.parametrize("arch,encoder,classes,size,n,dataset", CASES[:3])
+def test_engine_vs_fp32_oracle_on_conditioned_weights(arch, encoder, classes, size, n, dataset):
+    """the north-star tolerance against the PLAIN fp32 oracle, on weights conditioned by 12 fp32 Adam steps of the
+    oracle: loss within 5e-4 relative, logits within 2e-2 relative L2, Dice (samplewise F1) within 1e-3 absolute."""
+    from aadg_b200.nn.network import dice_from_counts
+    from oracle.segnet_torch import f1_samplewise
+    x, target = make_data(n, size, classes, dataset=dataset)
+    sub = slice(0, min(n, 16))     # conditioning uses a sub-batch (cheap); the comparison uses the whole batch
+    ref, twin, net = make_models(arch, encoder, classes, presteps=12, x=x[sub], target=target[sub])
+    logits, pooled, loss = oracle_step(ref, x, target)
+    _, _, loss_twin = oracle_step(twin, x, target)
+    net.store.zero_grad()
+    out = net.loss_step(x, target, want_logits=True)
+    e_loss = abs(out["loss"].item() - loss) / abs(loss)
+    e_pool, e_logit = l2err(out["pooled"], pooled), l2err(out["logits"], logits)
+    dice = dice_from_counts(out["counts"])
+    e_dice = max(abs(dice[k].item() - f1_samplewise(torch.sigmoid(logits)[:, k], target[:, k]).item())
+                 for k in range(classes))
+    rows = grad_table(net, ref)
+    worst = sorted(rows, key=lambda r: r[1])[:4]
+    print("PARITY fp32-oracle (conditioned) %s/%s %d^2 n=%d: loss %.5f rel %.2e (bf16-storage oracle alone: %.2e) pooled "
+          "%.2e logits %.2e dice abs %.2e | min grad cos %.4f %s" %
+          (arch, encoder, size, n, loss, e_loss, abs(loss_twin - loss) / abs(loss), e_pool, e_logit, e_dice, worst[0][1],
+           [(w[0], round(w[1], 4)) for w in worst]))
+    assert e_loss <= 5e-4, e_loss
+    assert e_logit <= 2e-2 and e_pool <= 2e-2, (e_logit, e_pool)
+    assert e_dice <= 1e-3, e_dice
+    assert worst[0][1] >= 0.95, worst
+
+
+def test_training_trajectory_50_steps_vs_fp32_oracle():
+    """50 Adam steps from identical weights on identical data (search_dg.py:140-142,164-172): the engine's loss curve
+    stays within 3 % of the fp32 oracle's and its Dice within 0.03 at every step (bf16-storage oracle on the CPU:
+    1.5 % / 0.02, DESIGN.md "Precision"); both learn (loss falls by > 10x)."""
+    from aadg_b200.nn.network import dice_from_counts
+    from oracle.segnet_torch import f1_samplewise
+    x, target = make_data(8, 128, 2)
+    ref, twin, net = make_models("deeplabv3plus", "resnet18", 2)
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    curve = []
+    for step in range(50):
+        logits, _ = ref(x)
+        loss = F.binary_cross_entropy(torch.sigmoid(logits), target)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        d_ref = f1_samplewise(torch.sigmoid(logits.detach())[:, 1], target[:, 1]).item()
+        net.store.zero_grad()
+        out = net.loss_step(x, target)
+        net.store.adam_step(1e-3)
+        curve.append((loss.item(), out["loss"].item(), d_ref, dice_from_counts(out["counts"])[1].item()))
+    rel = [abs(b - a) / a for a, b, _, _ in curve]
+    dd = [abs(d - c) for _, _, c, d in curve]
+    print("TRAJECTORY resnet18 128^2 n=8: loss %.4f -> oracle %.5f / engine %.5f; max rel %.3e at step %d; max dice diff "
+          "%.4f; step0 rel %.2e" % (curve[0][0], curve[-1][0], curve[-1][1], max(rel), int(np.argmax(rel)), max(dd), rel[0]))
+    assert rel[0] <= 1e-3, rel[0]
+    assert max(rel) <= 3e-2, (max(rel), int(np.argmax(rel)))
+    assert max(dd) <= 3e-2, max(dd)
+    assert curve[-1][1] < 0.1 * curve[0][1]

@@ -44,9 +44,10 @@ def test_step_rewards_match_oracle_on_the_same_features():
     captured = {}
     orig = SK.diversity_rewards
 
-    def spy(feat, dc, M, rewards=None):
+    def spy(feat, dc, M, rewards=None, max_cloud=None):
         captured["feat"], captured["dc"] = feat.cpu().numpy(), dc.cpu().numpy()
-        return orig(feat, dc, M, rewards)
+        assert max_cloud == 4                     # 12 sources over 3 domains
+        return orig(feat, dc, M, rewards, max_cloud=max_cloud)
     import aadg_b200.host.search as S
     S.SK.diversity_rewards = spy
     try:
@@ -75,3 +76,145 @@ def test_pretrain_step_learns_without_policies():
         losses.append(float(out["seg_loss"]))
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
     assert float(eng.rewards.abs().sum()) == 0.0
+
+
+class _Cfg:
+    class CONTROLLER:
+        EXCLUDE_OPS = []
+        L = 2
+        NUM_MAGS = 10
+        EXCLUDE_OPS_NUM = 0
+        PENALTY = 0.00001
+        LOSS = "reinforce"
+    SEED = 0
+
+
+def test_warmup_to_search_transition():
+    """search_dg.py:336-337 + scheduler.py:11: after the warm-up steps the first set_policies() copies the live
+    discriminator into its EMA twin and drops the model's learning rate by 10x (the discriminator's stays)."""
+    from aadg_b200.data.policy import parse_policies
+    from aadg_b200.host.search import SearchEngine
+    from aadg_b200.nn import DeepLabV3Plus
+    from aadg_b200.synth import fundus_batch, random_policies
+    model = DeepLabV3Plus(encoder_name="resnet18", classes=2)
+    eng = SearchEngine(model, n_domains=3, M=6, crop=64, lr=1e-3)
+    imgs, masks = fundus_batch(6, 64, 64, seed=4)
+    x, m = torch.from_numpy(imgs).cuda(), torch.from_numpy(masks).cuda()
+    for _ in range(3):
+        eng.pretrain_step(x, m, [0, 1, 2, 0, 1, 2])
+    dis = eng.discriminator
+    assert not torch.equal(dis.dis[0].weight, dis.mom_dis[0].weight)       # the live branch trained, the twin did not
+    assert abs(float(model.store.hyper[0]) - 1e-3) < 1e-9
+    eng.set_policies(parse_policies(random_policies(seed=3), _Cfg), epoch=3)
+    for q, k in dis._pairs():
+        assert torch.equal(q, k)
+    assert abs(float(model.store.hyper[0]) - 1e-4) < 1e-9 and abs(eng.lr - 1e-4) < 1e-12
+    assert eng.dis_optimizer.param_groups[0]["lr"] == 1e-3
+    out = eng.step(x, m, [0, 1, 2, 0, 1, 2])
+    assert np.isfinite(float(out["seg_loss"])) and torch.isfinite(eng.normalized_rewards()).all()
+    eng.set_policies(parse_policies(random_policies(seed=4), _Cfg), epoch=4)     # idempotent: no second drop
+    assert abs(float(model.store.hyper[0]) - 1e-4) < 1e-9
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """the captured step (graph=True) and the eager step walk the same trajectory: same decisions, same dropout seeds
+    and Adam step counts from device memory; differences are the summation order of the gradient atomics"""
+    from aadg_b200.data.policy import parse_policies
+    from aadg_b200.host.search import SearchEngine
+    from aadg_b200.nn import DeepLabV3Plus
+    from aadg_b200.synth import fundus_batch, random_policies
+    imgs, masks = fundus_batch(6, 64, 64, seed=11)
+    x, m = torch.from_numpy(imgs).cuda(), torch.from_numpy(masks).cuda()
+    curves = []
+    for graph in (False, True):
+        model = DeepLabV3Plus(encoder_name="resnet18", classes=2, seed=3)
+        eng = SearchEngine(model, n_domains=3, M=6, crop=64, graph=graph, seed=21)
+        eng.set_policies(parse_policies(random_policies(seed=3), _Cfg), epoch=0)
+        losses = [float(eng.step(x, m, [0, 1, 2, 0, 1, 2])["seg_loss"]) for _ in range(6)]
+        curves.append((losses, eng.rewards.cpu().numpy().copy(), int(model.store.step_dev.item()), model.steps,
+                       int(model.seed_dev.item())))
+        if graph:
+            assert len(eng._graphs) == 1 and list(eng._graphs.values())[0][0] is not None
+            assert list(eng._graphs.values())[0][0].launches > 100
+    (le, re_, se, te, de), (lg, rg, sg, tg, dg) = curves
+    print("GRAPH vs EAGER losses", le, lg)
+    assert (se, te, de) == (sg, tg, dg) == (6, 6, 0x5EED0000 + 3 + 6)
+    assert np.allclose(le, lg, rtol=2e-2) and abs(le[0] - lg[0]) <= 1e-5 * abs(le[0])
+    assert np.allclose(re_, rg, rtol=5e-2)
+    assert lg[-1] < lg[0]
+
+
+def test_diversity_rewards_general_path_for_large_clouds():
+    """clouds larger than the one-launch kernel's limit go through the streamed path: same rewards as the
+    float64 oracle; an empty domain raises instead of poisoning the rewards with NaN"""
+    from aadg_b200.ops import sinkhorn as SK
+    from aadg_b200.synth import feature_cloud
+    from oracle import sinkhorn as OS
+    M, per = 2, SK.small_max_points() + 6
+    rng = np.random.RandomState(0)
+    feats, dcs = [], []
+    for i in range(3 * per):
+        d = i % 3
+        for j in range(M):
+            feats.append(feature_cloud(1, 32, d, seed=1000 * j + i)[0] + 0.05 * j)
+            dc = np.full(3, 0.05, np.float32)
+            dc[d] = 0.9
+            dcs.append(dc)
+    f = torch.from_numpy(np.stack(feats).astype(np.float32)).cuda()
+    dc = torch.from_numpy(np.stack(dcs)).cuda()
+    rewards, pairs = SK.diversity_rewards(f, dc, M)
+    want, _ = OS.diversity_rewards(f.cpu().numpy(), dc.cpu().numpy(), M)
+    assert np.allclose(rewards.cpu().numpy(), want, rtol=2e-4), (rewards, want)
+    dc2 = dc.clone()
+    dc2[:, 2] = 0.0                                   # nobody belongs to domain 2 any more
+    with pytest.raises(RuntimeError):
+        SK.diversity_rewards(f, dc2, M)
+    small = SK.diversity_rewards(f[:12], dc2[:12], M)[0]          # fused kernel: NaN + status, caught at the boundary
+    with pytest.raises(RuntimeError):
+        SK.normalize_rewards(small)
+
+
+def test_reinforce_loss_runs_on_the_fused_controller():
+    """losses.py:96-114 with FusedController: graph-less sampled log-probs are rebuilt with a graph"""
+    from aadg_b200.host.controller import FusedController
+    from aadg_b200.host.losses import search_loss
+    ctl = FusedController(_Cfg, seed=2).cuda()
+    crit = search_loss(_Cfg)
+    opt = torch.optim.Adam(ctl.parameters(), lr=3.5e-4)
+    crit.register_optimizer(opt)
+    pol, _, _, logp, ent = ctl(6)
+    before = [p.detach().clone() for p in ctl.parameters()]
+    loss, score, e = crit(ctl, pol, logp, ent, torch.linspace(-1, 1, 6, device="cuda"))
+    assert torch.isfinite(loss) and any(not torch.equal(a, b) for a, b in zip(before, ctl.parameters()))
+    sd = ctl.state_dict()
+    assert sd["_extra_state"]["calls"] == 1
+    other = FusedController(_Cfg, seed=2).cuda()
+    other.load_state_dict(sd)
+    assert other.calls == 1
+
+
+def test_policy_call_shape_replays_the_reference_draws():
+    """data/policy.py:15-43 call shapes: `Policy(policy)(img, mask)` draws from the GLOBAL random / np.random state in the
+    reference's order, so it equals the bank applied to the rows `replay_sample` resolves under the same seeds (the
+    path pinned to reference-run goldens in test_u8_gpu.py)."""
+    import random
+    from aadg_b200.data import decisions as D
+    from aadg_b200.data.policy import MultiPolicy, Policy, parse_policies
+    from aadg_b200.ops import u8 as U8
+    from aadg_b200.synth import fundus_batch, random_policies
+    parsed = parse_policies(random_policies(seed=9), _Cfg)
+    imgs, masks = fundus_batch(1, 64, 80, seed=2)
+    x, m = torch.from_numpy(imgs).cuda(), torch.from_numpy(masks).cuda()
+    random.seed(5)
+    np.random.seed(5)
+    pols = [Policy(p) for p in parsed]
+    got = [pol(x[0], m[0]) for pol in pols]
+    py, npr = random.Random(5), np.random.RandomState(5)
+    rows, _ = D.replay_sample(parsed, 0, x.shape[2], x.shape[1], x.shape[2], (1, 1.5), py, npr, D.PolicyState(len(parsed)),
+                              scale_crop=False)
+    want, want_m = U8.apply_policy(x, m, rows, want_masks=True)
+    for j, (gi, gm) in enumerate(got):
+        assert gi.shape == x[0].shape and torch.equal(gi, want[j]) and torch.equal(gm, want_m[j])
+    multi = MultiPolicy(parsed, rng=(random.Random(5), np.random.RandomState(5)))
+    outs = multi(x[0])
+    assert len(outs) == len(parsed) and all(torch.equal(o[0], want[j]) and o[1] is None for j, o in enumerate(outs))
