@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 namespace aadg {
@@ -369,6 +370,140 @@ __global__ void __launch_bounds__(NT) pass_kernel(const PassArgs a) {
   }
 }
 
+// ---- streaming kernel: programs made only of pointwise steps (tables, Color, Cutout) ---------------------------
+// 9 of the 10 searchable ops are pointwise, so most rows never need a staged tile.  A thread owns pixel QUADS: four
+// consecutive pixels = 12 bytes = three 32-bit loads, and a warp's three load instructions cover 384 contiguous bytes;
+// the results leave as one 16-byte store per channel plane (MODE_F32: a warp writes 512 contiguous bytes per plane) or
+// three 32-bit stores (MODE_U8).  SQ quads per thread are loaded before the first use, so a CTA keeps
+// SQ * 12 B * 256 threads of reads in flight without any shared-memory staging or barrier in the loop.
+// Requires W % 4 == 0 (a quad never straddles a row) and 4-byte aligned images; other shapes use pass_kernel.
+constexpr int SQ = 4;             // quads per thread per iteration
+
+struct StreamArgs {
+  const DevRow* rows;
+  const PassItem* items;
+  const uint8_t* luts;
+  const uint8_t* src;
+  const uint8_t* scratch;
+  uint8_t* out_u8;
+  float* out_f32;
+  Stat* stats;
+  int H, W;
+  int quads_per_cta;              // multiple of NT * SQ
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs a) {
+  __shared__ __align__(16) uint8_t s_luts[AADG_MAX_OPS * 768];
+  __shared__ float s_f[768];                                       // normalised value of (composite) table entry
+  __shared__ __align__(16) uint8_t s_comp[768];
+  __shared__ unsigned int s_hist[MODE == MODE_STATS ? (NT / 32) * 768 : 1];
+  __shared__ DevRow s_row;
+
+  const PassItem it = a.items[blockIdx.y];
+  const int W = a.W, H = a.H;
+  const int tid = threadIdx.x;
+  if (tid < (int)(sizeof(DevRow) / 4)) ((int*)&s_row)[tid] = ((const int*)&a.rows[it.row])[tid];
+  const bool fast = it.pad_ != 0;
+  {
+    const uint4* g = (const uint4*)(a.luts + (size_t)it.row * AADG_MAX_OPS * 768);
+    uint4* sl = (uint4*)s_luts;
+    for (int i = tid; i < AADG_MAX_OPS * 768 / 16; i += NT) sl[i] = g[i];
+    if (MODE == MODE_STATS)
+      for (int i = tid; i < (NT / 32) * 768; i += NT) s_hist[i] = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < 768; i += NT) {
+    const int c = i >> 8;
+    int v = i & 255;
+    if (fast)
+      for (int k = it.s0; k < it.s1; ++k) v = s_luts[k * 768 + c * 256 + v];
+    s_comp[i] = (uint8_t)v;
+    s_f[i] = __fsub_rn(__fdiv_rn((float)v, 127.5f), 1.0f);          // Normalize_dg: x / 127.5 - 1
+  }
+  __syncthreads();
+  const DevRow& row = s_row;
+  const size_t plane = (size_t)H * W;
+  const uint8_t* base = it.base < 0 ? a.src + (size_t)row.src * plane * 3 : a.scratch + (size_t)it.base * plane * 3;
+  const uint32_t* in = (const uint32_t*)base;
+  const int n_quads = (int)(plane >> 2);
+  const int q_begin = blockIdx.x * a.quads_per_cta;
+  const int q_end = min(n_quads, q_begin + a.quads_per_cta);
+  const int wq = W >> 2;                       // quads per image row
+  unsigned int lsum = 0;
+
+  for (int q0 = q_begin + tid; q0 < q_end; q0 += NT * SQ) {
+    uint32_t w[SQ][3];
+#pragma unroll
+    for (int u = 0; u < SQ; ++u) {
+      const int q = q0 + u * NT;
+      if (q < q_end) {
+        const uint32_t* p = in + (size_t)q * 3;
+        w[u][0] = __ldg(p); w[u][1] = __ldg(p + 1); w[u][2] = __ldg(p + 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SQ; ++u) {
+      const int q = q0 + u * NT;
+      if (q >= q_end) break;
+      // bytes: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+      int vr[4], vg[4], vb[4];
+      vr[0] = w[u][0] & 255; vg[0] = (w[u][0] >> 8) & 255; vb[0] = (w[u][0] >> 16) & 255; vr[1] = w[u][0] >> 24;
+      vg[1] = w[u][1] & 255; vb[1] = (w[u][1] >> 8) & 255; vr[2] = (w[u][1] >> 16) & 255; vg[2] = w[u][1] >> 24;
+      vb[2] = w[u][2] & 255; vr[3] = (w[u][2] >> 8) & 255; vg[3] = (w[u][2] >> 16) & 255; vb[3] = w[u][2] >> 24;
+      if (!fast) {
+        const int y = q / wq, x0 = (q - y * wq) << 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          for (int k = it.s0; k < it.s1; ++k) apply_point(row.s[k], s_luts + k * 768, x0 + i, y, vr[i], vg[i], vb[i]);
+      }
+      if (MODE == MODE_STATS) {
+        unsigned int* hh = s_hist + (tid >> 5) * 768;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = fast ? s_comp[vr[i]] : vr[i], g = fast ? s_comp[256 + vg[i]] : vg[i],
+                    b = fast ? s_comp[512 + vb[i]] : vb[i];
+          atomicAdd(&hh[r], 1u); atomicAdd(&hh[256 + g], 1u); atomicAdd(&hh[512 + b], 1u);
+          lsum += luma_u8(r, g, b);
+        }
+      } else if (MODE == MODE_U8) {
+        if (fast) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { vr[i] = s_comp[vr[i]]; vg[i] = s_comp[256 + vg[i]]; vb[i] = s_comp[512 + vb[i]]; }
+        }
+        uint32_t* o = (uint32_t*)(a.out_u8 + (size_t)it.out * plane * 3) + (size_t)q * 3;
+        o[0] = vr[0] | (vg[0] << 8) | (vb[0] << 16) | (vr[1] << 24);
+        o[1] = vg[1] | (vb[1] << 8) | (vr[2] << 16) | (vg[2] << 24);
+        o[2] = vb[2] | (vr[3] << 8) | (vg[3] << 16) | (vb[3] << 24);
+      } else {
+        // fast: s_f holds the normalised composite table per channel; otherwise entries 0..255 of every channel block
+        // are the plain normalisation map (s_comp is the identity then)
+        const float* tr = s_f;
+        const float* tg = s_f + 256;
+        const float* tb = s_f + 512;
+        float* o = a.out_f32 + (size_t)it.out * 3 * plane + ((size_t)q << 2);
+        __stcs((float4*)o, make_float4(tr[vr[0]], tr[vr[1]], tr[vr[2]], tr[vr[3]]));
+        __stcs((float4*)(o + plane), make_float4(tg[vg[0]], tg[vg[1]], tg[vg[2]], tg[vg[3]]));
+        __stcs((float4*)(o + 2 * plane), make_float4(tb[vb[0]], tb[vb[1]], tb[vb[2]], tb[vb[3]]));
+      }
+    }
+  }
+
+  if (MODE == MODE_STATS) {
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    Stat* st = a.stats + it.out;
+    for (int i = tid; i < 768; i += NT) {
+      unsigned int v = 0;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) v += s_hist[w * 768 + i];
+      if (v) atomicAdd(&st->hist[0][0] + i, v);
+    }
+    if ((tid & 31) == 0 && lsum) atomicAdd(&st->luma_sum, (unsigned long long)lsum);
+  }
+}
+
 // ---- look-up table construction ------------------------------------------------------------------
 // One CTA of 256 threads per (row, step): thread i owns entry i of the three channel tables.
 struct LutItem { int row; int step; };
@@ -698,6 +833,42 @@ static Layout layout(int n_rows, int n_src, int H, int W) {
   return L;
 }
 
+static int num_sms_u8() {
+  static int v = 0;
+  if (!v) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+  }
+  return v;
+}
+
+// items [0, n) are pointwise-only programs on a quad-aligned shape: the streaming kernel
+template <int MODE>
+static int launch_stream(const PassArgs& base, const PassItem* d_items, int n, cudaStream_t st) {
+  if (n == 0) return AADG_OK;
+  StreamArgs a{};
+  a.rows = base.rows; a.luts = base.luts; a.src = base.src; a.scratch = base.scratch;
+  a.out_u8 = base.out_u8; a.out_f32 = base.out_f32; a.stats = base.stats; a.H = base.H; a.W = base.W;
+  const long long n_quads = (long long)base.H * base.W / 4;
+  // CTAs per image: enough CTAs for ~6 waves of 8 resident CTAs per SM when the batch is small, at least one
+  // iteration's worth of quads each, at most 64 iterations (amortises the per-CTA table set-up)
+  const int unit = NT * SQ;
+  long long want_ctas = (8LL * 6 * num_sms_u8() + n - 1) / n;
+  long long per = (n_quads + want_ctas - 1) / want_ctas;
+  per = std::max<long long>(unit, std::min<long long>(per, 64LL * unit));
+  per = (per + unit - 1) / unit * unit;
+  a.quads_per_cta = (int)per;
+  const int chunks = (int)((n_quads + per - 1) / per);
+  for (int done = 0; done < n; done += 65535) {
+    a.items = d_items + done;
+    dim3 grid(chunks, std::min(n - done, 65535));
+    stream_kernel<MODE><<<grid, NT, 0, st>>>(a);
+  }
+  return check_launch("aug_u8 stream kernel");
+}
+
 template <int MODE>
 static int launch_pass(const PassArgs& base, const PassItem* d_items, int n, cudaStream_t st) {
   if (n == 0) return AADG_OK;
@@ -732,6 +903,17 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
     return AADG_ENOSPC;
   }
   char* w = (char*)ws;
+  // pointwise-only programs go to the streaming kernel (quad-aligned shapes): put them first in every list
+  const bool can_stream = (W % 4 == 0) && (((uintptr_t)src_images & 3) == 0) && (!out_u8 || ((uintptr_t)out_u8 & 3) == 0) &&
+                          (!out_f32 || ((uintptr_t)out_f32 & 15) == 0);
+  auto split = [&](std::vector<PassItem>& v) -> int {
+    if (!can_stream) return 0;
+    auto mid = std::stable_partition(v.begin(), v.end(), [](const PassItem& it) { return it.sharp < 0 && !it.gather; });
+    return (int)(mid - v.begin());
+  };
+  const int ns_src = split(pl.src_stats), ns_fin = split(pl.fin);
+  int ns_mat[AADG_MAX_OPS], ns_stat[AADG_MAX_OPS];
+  for (int k = 0; k < AADG_MAX_OPS; ++k) { ns_mat[k] = split(pl.mat[k]); ns_stat[k] = split(pl.stat[k]); }
   // one host blob -> one copy: rows, then every launch's item list back to back
   std::vector<PassItem> items;
   std::vector<LutItem> litems;
@@ -765,15 +947,20 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
   const PassItem* d_items = (const PassItem*)(w + L.items);
   const LutItem* d_litems = (const LutItem*)(w + L.lut_items);
 
-  rc = launch_pass<MODE_STATS>(a, d_items + o_src, (int)pl.src_stats.size(), st);
-  if (rc) return rc;
+  // a list = [streamable | tiled]: two launches
+#define AADG_U8_LAUNCH(MODE, ARGS, OFF, NS, N)                                          \
+  {                                                                                     \
+    rc = launch_stream<MODE>(ARGS, d_items + (OFF), (NS), st);                          \
+    if (rc) return rc;                                                                  \
+    rc = launch_pass<MODE>(ARGS, d_items + (OFF) + (NS), (N) - (NS), st);               \
+    if (rc) return rc;                                                                  \
+  }
+  AADG_U8_LAUNCH(MODE_STATS, a, o_src, ns_src, (int)pl.src_stats.size())
   for (int k = 0; k < AADG_MAX_OPS; ++k) {
     PassArgs am = a;
     am.out_u8 = (uint8_t*)(w + L.scratch);
-    rc = launch_pass<MODE_U8>(am, d_items + o_mat[k], (int)pl.mat[k].size(), st);
-    if (rc) return rc;
-    rc = launch_pass<MODE_STATS>(a, d_items + o_stat[k], (int)pl.stat[k].size(), st);
-    if (rc) return rc;
+    AADG_U8_LAUNCH(MODE_U8, am, o_mat[k], ns_mat[k], (int)pl.mat[k].size())
+    AADG_U8_LAUNCH(MODE_STATS, a, o_stat[k], ns_stat[k], (int)pl.stat[k].size())
     if (!pl.lut[k].empty()) {
       lut_kernel<<<(unsigned)pl.lut[k].size(), 256, 0, st>>>(a.rows, d_litems + o_lut[k], (uint8_t*)(w + L.luts),
                                                             a.stats, H * W);
@@ -785,8 +972,7 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
     AADG_REQUIRE(out_u8, "null out_u8");
     PassArgs af = a;
     af.out_u8 = out_u8;
-    rc = launch_pass<MODE_U8>(af, d_items + o_fin, n_rows, st);
-    if (rc) return rc;
+    AADG_U8_LAUNCH(MODE_U8, af, o_fin, ns_fin, n_rows)
     if (out_masks) {
       AADG_REQUIRE(src_masks, "out_masks requested without src_masks");
       dim3 grid(std::min((H * W + 255) / 256, 1024), n_rows);
@@ -797,8 +983,7 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
     if (out_f32) {
       PassArgs af = a;
       af.out_f32 = out_f32;
-      rc = launch_pass<MODE_F32>(af, d_items + o_fin, n_rows, st);
-      if (rc) return rc;
+      AADG_U8_LAUNCH(MODE_F32, af, o_fin, ns_fin, n_rows)
     }
     if (out_labels) {
       AADG_REQUIRE(src_masks, "out_labels requested without src_masks");

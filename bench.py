@@ -145,15 +145,19 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm on host cores (oracle port; /root/reference does not exist on the box)
 # ---------------------------------------------------------------------------------------------------
-def _aug_one_source(job):
-    """worker: the oracle's DGMultiPolicy -> DGRandomScaleCrop -> Normalize_dg -> ToTensor for ONE source image
-    (its M = 6 augmented copies), the unit a DataLoader worker of the reference processes (data/optic.py:79-91)"""
-    import numpy as _np
+def _worker_init():
+    """augmentation workers are single-threaded numpy (the model's torch threads belong to the parent)"""
     try:
         import torch as _t
         _t.set_num_threads(1)
     except Exception:
         pass
+
+
+def _aug_one_source(job):
+    """worker: the oracle's DGMultiPolicy -> DGRandomScaleCrop -> Normalize_dg -> ToTensor for ONE source image
+    (its M = 6 augmented copies), the unit a DataLoader worker of the reference processes (data/optic.py:79-91)"""
+    import numpy as _np
     from oracle import u8_policy as OP
     img, mask, rows, crop, dataset = job
     rows = rows.copy()
@@ -188,7 +192,7 @@ class CpuReference:
         self.model = (DeepLabV3PlusTorch if a.arch == "deeplabv3plus" else UnetTorch)(a.backbone, classes).train()
         self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3)
         self.clouds = [feature_cloud(8, 128, k, seed=k) for k in range(d)]
-        self.pool = mp.get_context("fork").Pool(min(self.cores, n_src)) if n_src > 1 else None
+        self.pool = mp.get_context("fork").Pool(min(self.cores, n_src), initializer=_worker_init) if n_src > 1 else None
         self.step_idx = 0
         self.split = {}
 

@@ -86,6 +86,8 @@ class _Cfg:
         EXCLUDE_OPS_NUM = 0
         PENALTY = 0.00001
         LOSS = "reinforce"
+        T = 2
+        C = 2.5
     SEED = 0
 
 
