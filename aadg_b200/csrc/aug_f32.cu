@@ -296,6 +296,275 @@ __global__ void __launch_bounds__(128) op_kernel(const OpArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// backward: gradients of  out = clamp(mk * clamp(op(x, m)) + (1 - mk) * x)  with respect to x, the per-sample
+// magnitude m_b and the per-sample mask mk_b, as torch autograd computes them through the reference's code
+// (operations.py:73-100, functional.py): clamp passes the gradient where lo <= v <= hi (inclusive), the straight
+// -through estimators of functional.py:21-46 send the gradient of Solarize / Posterize to the MAGNITUDE only (summed)
+// and of AutoContrast / Equalize straight to the image, Contrast's rounded mean and the look-up tables carry none.
+// ---------------------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  const float* x; const float* go; float* gx;
+  const float* mag; const float* mask; const int* perm;
+  const PlaneStat* ps; const SampleStat* ss;
+  float* gmag; float* gmask;
+  int B, H, W, op, scatter;
+};
+
+__device__ __forceinline__ float gate01(float v) { return (v >= 0.f && v <= 1.f) ? 1.f : 0.f; }
+
+// forward-mode duals over the directions (x_r, x_g, x_b, m): used for Hue, whose Jacobian goes through HSV
+struct Dual { float v; float d[4]; };
+__device__ __forceinline__ Dual dconst(float v) { Dual r; r.v = v; r.d[0] = r.d[1] = r.d[2] = r.d[3] = 0.f; return r; }
+__device__ __forceinline__ Dual dvar(float v, int k) { Dual r = dconst(v); r.d[k] = 1.f; return r; }
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { a.v += b.v; for (int i = 0; i < 4; ++i) a.d[i] += b.d[i]; return a; }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { a.v -= b.v; for (int i = 0; i < 4; ++i) a.d[i] -= b.d[i]; return a; }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) {
+  Dual r; r.v = a.v * b.v;
+  for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+  return r;
+}
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+  Dual r; r.v = a.v / b.v;
+  for (int i = 0; i < 4; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v;
+  return r;
+}
+__device__ __forceinline__ Dual dshift(Dual a, float c) { a.v += c; return a; }      // + constant (floor terms)
+__device__ __forceinline__ void hue_dual(float xr, float xg, float xb, float m, Dual out[3]) {
+  const Dual r = dvar(xr, 0), g = dvar(xg, 1), b = dvar(xb, 2), mm = dvar(m, 3);
+  const Dual mx = (xr >= xg && xr >= xb) ? r : (xg >= xb ? g : b);
+  const Dual mn = (xr <= xg && xr <= xb) ? r : (xg <= xb ? g : b);
+  const Dual d = mx - mn;
+  const Dual v = mx;
+  const Dual s = mx.v > 0.f ? d / mx : dconst(0.f);
+  Dual h = dconst(0.f);
+  if (d.v > 0.f) {
+    Dual hh;
+    if (mx.v == xr) { hh = (g - b) / d; hh = dshift(hh, -6.f * floorf(hh.v / 6.f)); }
+    else if (mx.v == xg) hh = dshift((b - r) / d, 2.f);
+    else hh = dshift((r - g) / d, 4.f);
+    hh = hh * dconst(1.f / 6.f);
+    h = dshift(hh, -floorf(hh.v));
+  }
+  h = h + mm;
+  h = dshift(h, -floorf(h.v));
+  const Dual h6 = h * dconst(6.f);
+  const float fi = floorf(h6.v);
+  const Dual f = dshift(h6, -fi);
+  const Dual one = dconst(1.f);
+  const Dual p = v * (one - s), q = v * (one - f * s), t = v * (one - (one - f) * s);
+  int i = (int)fi % 6;
+  if (i < 0) i += 6;
+  switch (i) {
+    case 0: out[0] = v; out[1] = t; out[2] = p; break;
+    case 1: out[0] = q; out[1] = v; out[2] = p; break;
+    case 2: out[0] = p; out[1] = v; out[2] = t; break;
+    case 3: out[0] = p; out[1] = q; out[2] = v; break;
+    case 4: out[0] = t; out[1] = p; out[2] = v; break;
+    default: out[0] = v; out[1] = p; out[2] = q; break;
+  }
+}
+
+// grid (x chunks, H, B), one pixel per thread-iteration
+__global__ void __launch_bounds__(128) op_bwd_kernel(const BwdArgs a) {
+  const int b = blockIdx.z, y = blockIdx.y;
+  const int H = a.H, W = a.W;
+  const size_t HW = (size_t)H * W;
+  const float m = a.mag ? a.mag[b] : 0.f;
+  const float mk = a.mask ? a.mask[b] : 1.f;
+  const float omk = __fsub_rn(1.f, mk);
+  const float* xb = a.x + (size_t)b * 3 * HW;
+  const float* gob = a.go + (size_t)b * 3 * HW;
+  float* gxb = a.gx + (size_t)b * 3 * HW;
+  OpArgs fa{};
+  fa.x = a.x; fa.mag = a.mag; fa.mask = a.mask; fa.perm = a.perm; fa.ps = a.ps; fa.ss = a.ss; fa.B = a.B; fa.H = H; fa.W = W;
+  fa.op = a.op;
+  float acc_mag = 0.f, acc_mask = 0.f;
+  for (int xx = blockIdx.x * blockDim.x + threadIdx.x; xx < W; xx += gridDim.x * blockDim.x) {
+    const size_t i = (size_t)y * W + xx;
+    const float xv[3] = {xb[i], xb[HW + i], xb[2 * HW + i]};
+    float yv[3];
+    eval_op(fa, b, y, xx, m, yv[0], yv[1], yv[2]);      // the forward value (blend ops: already clamped)
+    float gy[3], gdir[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float yc = clamp01(yv[c]);
+      const float pre = __fadd_rn(__fmul_rn(mk, yc), __fmul_rn(omk, xv[c]));
+      const float g1 = gob[c * HW + i] * gate01(pre);
+      acc_mask += g1 * (yc - xv[c]);
+      gdir[c] = g1 * omk;
+      gy[c] = g1 * mk * gate01(yv[c]);                     // tensor_function's clamp of the op output
+    }
+    float gxo[3] = {0.f, 0.f, 0.f};                        // the op's contribution to d/dx at THIS pixel
+    switch (a.op) {
+      case HFLIP: case VFLIP: {
+        const size_t j = a.op == HFLIP ? (size_t)y * W + (W - 1 - xx) : (size_t)(H - 1 - y) * W + xx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(gxb + c * HW + j, gy[c]);
+        break;
+      }
+      case SHEAR_X: case SHEAR_Y: case TRANSLATE_X: case TRANSLATE_Y: case ROTATE: {
+        double m00 = 1, m01 = 0, m02 = 0, m10 = 0, m11 = 1, m12 = 0;
+        const double mg = (double)m;
+        if (a.op == SHEAR_X) m01 = mg;
+        else if (a.op == SHEAR_Y) m10 = mg;
+        else if (a.op == TRANSLATE_X) m02 = mg * W;
+        else if (a.op == TRANSLATE_Y) m12 = mg * H;
+        else {
+          const double ang = mg * 0.017453292519943295, c = cos(ang), s = sin(ang);
+          const double cx = (W - 1) * 0.5, cy = (H - 1) * 0.5;
+          m00 = c; m01 = s; m02 = (1 - c) * cx - s * cy;
+          m10 = -s; m11 = c; m12 = s * cx + (1 - c) * cy;
+        }
+        const double det = m00 * m11 - m01 * m10;
+        const double i00 = m11 / det, i01 = -m01 / det, i10 = -m10 / det, i11 = m00 / det;
+        const double i02 = -(i00 * m02 + i01 * m12), i12 = -(i10 * m02 + i11 * m12);
+        const float sx = (float)(i00 * xx + i01 * y + i02), sy = (float)(i10 * xx + i11 * y + i12);
+        const float fx0 = floorf(sx), fy0 = floorf(sy);
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const float fx = sx - fx0, fy = sy - fy0;
+        // d(source coordinate)/d(magnitude) of the INVERSE map
+        float dsx = 0.f, dsy = 0.f;
+        if (a.op == SHEAR_X) dsx = -(float)y;
+        else if (a.op == SHEAR_Y) dsy = -(float)xx;
+        else if (a.op == TRANSLATE_X) dsx = -(float)W;
+        else if (a.op == TRANSLATE_Y) dsy = -(float)H;
+        else { dsx = -(sy - (H - 1) * 0.5f) * 0.017453292519943295f; dsy = (sx - (W - 1) * 0.5f) * 0.017453292519943295f; }
+        float v[3][2][2];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int xi = x0 + dx, yi = y0 + dy;
+            const bool in = xi >= 0 && xi < W && yi >= 0 && yi < H;
+            const size_t j = in ? (size_t)yi * W + xi : 0;
+            const float wgt = (dy ? fy : 1.f - fy) * (dx ? fx : 1.f - fx);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              v[c][dy][dx] = in ? xb[c * HW + j] : 0.f;
+              if (in && gy[c] != 0.f) atomicAdd(gxb + c * HW + j, wgt * gy[c]);
+            }
+          }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float dIdx = (1.f - fy) * (v[c][0][1] - v[c][0][0]) + fy * (v[c][1][1] - v[c][1][0]);
+          const float dIdy = (1.f - fx) * (v[c][1][0] - v[c][0][0]) + fx * (v[c][1][1] - v[c][0][1]);
+          acc_mag += gy[c] * (dIdx * dsx + dIdy * dsy);
+        }
+        break;
+      }
+      case INVERT: for (int c = 0; c < 3; ++c) gxo[c] = -gy[c]; break;
+      case SOLARIZE: case POSTERIZE: acc_mag += gy[0] + gy[1] + gy[2]; break;                 // STE: magnitude only
+      case AUTO_CONTRAST: case EQUALIZE: for (int c = 0; c < 3; ++c) gxo[c] = gy[c]; break;     // STE: straight to the image
+      case GRAY: {
+        const float t = gy[0] + gy[1] + gy[2];
+        gxo[0] = 0.299f * t; gxo[1] = 0.587f * t; gxo[2] = 0.110f * t;
+        break;
+      }
+      case CONTRAST: {
+        const float mean = __fdiv_rn(floorf((float)(a.ss[b].gray_sum / (double)HW) + 0.5f), 255.f);
+        const float al = __fsub_rn(1.f, m);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float t = __fadd_rn(mean, __fmul_rn(al, __fsub_rn(xv[c], mean)));
+          const float gt = gy[c] * gate01(t);
+          gxo[c] = gt * al;
+          acc_mag -= gt * (xv[c] - mean);
+        }
+        break;
+      }
+      case SATURATE: {
+        const float gr = gray_of(xv[0], xv[1], xv[2]), al = __fsub_rn(1.f, m);
+        float gsum = 0.f, gt[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float t = __fadd_rn(gr, __fmul_rn(al, __fsub_rn(xv[c], gr)));
+          gt[c] = gy[c] * gate01(t);
+          gsum += gt[c];
+          acc_mag -= gt[c] * (xv[c] - gr);
+        }
+        const float wc[3] = {0.299f, 0.587f, 0.110f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gxo[c] = gt[c] * al + wc[c] * (1.f - al) * gsum;
+        break;
+      }
+      case BRIGHTNESS: {
+        const float al = __fsub_rn(1.f, m);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float gt = gy[c] * gate01(__fmul_rn(al, xv[c]));
+          gxo[c] = gt * al;
+          acc_mag -= gt * xv[c];
+        }
+        break;
+      }
+      case HUE: {
+        Dual o[3];
+        hue_dual(xv[0], xv[1], xv[2], m, o);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          gxo[0] += gy[c] * o[c].d[0]; gxo[1] += gy[c] * o[c].d[1]; gxo[2] += gy[c] * o[c].d[2];
+          acc_mag += gy[c] * o[c].d[3];
+        }
+        break;
+      }
+      case SAMPLE_PAIRING: {
+        const float* xo = a.x + (size_t)a.perm[b] * 3 * HW;
+        float* gxp = a.gx + (size_t)a.perm[b] * 3 * HW;
+        const float om = __fsub_rn(1.f, m);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          gxo[c] = gy[c] * om;
+          atomicAdd(gxp + c * HW + i, gy[c] * m);
+          acc_mag += gy[c] * (xo[c * HW + i] - xv[c]);
+        }
+        break;
+      }
+      case SHARPNESS: {
+        const float k1 = __fdiv_rn(1.f, 13.f), k5 = __fdiv_rn(5.f, 13.f);
+        const float al = __fsub_rn(1.f, m);
+        float blur[3] = {0.f, 0.f, 0.f};
+        size_t js[9];
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const size_t j = (size_t)reflect(y + dy, H) * W + reflect(xx + dx, W);
+            js[(dy + 1) * 3 + dx + 1] = j;
+            const float k = (dy == 0 && dx == 0) ? k5 : k1;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) blur[c] = __fadd_rn(blur[c], __fmul_rn(k, xb[c * HW + j]));
+          }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float t = __fadd_rn(blur[c], __fmul_rn(al, __fsub_rn(xv[c], blur[c])));
+          const float gt = gy[c] * gate01(t);
+          gxo[c] = gt * al;
+          acc_mag -= gt * (xv[c] - blur[c]);
+          const float gb = gt * (1.f - al);
+          if (gb != 0.f)
+#pragma unroll
+            for (int q = 0; q < 9; ++q) atomicAdd(gxb + c * HW + js[q], gb * (q == 4 ? k5 : k1));
+        }
+        break;
+      }
+      default: break;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = gdir[c] + gxo[c];
+      if (a.scatter) { if (t != 0.f) atomicAdd(gxb + c * HW + i, t); }
+      else gxb[c * HW + i] = t;
+    }
+  }
+  acc_mag = warp_sum(acc_mag);
+  acc_mask = warp_sum(acc_mask);
+  if ((threadIdx.x & 31) == 0) {
+    if (a.gmag && acc_mag != 0.f) atomicAdd(a.gmag + b, acc_mag);
+    if (a.gmask && acc_mask != 0.f) atomicAdd(a.gmask + b, acc_mask);
+  }
+}
+
 }  // namespace f32
 }  // namespace aadg
 
@@ -338,6 +607,44 @@ int aadg_f32_op(int op, const float* x, int batch, int h, int w, const float* ma
   dim3 grid(std::max(1, std::min((w / 4 + 127) / 128, 8)), h, batch);
   op_kernel<<<grid, 128, 0, st>>>(a);
   return check_launch("f32 op kernel");
+}
+
+/* Backward of aadg_f32_op: given go = d(loss)/d(out) (float32 [batch,3,h,w]) writes gx = d/dx (same shape) and
+ * ACCUMULATES nothing: gmag / gmask (float32 [batch], may be NULL) receive d/d(mag_b) and d/d(mask_b).  Gradient
+ * semantics are torch autograd's through data/operations.py:73-100 and data/functional.py (inclusive clamp gates, the
+ * straight-through estimators of functional.py:21-46).  Same workspace as the forward call. */
+int aadg_f32_op_backward(int op, const float* x, const float* go, int batch, int h, int w, const float* mag,
+                         const float* mask, const int32_t* perm, float* gx, float* gmag, float* gmask, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  AADG_REQUIRE(op >= 0 && op < OP_COUNT, "unknown op %d", op);
+  AADG_REQUIRE(batch > 0 && h > 0 && w > 0 && x && go && gx && gx != x && gx != go, "bad arguments");
+  AADG_REQUIRE(op != SAMPLE_PAIRING || perm, "SamplePairing needs a permutation");
+  AADG_REQUIRE(h <= 65535 && batch <= 65535, "image too tall / batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdArgs a{};
+  a.x = x; a.go = go; a.gx = gx; a.mag = mag; a.mask = mask; a.perm = perm; a.gmag = gmag; a.gmask = gmask;
+  a.B = batch; a.H = h; a.W = w; a.op = op;
+  a.scatter = (op <= ROTATE && op != INVERT) || op == SAMPLE_PAIRING || op == SHARPNESS;
+  if (op == CONTRAST || op == AUTO_CONTRAST || op == EQUALIZE) {
+    if (!workspace || workspace_bytes < aadg_f32_workspace_bytes(batch)) {
+      set_error("workspace too small");
+      return AADG_ENOSPC;
+    }
+    PlaneStat* ps = (PlaneStat*)workspace;
+    SampleStat* ss = (SampleStat*)((char*)workspace + align_up(sizeof(PlaneStat) * 3 * (size_t)batch, 256));
+    const int planes = 3 * batch;
+    init_stats_kernel<<<(planes * 256 + 255) / 256, 256, 0, st>>>(ps, ss, planes, batch);
+    dim3 sg(std::max(1, std::min((h * w + 255) / 256, 64)), batch);
+    stats_kernel<<<sg, 256, 0, st>>>(x, h * w, ps, ss, op == EQUALIZE);
+    if (op != CONTRAST) lut_kernel<<<planes, 256, 0, st>>>(ps, op);
+    a.ps = ps; a.ss = ss;
+  }
+  if (a.scatter) AADG_CUDA_TRY(cudaMemsetAsync(gx, 0, sizeof(float) * 3 * (size_t)batch * h * w, st));
+  if (gmag) AADG_CUDA_TRY(cudaMemsetAsync(gmag, 0, sizeof(float) * batch, st));
+  if (gmask) AADG_CUDA_TRY(cudaMemsetAsync(gmask, 0, sizeof(float) * batch, st));
+  dim3 grid(std::max(1, std::min((w + 127) / 128, 8)), h, batch);
+  op_bwd_kernel<<<grid, 128, 0, st>>>(a);
+  return check_launch("f32 op backward kernel");
 }
 
 }  // extern "C"

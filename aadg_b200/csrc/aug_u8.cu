@@ -935,6 +935,9 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
     AADG_CUDA_TRY(cudaMemcpyAsync(w + L.lut_items, litems.data(), sizeof(LutItem) * litems.size(), cudaMemcpyHostToDevice, st));
   if (pl.n_stat_slots)
     AADG_CUDA_TRY(cudaMemsetAsync(w + L.stats, 0, sizeof(Stat) * pl.n_stat_slots, st));
+  // the kernels stage a row's whole table block [MAX_OPS][768] in shared memory, including the slots of steps that are
+  // not tables (never indexed): keep those bytes defined
+  AADG_CUDA_TRY(cudaMemsetAsync(w + L.luts, 0, (size_t)n_rows * AADG_MAX_OPS * 768, st));
 
   PassArgs a{};
   a.rows = (const DevRow*)(w + L.rows);

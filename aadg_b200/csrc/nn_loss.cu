@@ -185,6 +185,45 @@ __global__ void loss_bwd_kernel(const float* z, int N, int h, int w, int K, cons
   }
 }
 
+// transpose of the align_corners bilinear up-sampling for an ARBITRARY incoming gradient: dz[n,iy,ix,k] = sum over the
+// outputs (oy,ox) that sample cell (iy,ix) of weight * dlogits[n,k,oy,ox] (the autograd surface: the caller computed
+// its own loss on the full-resolution logits, search_dg.py:140-142,170)
+__global__ void upsample_logits_bwd_kernel(const float* dlogits, int N, int h, int w, int K, int H, int W, float* dz) {
+  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const long long total = (long long)N * h * w * K;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % K);
+    long long q = e / K;
+    const int ix = (int)(q % w); q /= w;
+    const int iy = (int)(q % h);
+    const int n = (int)(q / h);
+    const float* gn = dlogits + ((size_t)n * K + k) * H * W;
+    const int oy_lo = sy > 0.f ? max(0, (int)floorf((float)(iy - 1) / sy)) : 0;
+    const int oy_hi = sy > 0.f ? min(H - 1, (int)ceilf((float)(iy + 1) / sy)) : H - 1;
+    const int ox_lo = sx > 0.f ? max(0, (int)floorf((float)(ix - 1) / sx)) : 0;
+    const int ox_hi = sx > 0.f ? min(W - 1, (int)ceilf((float)(ix + 1) / sx)) : W - 1;
+    float acc = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1; float ly;
+      src_index(oy, sy, h, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        int x0, x1; float lx;
+        src_index(ox, sx, w, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx == 0.f) continue;
+        acc = fmaf(wy * wx, gn[(size_t)oy * W + ox], acc);
+      }
+    }
+    dz[e] = acc;
+  }
+}
+
 // Scatter form of the same gradient for the up-sampling factor smp uses (H = 4h, W = 4w): a CTA owns a 64 x 64
 // block of output pixels of one (image, class); a thread owns a 4 x 4 patch (four float4 target loads), evaluates
 // the up-sampled logit from a shared-memory copy of the low-resolution logits, folds its 16 gradients into the
@@ -490,6 +529,17 @@ int aadg_seg_loss_bwd(const float* z, int n, int h, int w, int classes, const fl
   const int blocks = (int)std::min<long long>((total + 127) / 128, 148 * 32);
   loss_bwd_kernel<<<std::max(blocks, 1), 128, 0, (cudaStream_t)stream>>>(z, n, h, w, classes, target, H, W, grad_scale, dz);
   return check_launch("seg_loss_bwd");
+}
+
+/* dz fp32 [n,h,w,classes] = transpose of the head's bilinear (align_corners=True) up-sampling applied to an arbitrary
+ * gradient dlogits fp32 [n,classes,H,W] */
+int aadg_upsample_logits_bwd(const float* dlogits, int n, int h, int w, int classes, int H, int W, float* dz, void* stream) {
+  AADG_REQUIRE(classes >= 1 && classes <= MAXK && n > 0 && h > 0 && w > 0 && H >= h && W >= w, "bad sizes");
+  AADG_REQUIRE(dlogits && dz, "null pointer");
+  const long long total = (long long)n * h * w * classes;
+  const int blocks = (int)std::min<long long>((total + 127) / 128, 148 * 32);
+  upsample_logits_bwd_kernel<<<std::max(blocks, 1), 128, 0, (cudaStream_t)stream>>>(dlogits, n, h, w, classes, H, W, dz);
+  return check_launch("upsample_logits_bwd");
 }
 
 /* da bf16 [pixels][ldda] = dz . w ; dw fp32 [classes][c] += dz^T a ; db fp32 [classes] += sum dz */

@@ -3,9 +3,11 @@
 Same class names, constructor arguments, `magnitude` / `probability` properties and `forward(input)`:
     training: out = clamp(mask*op(x, mag) + (1-mask)*x), mask ~ RelaxedBernoulli(temperature, p)
     eval:     mask ~ Bernoulli(p); the op replaces the selected rows
-Forward values only (the reference's straight-through gradients belong to Faster-AutoAugment's policy
-search, which AADG does not use).  `forward` does not modify its input (the reference's eval branch writes
-into it in place)."""
+Differentiable like the reference's: in training mode the output carries a graph to the image, to `_magnitude` and
+(through the RelaxedBernoulli sample) to `_probability`; the backward pass is one CUDA kernel per op
+(aadg_f32_op_backward) with torch autograd's semantics through the reference code, straight-through estimators
+included (functional.py:21-46).  `forward` does not modify its input (the reference's eval branch writes into it in
+place)."""
 import torch
 from torch import nn
 from torch.distributions import RelaxedBernoulli, Bernoulli
@@ -63,14 +65,16 @@ class _Operation(nn.Module):
 
     def forward(self, input):
         b = input.size(0)
-        mask = self.get_mask(b).reshape(b).detach()
+        mask = self.get_mask(b).reshape(b)
         mag = self.magnitude
         if mag is not None:
-            mag = mag.detach().reshape(-1).expand(b) if mag.numel() == 1 else mag.detach()
+            mag = mag.reshape(-1).expand(b) if mag.numel() == 1 else mag
             if self.flip_magnitude:
                 mag = torch.randint(2, (b,), dtype=torch.float32, device=input.device).mul_(2).sub_(1) * mag
         perm = torch.randperm(b, device=input.device) if self.op_name == "SamplePairing" else None
-        return _f32.apply(self.op_name, input, mag, mask, perm)
+        if self.training and torch.is_grad_enabled():
+            return _f32.differentiable(self.op_name, input, mag, mask, perm)
+        return _f32.apply(self.op_name, input, None if mag is None else mag.detach(), mask.detach(), perm)
 
 
 def _make(name, has_mag=True, flip=False, scale=1, default_mag=0.5):

@@ -114,6 +114,13 @@ class ParamStore:
     def refresh(self):
         """bf16 (and transposed) copies of the convolution weights from the fp32 masters."""
         K.weight_prep(self.params, self.wb, self.wbt, self.descs, self.n_descs)
+        self._synced_version = self.params._version
+
+    def sync(self):
+        """refresh the bf16 copies if a torch in-place op (an optimizer stepping the parameter leaves, copy_) touched the
+        masters since the last refresh; the engine's own Adam kernels refresh by themselves"""
+        if self.params._version != getattr(self, "_synced_version", -1):
+            self.refresh()
 
     def zero_grad(self):
         self.grads.zero_()
@@ -865,6 +872,52 @@ class UnetDecoder:
         return d, d_skips
 
 
+class _SegNetFunction(torch.autograd.Function):
+    """`logits, pooled = model(x)` with an autograd node behind it, so that the reference's own lines
+    `seg_loss.backward(); model_optimizer.step()` (search_dg.py:170-172) drive the engine: backward receives
+    d(loss)/d(logits) (and, if the pooled feature was used undetached, its gradient), runs the engine's explicit backward
+    pass and leaves the parameter gradients in the flat buffer that the `.grad` of every `model.parameters()` leaf views."""
+
+    @staticmethod
+    def forward(ctx, net, x, *leaves):
+        dec, pooled = net.features(x)
+        z = net._head(dec)
+        n, _, hh, ww = x.shape
+        logits = torch.empty((n, net.classes, hh, ww), dtype=torch.float32, device=x.device)
+        K.seg_loss_fwd(z, torch.zeros_like(logits), 0.5, torch.zeros(1, dtype=torch.float64, device=x.device),
+                       torch.zeros((n, net.classes, 3), dtype=torch.int32, device=x.device), logits)
+        ctx.net, ctx.dec, ctx.z_shape = net, dec, tuple(z.shape)
+        ctx.set_materialize_grads(False)
+        return logits, pooled
+
+    @staticmethod
+    def backward(ctx, dlogits, dpooled):
+        net, dec = ctx.net, ctx.dec
+        net._bind_grads()
+        if dlogits is None:
+            dlogits = torch.zeros((dec.shape[0], net.classes, ctx.z_shape[1] * 4, ctx.z_shape[2] * 4), device=dec.device)
+        dz = K.upsample_logits_bwd(dlogits.float(), ctx.z_shape)
+        ddec = torch.empty(dec.shape, dtype=BF16, device=dec.device)
+
+        def add_pooled(d_last):
+            if dpooled is not None:       # pooled = mean over pixels of the last encoder map
+                hw = d_last.shape[1] * d_last.shape[2]
+                K.broadcast_add_pixels(dpooled.float().contiguous(), d_last, 1.0 / hw)
+            return d_last
+        if net.arch == "unet":
+            K.seg_head3x3_bwd(dz, dec, net.head_w.data, ddec, net.head_w.grad, net.head_b.grad)
+            d_last, d_skips = net.decoder.backward(ddec)
+            net.encoder.backward(add_pooled(d_last), d_skips=d_skips)
+        else:
+            K.seg_head_bwd(dz, dec, net.head_w.data, ddec, net.head_w.grad, net.head_b.grad)
+            d_last, d_high = net.decoder.backward(ddec)
+            net.encoder.backward(add_pooled(d_last), d_high)
+        net.steps += 1
+        if net.dropout_enabled:
+            net.seed_dev += 1
+        return (None, None) + (None,) * len(net._leaves)
+
+
 class SegNet:
     """encoder + decoder + segmentation head (Conv2d(256, classes, 1) -> UpsamplingBilinear2d(4)) and the
     patched classification head (AdaptiveAvgPool2d(1) + flatten of the last encoder map, models/heads.py:14-25)."""
@@ -900,6 +953,10 @@ class SegNet:
                                      lambda s: (torch.rand(s) * 2 - 1) * bound)
         self.store.finalize()
         torch.random.set_rng_state(gen_state)
+        # torch.nn.Module-like parameter surface: one leaf tensor per parameter, a VIEW of the flat fp32 master buffer,
+        # whose .grad is a view of the flat gradient buffer -- torch.optim.Adam(model.parameters()) updates the masters
+        # in place (the bf16 weight copies are refreshed lazily: ParamStore.sync())
+        self._leaves = [p.data.requires_grad_(True) for p in self.store.items]
         self.training = True
         self.dropout_seed = 0x5EED0000 + seed
         self.dropout_enabled = True      # Dropout(0.5) of the ASPP projection (train mode)
@@ -920,7 +977,27 @@ class SegNet:
         return self
 
     def parameters(self):
-        return [p.data for p in self.store.items]
+        return list(self._leaves)
+
+    def named_parameters(self):
+        return [(p.name, leaf) for p, leaf in zip(self.store.items, self._leaves)]
+
+    def zero_grad(self, set_to_none=True):
+        for leaf in self._leaves:
+            leaf.grad = None
+        self.store.zero_grad()
+
+    def _bind_grads(self):
+        """before a backward pass through the autograd surface: every leaf's .grad is its slice of the flat gradient
+        buffer; after `optimizer.zero_grad()` (set_to_none, the default) the buffer starts from zero, otherwise the
+        new gradients accumulate onto the old ones like torch's"""
+        if all(leaf.grad is None for leaf in self._leaves):
+            self.store.grads.zero_()
+        for p, leaf in zip(self.store.items, self._leaves):
+            if leaf.grad is None:
+                leaf.grad = p.grad
+            elif leaf.grad.data_ptr() != p.grad.data_ptr():
+                raise RuntimeError("parameter %s: .grad was replaced by a foreign tensor" % p.name)
 
     def named_params(self):
         return {p.name: p for p in self.store.items}
@@ -997,6 +1074,7 @@ class SegNet:
         """encoder + decoder; returns (decoder map bf16 [N,H/4,W/4,256], pooled encoder feature fp32 [N,C])."""
         if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3):
             raise ValueError("input must be CUDA float32 [N,3,H,W]")
+        self.store.sync()
         feats = self.encoder.forward(x.contiguous(), self.training)
         last = feats[-1]
         pooled = K.global_sum(last, 1.0 / (last.shape[1] * last.shape[2]))
@@ -1013,7 +1091,10 @@ class SegNet:
         return K.seg_head_fwd(dec, self.head_w.data, self.head_b.data)
 
     def __call__(self, x):
-        """smp call shape: (logits float32 [N,classes,H,W], pooled feature float32 [N,C_enc])."""
+        """smp call shape: (logits float32 [N,classes,H,W], pooled feature float32 [N,C_enc]).  In training mode with
+        autograd enabled the outputs carry a graph (see _SegNetFunction): `loss.backward()` runs the engine's backward."""
+        if self.training and torch.is_grad_enabled():
+            return _SegNetFunction.apply(self, x.detach(), *self._leaves)
         dec, pooled = self.features(x)
         z = self._head(dec)
         n, _, hh, ww = x.shape

@@ -225,6 +225,16 @@ def seg_loss_bwd(z, target, grad_scale):
     return dz
 
 
+def upsample_logits_bwd(dlogits, z_shape):
+    """dlogits fp32 [n,k,H,W] -> dz fp32 [n,h,w,k] (transpose of the head's align_corners bilinear up-sampling)"""
+    n, h, w, k = z_shape
+    dlogits = dlogits.contiguous()
+    assert dlogits.is_cuda and dlogits.dtype == torch.float32 and dlogits.shape[:2] == (n, k)
+    dz = torch.empty((n, h, w, k), dtype=torch.float32, device=dlogits.device)
+    _call("aadg_upsample_logits_bwd", p(dlogits), n, h, w, k, dlogits.shape[2], dlogits.shape[3], p(dz))
+    return dz
+
+
 def seg_head_bwd(dz, a, w, da, dw, db):
     n, h, wd, c = a.shape
     _call("aadg_seg_head_bwd", p(dz), p(a), n * h * wd, c, _ld(a), p(w), w.shape[0], p(da), _ld(da), p(dw), p(db))

@@ -115,6 +115,14 @@ int aadg_u8_scale_crop_normalize(const uint8_t* images, int image_by_row, const 
 size_t aadg_f32_workspace_bytes(int batch);
 int aadg_f32_op(int op, const float* x, int batch, int h, int w, const float* mag, const float* mask,
                 const int32_t* perm, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of aadg_f32_op (the point of the reference's bank: operations.py:73-108 draws a RelaxedBernoulli mask and
+ * functional.py:21-46 uses straight-through estimators so that probabilities and magnitudes can be learned): given go =
+ * d(loss)/d(out) writes gx = d/dx [batch,3,h,w] and gmag / gmask float32 [batch] (either may be NULL) = d/d(mag_b),
+ * d/d(mask_b).  torch autograd's semantics through the reference code: clamp gates inclusive, Solarize / Posterize send
+ * their gradient to the magnitude only (summed), AutoContrast / Equalize straight to the image. */
+int aadg_f32_op_backward(int op, const float* x, const float* go, int batch, int h, int w, const float* mag,
+                         const float* mask, const int32_t* perm, float* gx, float* gmag, float* gmask, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sinkhorn diversity reward — replaces geomloss.SamplesLoss("sinkhorn", cost=<cosine KeOps formula>,
@@ -297,6 +305,10 @@ int aadg_seg_loss_fwd(const float* z, int n, int h, int w, int classes, const fl
                       double* loss_sum, int* counts, float* logits_out, void* stream);
 int aadg_seg_loss_bwd(const float* z, int n, int h, int w, int classes, const float* target, int H, int W,
                       float grad_scale, float* dz, void* stream);
+/* transpose of the head's UpsamplingBilinear2d for an ARBITRARY gradient: dz fp32 [n,h,w,classes] from dlogits fp32
+ * [n,classes,H,W] -- what `seg_loss.backward()` (search_dg.py:170) sends into the network when the caller computes its
+ * own loss on `model(x)`'s logits (the autograd surface of aadg_b200.nn) */
+int aadg_upsample_logits_bwd(const float* dlogits, int n, int h, int w, int classes, int H, int W, float* dz, void* stream);
 int aadg_seg_head_bwd(const float* dz, const void* a, long long pixels, int c, int lda, const float* w, int classes,
                       void* da, int ldda, float* dw, float* db, void* stream);
 

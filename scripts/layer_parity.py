@@ -20,7 +20,7 @@ BF = torch.bfloat16
 
 
 def nhwc(x):
-    return x.permute(0, 2, 3, 1).contiguous()
+    return x.permute(0, 2, 3, 1).clone(memory_format=torch.contiguous_format)
 
 
 def nchw(x):
@@ -65,7 +65,13 @@ def main():
             if cname in io:
                 xin, want = io[cname]
                 got = C.fprop(nhwc(xin).to(BF), o.w.bf16, o.k, o.k, o.stride, o.pad, o.dil)
-                rows.append((l2(nchw(got), want), "conv", cname, tuple(xin.shape), "k%d s%d d%d" % (o.k, o.stride, o.dil)))
+                # the same convolution in float64 (bf16-rounded weights), rounded to bf16: tells the oracle's own fp32
+                # algorithm error (cuDNN may pick Winograd / FFT) from the engine's
+                m = mods[cname]
+                w64 = m.weight.detach().to(BF).double()
+                exact = torch.nn.functional.conv2d(xin.double(), w64, None, m.stride, m.padding, m.dilation).to(BF).float()
+                rows.append((l2(nchw(got), want), "conv", cname, tuple(xin.shape), "k%d s%d d%d | engine vs fp64: %.2e, "
+                             "oracle vs fp64: %.2e" % (o.k, o.stride, o.dil, l2(nchw(got), exact), l2(want, exact))))
                 walk_bn(o.bn, want, relu=o.relu, relu6=o.relu6)
         elif isinstance(o, NW.Depthwise3x3):
             cname = o.w.name[:-len(".weight")]
@@ -96,7 +102,14 @@ def main():
         y = torch.empty_like(xi)
         K.bn_apply(xi, buf[4], buf[5], y, relu=False)
         rounded = bool(torch.equal(want, want.to(BF).float()))
-        rows.append((l2(nchw(y), want), "bn" if rounded else "bn(unrounded oracle: expect ~1e-3)", bn.name, tuple(xin.shape), ""))
+        # float64 statistics of the same tensor: how far are the engine's (and torch's) mean / invstd from exact?
+        x64 = conv_out.double()
+        mean64 = x64.mean((0, 2, 3))
+        inv64 = (x64.var((0, 2, 3), unbiased=False) + NW.BN_EPS).rsqrt()
+        e_mean = ((buf[2].double() - mean64).abs() * inv64).max().item()          # in units of sigma
+        e_inv = ((buf[3].double() - inv64).abs() / inv64).max().item()
+        rows.append((l2(nchw(y), want), "bn" if rounded else "bn(unrounded oracle: expect ~1e-3)", bn.name, tuple(xin.shape),
+                     "| engine stats vs fp64: mean %.1e sigma, invstd rel %.1e" % (e_mean, e_inv)))
         # fused statistics of the convolution epilogue vs the separate pass, on the same tensor
     walk(net.encoder)
     walk(net.decoder)
@@ -104,15 +117,19 @@ def main():
     if hasattr(net.encoder, "stem_w"):
         cname = net.encoder.stem_w.name[:-len(".weight")]
         xin, want = io[cname]
+        m = mods[cname]
+        exact = torch.nn.functional.conv2d(xin.double(), m.weight.detach().to(BF).double(), None, m.stride, m.padding,
+                                           m.dilation).to(BF).float()
         if enc == "mobilenet_v2":
             col = K.im2col_stem(xin.contiguous(), 3, 3, 2, 1, 3 * NW.MBV2_STEM_RP, row_pitch=NW.MBV2_STEM_RP)
         else:
             col = K.im2col_stem(xin.contiguous(), 7, 7, 2, 3, NW.STEM_KP, row_pitch=NW.STEM_RP)
         got = C.fprop(col, net.encoder.stem_w.bf16, 1, 1)
-        rows.append((l2(nchw(got), want), "stem conv", cname, tuple(xin.shape), ""))
+        rows.append((l2(nchw(got), want), "stem conv", cname, tuple(xin.shape), "| engine vs fp64: %.2e, oracle vs fp64: %.2e" %
+                     (l2(nchw(got), exact), l2(want, exact))))
     rows.sort(reverse=True)
     print("== teacher-forced per-layer residuals (%s/%s %d^2 n=%d), worst first ==" % (arch, enc, size, n))
-    for r in rows[:25]:
+    for r in rows[:40]:
         print("  %.3e  %-10s %-45s %s %s" % r)
     print("  ... %d layers, median %.3e" % (len(rows), sorted(r[0] for r in rows)[len(rows) // 2]))
 

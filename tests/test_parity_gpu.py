@@ -199,3 +199,46 @@ def test_training_trajectory_50_steps_vs_fp32_oracle():
     assert max(rel) <= 3e-2, (max(rel), int(np.argmax(rel)))
     assert max(dd) <= 3e-2, max(dd)
     assert curve[-1][1] < 0.1 * curve[0][1]
+
+
+def test_autograd_surface_runs_the_reference_training_lines():
+    """`seg_output, feature = model(input)` ... `model_optimizer.zero_grad(); seg_loss.backward(); model_optimizer.step()`
+    (search_dg.py:132,140-142,170-172) verbatim, with torch.optim.Adam over `model.parameters()`, against the engine's own
+    fused loss_step + Adam on an identical model: same losses, same gradients, same parameters after three steps."""
+    from aadg_b200.nn import DeepLabV3Plus
+    M = 2
+    x, target = make_data(6, 64, 2)
+    nets = [DeepLabV3Plus(encoder_name="resnet18", encoder_weights=None, in_channels=3, classes=2,
+                          aux_params=dict(pooling="avg"), seed=4) for _ in range(2)]
+    a, b = nets
+    assert torch.equal(a.store.params, b.store.params)
+    model_optimizer = torch.optim.Adam(b.parameters(), lr=1e-3)
+    model_criterion = torch.nn.BCELoss()
+    for step in range(3):
+        seg_output, feature = b(x)
+        assert seg_output.requires_grad and seg_output.shape == (6, 2, 64, 64) and feature.shape == (6, 512)
+        seg_soft = torch.sigmoid(seg_output)
+        seg_loss = torch.mean(torch.stack([model_criterion(seg_soft[j::M], target[j::M]) for j in range(M)]))
+        model_optimizer.zero_grad()
+        seg_loss.backward()
+        a.store.zero_grad()
+        out = a.loss_step(x, target)
+        rel = abs(seg_loss.item() - out["loss"].item()) / out["loss"].item()
+        ga, gb = a.store.grads.double(), b.store.grads.double()
+        cos = (ga @ gb / (ga.norm() * gb.norm())).item()
+        print("AUTOGRAD step %d: loss rel %.2e grad cos %.6f norm ratio %.5f" % (step, rel, cos, (gb.norm() / ga.norm()).item()))
+        assert rel <= (1e-5 if step == 0 else 2e-3), (step, rel)
+        assert cos >= (0.9999 if step == 0 else 0.99), (step, cos)
+        for name, leaf in b.named_parameters():
+            assert leaf.grad is not None and leaf.grad.data_ptr() == b.named_params()[name].grad.data_ptr()
+        model_optimizer.step()
+        a.store.adam_step(1e-3)
+    assert l2err(b.store.params, a.store.params) <= 2e-3
+    # the pooled feature is differentiable too (the reference detaches it; a caller need not)
+    b.zero_grad()
+    seg_output, feature = b(x)
+    feature.square().mean().backward()
+    g = b.store.grads
+    assert torch.isfinite(g).all() and float(g.abs().sum()) > 0
+    dec_w = b.named_params()["decoder.block2.1.weight"].grad
+    assert float(dec_w.abs().sum()) == 0.0            # nothing flowed through the decoder
