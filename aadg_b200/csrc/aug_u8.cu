@@ -504,6 +504,159 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs a) {
   }
 }
 
+// ---- streaming stencil kernel: [pointwise steps] Sharpness [pointwise steps] -------------------------------------------
+// Same quad ownership as stream_kernel, for programs that contain ONE Sharpness step and no gather.  A WARP owns a strip
+// of 128 pixels x `rows_per_band` image rows and walks DOWN it: per image row a thread loads the five 32-bit words that
+// hold its four pixels plus one neighbour on each side (a warp's loads cover 384 contiguous bytes + 2 words), applies the
+// steps before the stencil to those six pixels ONCE, converts them to float ONCE, forms the two horizontal partial sums
+// Pillow's SMOOTH needs from a row -- (a*k1 + b*k1) + c*k1 when the row is above / below the centre and
+// (a*k1 + b*k5) + c*k1 when it is the centre row -- and keeps them in registers for the three output rows that use
+// them.  Output row y = ((0.5 + A(y+1)) + B(y)) + A(y-1): the float operation order of ImagingFilter3x3, bit for bit.
+// No shared-memory tile, no barrier in the loop; every image byte is loaded (rows+2)/rows times per strip.
+struct SharpRow {            // what a thread keeps of one image row: partial sums and the (pre-stepped) centre pixels
+  float A[4][3], B[4][3];
+  int c[4][3];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NT) stencil_kernel(const StreamArgs a) {
+  __shared__ __align__(16) uint8_t s_luts[AADG_MAX_OPS * 768];
+  __shared__ float s_f[256];
+  __shared__ unsigned int s_hist[MODE == MODE_STATS ? (NT / 32) * 768 : 1];
+  __shared__ DevRow s_row;
+
+  const PassItem it = a.items[blockIdx.y];
+  const int W = a.W, H = a.H;
+  const int tid = threadIdx.x;
+  if (tid < (int)(sizeof(DevRow) / 4)) ((int*)&s_row)[tid] = ((const int*)&a.rows[it.row])[tid];
+  {
+    const uint4* g = (const uint4*)(a.luts + (size_t)it.row * AADG_MAX_OPS * 768);
+    uint4* sl = (uint4*)s_luts;
+    for (int i = tid; i < AADG_MAX_OPS * 768 / 16; i += NT) sl[i] = g[i];
+    s_f[tid] = __fsub_rn(__fdiv_rn((float)tid, 127.5f), 1.0f);
+    if (MODE == MODE_STATS)
+      for (int i = tid; i < (NT / 32) * 768; i += NT) s_hist[i] = 0;
+  }
+  __syncthreads();
+  const DevRow& row = s_row;
+  const size_t plane = (size_t)H * W;
+  const uint8_t* base = it.base < 0 ? a.src + (size_t)row.src * plane * 3 : a.scratch + (size_t)it.base * plane * 3;
+  const uint32_t* in = (const uint32_t*)base;
+  const int wq = W >> 2;                        // quads per row
+  const int row_words = wq * 3;
+  const int RB = a.quads_per_cta;               // here: image rows per band
+  const int strips = (wq + 31) >> 5, bands = (H + RB - 1) / RB;
+  const DevStep sharp = row.s[it.sharp];
+  const bool in01 = sharp.f >= 0.f && sharp.f <= 1.f;
+  const float k1 = __fdiv_rn(1.0f, 13.0f), k5 = __fdiv_rn(5.0f, 13.0f);
+  const bool has_pre = it.sharp > it.s0, has_post = it.sharp + 1 < it.s1;
+  unsigned int lsum = 0;
+
+  const int unit = blockIdx.x * (NT / 32) + (tid >> 5);          // (strip, band) of this warp
+  const int qx = (unit % strips) * 32 + (tid & 31);
+  const int band = unit / strips;
+  if (band < bands && qx < wq) {
+    const int x0 = qx << 2;
+    const int y_begin = band * RB, y_end = min(H, y_begin + RB);
+
+    // load image row yy (clamped: rows outside the image are only ever neighbours of pass-through border rows)
+    auto load_row = [&](int yy, SharpRow& R) {
+      const int yc = min(max(yy, 0), H - 1);
+      const uint32_t* p = in + (size_t)yc * row_words + qx * 3;
+      uint32_t w[5];
+      w[0] = qx > 0 ? __ldg(p - 1) : 0u;
+      w[1] = __ldg(p); w[2] = __ldg(p + 1); w[3] = __ldg(p + 2);
+      w[4] = qx + 1 < wq ? __ldg(p + 3) : 0u;
+      float f[6][3];
+#pragma unroll
+      for (int px = 0; px < 6; ++px) {
+        int v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int k = 3 * (px - 1) + c + 4;          // byte index inside the 20 loaded bytes
+          v[c] = (w[k >> 2] >> (8 * (k & 3))) & 255;
+        }
+        if (has_pre)
+          for (int k = it.s0; k < it.sharp; ++k) apply_point(row.s[k], s_luts + k * 768, x0 - 1 + px, yc, v[0], v[1], v[2]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          f[px][c] = (float)v[c];
+          if (px >= 1 && px <= 4) R.c[px - 1][c] = v[c];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float l = __fmul_rn(f[i][c], k1), r = __fmul_rn(f[i + 2][c], k1);
+          R.A[i][c] = __fadd_rn(__fadd_rn(l, __fmul_rn(f[i + 1][c], k1)), r);
+          R.B[i][c] = __fadd_rn(__fadd_rn(l, __fmul_rn(f[i + 1][c], k5)), r);
+        }
+    };
+
+    SharpRow up, mid, dn;                       // image rows y-1, y, y+1
+    load_row(y_begin - 1, up);
+    load_row(y_begin, mid);
+    for (int y = y_begin; y < y_end; ++y) {
+      load_row(y + 1, dn);
+      int vr[4], vg[4], vb[4];
+      const bool row_in = y >= 1 && y <= H - 2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i;
+        int v[3] = {mid.c[i][0], mid.c[i][1], mid.c[i][2]};
+        if (row_in && x >= 1 && x <= W - 2) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float ss = __fadd_rn(0.5f, dn.A[i][c]);
+            ss = __fadd_rn(ss, mid.B[i][c]);
+            ss = __fadd_rn(ss, up.A[i][c]);
+            const int d = ss <= 0.f ? 0 : (ss >= 255.f ? 255 : (int)ss);
+            v[c] = blend_u8(d, v[c], sharp.f, in01);
+          }
+        }
+        if (has_post)
+          for (int k = it.sharp + 1; k < it.s1; ++k) apply_point(row.s[k], s_luts + k * 768, x, y, v[0], v[1], v[2]);
+        vr[i] = v[0]; vg[i] = v[1]; vb[i] = v[2];
+      }
+      const size_t q = (size_t)y * wq + qx;
+      if (MODE == MODE_STATS) {
+        unsigned int* hh = s_hist + (tid >> 5) * 768;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          atomicAdd(&hh[vr[i]], 1u); atomicAdd(&hh[256 + vg[i]], 1u); atomicAdd(&hh[512 + vb[i]], 1u);
+          lsum += luma_u8(vr[i], vg[i], vb[i]);
+        }
+      } else if (MODE == MODE_U8) {
+        uint32_t* o = (uint32_t*)(a.out_u8 + (size_t)it.out * plane * 3) + q * 3;
+        o[0] = vr[0] | (vg[0] << 8) | (vb[0] << 16) | (vr[1] << 24);
+        o[1] = vg[1] | (vb[1] << 8) | (vr[2] << 16) | (vg[2] << 24);
+        o[2] = vb[2] | (vr[3] << 8) | (vg[3] << 16) | (vb[3] << 24);
+      } else {
+        float* o = a.out_f32 + (size_t)it.out * 3 * plane + (q << 2);
+        __stcs((float4*)o, make_float4(s_f[vr[0]], s_f[vr[1]], s_f[vr[2]], s_f[vr[3]]));
+        __stcs((float4*)(o + plane), make_float4(s_f[vg[0]], s_f[vg[1]], s_f[vg[2]], s_f[vg[3]]));
+        __stcs((float4*)(o + 2 * plane), make_float4(s_f[vb[0]], s_f[vb[1]], s_f[vb[2]], s_f[vb[3]]));
+      }
+      up = mid; mid = dn;
+    }
+  }
+
+  if (MODE == MODE_STATS) {
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    Stat* st = a.stats + it.out;
+    for (int i = tid; i < 768; i += NT) {
+      unsigned int v = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < NT / 32; ++w2) v += s_hist[w2 * 768 + i];
+      if (v) atomicAdd(&st->hist[0][0] + i, v);
+    }
+    if ((tid & 31) == 0 && lsum) atomicAdd(&st->luma_sum, (unsigned long long)lsum);
+  }
+}
+
 // ---- look-up table construction ------------------------------------------------------------------
 // One CTA of 256 threads per (row, step): thread i owns entry i of the three channel tables.
 struct LutItem { int row; int step; };
@@ -869,6 +1022,31 @@ static int launch_stream(const PassArgs& base, const PassItem* d_items, int n, c
   return check_launch("aug_u8 stream kernel");
 }
 
+// items [0, n): one Sharpness step, no gather, quad-aligned shape: the streaming stencil kernel
+template <int MODE>
+static int launch_stencil(const PassArgs& base, const PassItem* d_items, int n, cudaStream_t st) {
+  if (n == 0) return AADG_OK;
+  StreamArgs a{};
+  a.rows = base.rows; a.luts = base.luts; a.src = base.src; a.scratch = base.scratch;
+  a.out_u8 = base.out_u8; a.out_f32 = base.out_f32; a.stats = base.stats; a.H = base.H; a.W = base.W;
+  const int wq = base.W / 4;
+  const int strips = (wq + 31) / 32;
+  // rows per warp-strip: 32 (6 % halo re-reads) when the batch alone fills the GPU, fewer rows (more warps) when it
+  // does not: aim at ~6 waves of 8 resident CTAs per SM, never below 8 rows
+  const long long want_warps = (8LL * 6 * num_sms_u8() * (NT / 32) + n - 1) / n;
+  long long rb = ((long long)strips * base.H + want_warps - 1) / want_warps;
+  rb = std::max<long long>(8, std::min<long long>(rb, 32));
+  a.quads_per_cta = (int)rb;                                                         // image rows per band here
+  const long long units = (long long)strips * ((base.H + rb - 1) / rb);
+  const int chunks = (int)((units + NT / 32 - 1) / (NT / 32));
+  for (int done = 0; done < n; done += 65535) {
+    a.items = d_items + done;
+    dim3 grid(chunks, std::min(n - done, 65535));
+    stencil_kernel<MODE><<<grid, NT, 0, st>>>(a);
+  }
+  return check_launch("aug_u8 stencil kernel");
+}
+
 template <int MODE>
 static int launch_pass(const PassArgs& base, const PassItem* d_items, int n, cudaStream_t st) {
   if (n == 0) return AADG_OK;
@@ -906,13 +1084,18 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
   // pointwise-only programs go to the streaming kernel (quad-aligned shapes): put them first in every list
   const bool can_stream = (W % 4 == 0) && (((uintptr_t)src_images & 3) == 0) && (!out_u8 || ((uintptr_t)out_u8 & 3) == 0) &&
                           (!out_f32 || ((uintptr_t)out_f32 & 15) == 0);
-  auto split = [&](std::vector<PassItem>& v) -> int {
-    if (!can_stream) return 0;
-    auto mid = std::stable_partition(v.begin(), v.end(), [](const PassItem& it) { return it.sharp < 0 && !it.gather; });
-    return (int)(mid - v.begin());
+  // class 0: pointwise only (stream_kernel), 1: one Sharpness, no gather (stencil_kernel), 2: the tile kernel
+  struct Split { int stream, stencil; };
+  auto split = [&](std::vector<PassItem>& v) -> Split {
+    if (!can_stream) return Split{0, 0};
+    auto cls = [](const PassItem& it) { return it.gather ? 2 : (it.sharp >= 0 ? 1 : 0); };
+    std::stable_sort(v.begin(), v.end(), [&](const PassItem& x, const PassItem& y) { return cls(x) < cls(y); });
+    Split r{0, 0};
+    for (const PassItem& it : v) { r.stream += cls(it) == 0; r.stencil += cls(it) == 1; }
+    return r;
   };
-  const int ns_src = split(pl.src_stats), ns_fin = split(pl.fin);
-  int ns_mat[AADG_MAX_OPS], ns_stat[AADG_MAX_OPS];
+  const Split ns_src = split(pl.src_stats), ns_fin = split(pl.fin);
+  Split ns_mat[AADG_MAX_OPS], ns_stat[AADG_MAX_OPS];
   for (int k = 0; k < AADG_MAX_OPS; ++k) { ns_mat[k] = split(pl.mat[k]); ns_stat[k] = split(pl.stat[k]); }
   // one host blob -> one copy: rows, then every launch's item list back to back
   std::vector<PassItem> items;
@@ -950,13 +1133,15 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
   const PassItem* d_items = (const PassItem*)(w + L.items);
   const LutItem* d_litems = (const LutItem*)(w + L.lut_items);
 
-  // a list = [streamable | tiled]: two launches
-#define AADG_U8_LAUNCH(MODE, ARGS, OFF, NS, N)                                          \
-  {                                                                                     \
-    rc = launch_stream<MODE>(ARGS, d_items + (OFF), (NS), st);                          \
-    if (rc) return rc;                                                                  \
-    rc = launch_pass<MODE>(ARGS, d_items + (OFF) + (NS), (N) - (NS), st);               \
-    if (rc) return rc;                                                                  \
+  // a list = [pointwise | stencil | tiled]: up to three launches
+#define AADG_U8_LAUNCH(MODE, ARGS, OFF, NS, N)                                                              \
+  {                                                                                                         \
+    rc = launch_stream<MODE>(ARGS, d_items + (OFF), (NS).stream, st);                                       \
+    if (rc) return rc;                                                                                      \
+    rc = launch_stencil<MODE>(ARGS, d_items + (OFF) + (NS).stream, (NS).stencil, st);                       \
+    if (rc) return rc;                                                                                      \
+    rc = launch_pass<MODE>(ARGS, d_items + (OFF) + (NS).stream + (NS).stencil, (N) - (NS).stream - (NS).stencil, st); \
+    if (rc) return rc;                                                                                      \
   }
   AADG_U8_LAUNCH(MODE_STATS, a, o_src, ns_src, (int)pl.src_stats.size())
   for (int k = 0; k < AADG_MAX_OPS; ++k) {

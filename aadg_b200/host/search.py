@@ -55,6 +55,36 @@ def average_(flat):
     return flat
 
 
+def shutdown(engines=(), timeout_s=30.0):
+    """orderly end of a distributed run: captured graphs released, device drained, process group destroyed.  NCCL's
+    communicator teardown has been seen to wait forever when kernels of the communicator were captured into a CUDA graph;
+    the destroy call therefore runs under a watchdog and the process exits hard (status 0) if it does not return."""
+    import gc
+    import os
+    import sys
+    import threading
+    for e in engines:
+        e.close()
+    gc.collect()
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    torch.cuda.synchronize()
+    done = threading.Event()
+
+    def _destroy():
+        try:
+            dist.destroy_process_group()
+        finally:
+            done.set()
+    t = threading.Thread(target=_destroy, daemon=True)
+    t.start()
+    if not done.wait(timeout_s):
+        sys.stdout.flush()
+        sys.stderr.write("aadg_b200: destroy_process_group did not return within %.0f s; exiting\n" % timeout_s)
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def shard_sources(n_sources, rank, world):
     """contiguous block of source-image indices owned by `rank` (units are independent)."""
     per = (n_sources + world - 1) // world
@@ -130,6 +160,14 @@ class SearchEngine:
         self._reducer = BucketedAllReduce(model.store.grads) if self.world > 1 else None
         self._max_cloud = {}             # tuple(src_domains) -> largest per-domain source count of the global batch
         model.store.set_hyper(lr, weight_decay=weight_decay, grad_scale=1.0 / self.world)
+
+    def close(self):
+        """release the captured CUDA graphs (they hold NCCL kernels of the process group: drop them before
+        torch.distributed.destroy_process_group())"""
+        self._graphs.clear()
+        self._graph_pool = None
+        if self._reducer is not None:
+            self._reducer.works = []
 
     # ---- epoch-level protocol (search_dg.py:323-347) -----------------------------------------------------------
     def set_lr(self, lr):

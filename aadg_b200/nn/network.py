@@ -28,6 +28,10 @@ FUSE_BN_STATS = os.environ.get("AADG_FUSE_BN_STATS", "1") != "0"
 # residual blocks hand their two input-gradient branches to the next batch-norm backward as a pair (added on load)
 # instead of accumulating one into the other in the convolution epilogue
 GRAD_PAIRS = os.environ.get("AADG_GRAD_PAIRS", "0") != "0"   # measured: 1.7 ms/step slower than accumulating
+# ... except for the 1x1 expansion convolutions with few input channels (Cout >= 4*Cin, Cin <= UNFUSE_MAX_CIN): those
+# are bound by writing their output, the statistics warps slow that epilogue down by more than a separate read-only pass
+# over the output costs (per-layer A/B, profiles/: 64->256 @128^2 1.68 ms fused vs 1.15 + 0.22 ms separate)
+UNFUSE_MAX_CIN = int(os.environ.get("AADG_UNFUSE_MAX_CIN", "256"))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -361,7 +365,8 @@ class ConvBN:
     def forward(self, x, training, out=None, res=None, dropout_seed=None):
         n, h, w, _ = x.shape
         ho, wo = self.out_hw(h, w)
-        fused = training and FUSE_BN_STATS
+        fused = training and FUSE_BN_STATS and not (self.k == 1 and self.cout >= 4 * self.cin and
+                                                    self.cin <= UNFUSE_MAX_CIN)
         P = self._pack_factor(x)
         if P:
             pre = self._fprop_packed(x, P, fused)

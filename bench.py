@@ -501,9 +501,10 @@ def run_ours(a):
             dist.all_reduce(agg)
             extra["aggregate_over_gpus"] = {"n_gpus": world, "sinkhorn_iters_per_s": agg[0].item(),
                                             "aug_images_per_s": agg[1].item(), "note": "independent replicas (no collective)"}
+    from aadg_b200.host.search import shutdown
+    engines = [] if a.extras else [eng]
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(engines)
         return
     peaks = {}
     try:
@@ -547,8 +548,7 @@ def run_ours(a):
         except Exception as e:       # the baseline is a reported number, never a reason to lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: %r" % e}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(engines)
 
 
 if __name__ == "__main__":

@@ -70,6 +70,7 @@ def lockstep(rank, world, dev, graph):
     if graph:
         ok &= all(v[0] is not None for v in eng._graphs.values())
     ok = all_ok(ok, dev)
+    eng.close()
     if rank == 0:
         print("MULTIGPU_CHECK LOCKSTEP%s" % ("_GRAPH" if graph else ""), "OK" if ok else "FAILED", "world", world,
               "rewards", eng.rewards.cpu().numpy().round(5).tolist(), "param checksums", all_sums.cpu().numpy().tolist(),
@@ -78,7 +79,12 @@ def lockstep(rank, world, dev, graph):
 
 
 def parity(rank, world, dev):
-    """same global batch on N ranks (SyncBN) and on one: loss, rewards, parameters"""
+    """The same global batch on N ranks (SyncBN statistics) and on one GPU: loss, rewards, parameters.
+
+    The engine is not bitwise reproducible: its batch-norm statistics and weight gradients are summed with fp32 atomics,
+    and bf16 storage re-quantises any last-bit difference up to the bf16 noise floor within a few layers
+    (tests/test_parity_gpu.py, DESIGN.md "Precision").  "Equal" therefore means: the N-GPU run differs from the 1-GPU run
+    by no more than two 1-GPU runs of the same batch differ from each other (x4 margin; small absolute floors)."""
     from aadg_b200.data.policy import parse_policies
     from aadg_b200.host.search import SearchEngine, shard_sources
     from aadg_b200.nn import DeepLabV3Plus
@@ -99,26 +105,30 @@ def parity(rank, world, dev):
                            n_sources_total=n_src, src_offset=idx[0])
         eng.set_policies(parsed, epoch=0)
         x, m = torch.from_numpy(imgs[idx]).to(dev), torch.from_numpy(masks[idx]).to(dev)
-        losses = []
+        losses, rewards = [], []
         for _ in range(2):
             out = eng.step(x, m, [domains[i] for i in idx])
             losses.append(out["seg_loss"].reshape(1).clone())
+            rewards.append(eng.rewards.clone())
         NW.set_sync_bn(None)
-        return torch.cat(losses), eng.rewards.clone(), model.store.params.clone()
+        return torch.cat(losses), torch.stack(rewards), model.store.params.clone()
     l_n, r_n, p_n = run(True, mine)
     dist.all_reduce(l_n)
     l_n /= world                                                       # global loss = mean of the equal-sized shards' losses
     ok, msg = True, ""
     if rank == 0:
-        l_1, r_1, p_1 = run(False, list(range(n_src)))
-        e_loss = ((l_n - l_1).abs() / l_1.abs()).cpu().numpy()
-        e_rew = ((r_n - r_1).abs() / r_1.abs()).max().item()
-        e_par = ((p_n - p_1).norm() / p_1.norm()).item()
-        # step 0: same weights, so only summation order differs (1e-5); step 1 follows an Adam step, whose
-        # sign-like first update amplifies gradient noise on near-zero gradients (1e-3)
-        ok = bool(e_loss[0] <= 1e-5 and e_loss[1] <= 1e-3 and e_rew <= 1e-3 and e_par <= 1e-3)
-        msg = "loss 1-GPU %s N-GPU %s rel %s | rewards rel %.2e | params rel L2 %.2e" % (
-            l_1.cpu().numpy().tolist(), l_n.cpu().numpy().tolist(), e_loss.tolist(), e_rew, e_par)
+        l_a, r_a, p_a = run(False, list(range(n_src)))
+        l_b, r_b, p_b = run(False, list(range(n_src)))                 # the 1-GPU run again: the engine's own spread
+        rel = lambda u, v: ((u - v).abs() / v.abs()).cpu().numpy()      # noqa: E731
+        e_loss, s_loss = rel(l_n, l_a), rel(l_b, l_a)
+        e_rew, s_rew = rel(r_n, r_a).max(axis=1), rel(r_b, r_a).max(axis=1)
+        e_par = ((p_n - p_a).norm() / p_a.norm()).item()
+        s_par = ((p_b - p_a).norm() / p_a.norm()).item()
+        ok = bool((e_loss <= 4 * s_loss + 1e-4).all() and (e_rew <= 4 * s_rew + 2e-2).all() and e_par <= 4 * s_par + 1e-3)
+        msg = ("loss per step 1-GPU %s N-GPU %s | rel diff N-vs-1 %s, 1-GPU run-to-run %s | rewards (cumulative, per step) "
+               "N-vs-1 %s, run-to-run %s | params rel L2 N-vs-1 %.2e, run-to-run %.2e" %
+               (l_a.cpu().numpy().tolist(), l_n.cpu().numpy().tolist(), e_loss.tolist(), s_loss.tolist(), e_rew.tolist(),
+                s_rew.tolist(), e_par, s_par))
     ok = all_ok(ok, dev)
     if rank == 0:
         print("MULTIGPU_CHECK PARITY_1_vs_%d" % world, "OK" if ok else "FAILED", "global batch %d sources x 6 policies, "
@@ -132,8 +142,15 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     results = [lockstep(rank, world, dev, False), lockstep(rank, world, dev, True), parity(rank, world, dev)]
-    dist.destroy_process_group()
-    sys.exit(0 if all(results) else 1)
+    from aadg_b200.host.search import shutdown
+    sys.stdout.flush()
+    if not all(results):
+        sys.stderr.write("MULTIGPU_CHECK: a check failed\n")
+    rc = 0 if all(results) else 1
+    import threading
+    threading.Timer(45.0, lambda: os._exit(rc)).start()      # teardown watchdog (see search.shutdown)
+    shutdown()
+    os._exit(rc)
 
 
 if __name__ == "__main__":

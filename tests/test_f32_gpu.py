@@ -184,8 +184,10 @@ def test_gradients_of_the_kornia_backed_ops_vs_torch_autograd(f32):
     x0 = torch.rand(b, 3, h, w, device="cuda")
     G = torch.randn(b, 3, h, w, device="cuda")
     mask0 = torch.tensor([0.3, 0.8, 1.0], device="cuda")
-    cases = [("shear_x", "ShearX", [0.21, -0.3, 0.07]), ("shear_y", "ShearY", [-0.11, 0.3, 0.2]),
-             ("translate_x", "TranslateX", [0.2, -0.45, 0.05]), ("translate_y", "TranslateY", [-0.3, 0.1, 0.45]),
+    # magnitudes chosen so that no source coordinate lands on an integer (there the bilinear cell, hence d/dmag, is a
+    # matter of the last float bit: 0.3 * y is an integer on whole rows)
+    cases = [("shear_x", "ShearX", [0.21, -0.31, 0.07]), ("shear_y", "ShearY", [-0.11, 0.29, 0.19]),
+             ("translate_x", "TranslateX", [0.21, -0.44, 0.06]), ("translate_y", "TranslateY", [-0.3, 0.1, 0.45]),
              ("rotate", "Rotate", [17.0, -30.0, 4.5]), ("hue", "Hue", [0.3, 1.7, 0.95])]
     for kind, cls, mags in cases:
         x = x0.clone().requires_grad_(True)
