@@ -67,10 +67,17 @@ struct Stat {      // one statistics slot
 __device__ __forceinline__ int luma_u8(int r, int g, int b) {
   return (19595 * r + 38470 * g + 7471 * b + 0x8000) >> 16;   // Convert.c rgb2l
 }
-// ImagingBlend: a + alpha*(b-a) in float32, mul then add (no FMA), truncated; clipped outside [0,1]
-__device__ __forceinline__ int blend_u8(int a, int b, float alpha, bool inside01) {
-  float t = __fadd_rn((float)a, __fmul_rn(alpha, (float)(b - a)));
-  if (!inside01) t = t <= 0.f ? 0.f : (t >= 255.f ? 255.f : t);
+// exact (float)v for |v| < 2^22 on the fp32 / integer pipes (the conversion unit runs at a fraction of their rate):
+// 0x4B400000 is 1.5 * 2^23, whose ulp is 1, so adding v to its bit pattern adds v to its value
+__device__ __forceinline__ float i2f_small(int v) {
+  return __fsub_rn(__int_as_float(0x4B400000 + v), 12582912.0f);
+}
+// ImagingBlend: a + alpha*(b-a) in float32, mul then add (no FMA), truncated; clipped outside [0,1].  For alpha inside
+// [0,1] the clip is the identity on uint8 inputs (|fl(alpha*(b-a))| <= |b-a| by monotonicity of rounding), so it is
+// applied unconditionally: two min/max instead of a data-dependent branch.
+__device__ __forceinline__ int blend_u8(int a, int b, float alpha, bool /*inside01*/) {
+  float t = __fadd_rn(i2f_small(a), __fmul_rn(alpha, i2f_small(b - a)));
+  t = fminf(fmaxf(t, 0.f), 255.f);
   return (int)t;
 }
 
@@ -507,19 +514,28 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs a) {
 // ---- streaming stencil kernel: [pointwise steps] Sharpness [pointwise steps] -------------------------------------------
 // Same quad ownership as stream_kernel, for programs that contain ONE Sharpness step and no gather.  A WARP owns a strip
 // of 128 pixels x `rows_per_band` image rows and walks DOWN it: per image row a thread loads the five 32-bit words that
-// hold its four pixels plus one neighbour on each side (a warp's loads cover 384 contiguous bytes + 2 words), applies the
-// steps before the stencil to those six pixels ONCE, converts them to float ONCE, forms the two horizontal partial sums
-// Pillow's SMOOTH needs from a row -- (a*k1 + b*k1) + c*k1 when the row is above / below the centre and
-// (a*k1 + b*k5) + c*k1 when it is the centre row -- and keeps them in registers for the three output rows that use
-// them.  Output row y = ((0.5 + A(y+1)) + B(y)) + A(y-1): the float operation order of ImagingFilter3x3, bit for bit.
-// No shared-memory tile, no barrier in the loop; every image byte is loaded (rows+2)/rows times per strip.
-struct SharpRow {            // what a thread keeps of one image row: partial sums and the (pre-stepped) centre pixels
-  float A[4][3], B[4][3];
-  int c[4][3];
+// hold its four pixels plus one neighbour on each side (a warp's loads cover 384 contiguous bytes + 2 words, issued one
+// row ahead of their use), and keeps three rows of horizontal 3-sums in registers.  No shared-memory tile, no barrier
+// in the loop; every image byte is loaded (rows+2)/rows times per strip.
+//
+// Pillow's SMOOTH (ImagingFilter3x3, Filter.c) is float32: ss = 0.5 + sum k_i*x_i with k = {1,1,1,1,5,1,1,1,1}/13 in a
+// fixed order, then clip8 by truncation.  It equals the INTEGER expression d = (S + 5c + 6) / 13 (S = the 8 neighbours,
+// c = the centre) for every input, which is what the kernel evaluates, 2 x 16-bit lanes per register:
+//   * the exact value ss* = (2(S + 5c) + 13) / 26 has an ODD numerator, so it is never an integer and sits at least
+//     1/26 = 0.038 away from one;
+//   * the float evaluation is off by < 1.1e-4 (nine products with relative error <= 2^-23 on values <= 98.1, nine sums
+//     with half-ulp <= 2^-17 on partial sums < 256), so trunc(ss) = floor(ss*) = (2(S+5c)+13) div 26, and because the
+//     numerator is odd that is (2(S+5c)+12) div 26 = (S + 5c + 6) div 13; 0 <= d <= 255 (clip8 never clips);
+//   * n div 13 = (n * 5042) >> 16 for n <= 3321 (5042 = ceil(2^16/13), error n*0.77/65536 < 1/13).
+// The blend d + f*(x - d) keeps Pillow's float32 operation order (ImagingBlend); its int->float conversions use the
+// 1.5*2^23 trick (exact for |v| < 2^22) so that they run on the fp32 / integer pipes, not on the conversion unit.
+struct SharpRow {            // one image row as a thread keeps it: 12 horizontal 3-sums and its 12 own bytes,
+  uint32_t He[3], Ho[3];     // two zero-extended 16-bit lanes per register: word m of the quad, even / odd byte
+  uint32_t Ce[3], Co[3];     // lane lo <-> byte j = 4m (+1 odd), lane hi <-> byte j = 4m + 2 (+1 odd); j = 3*pixel + channel
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(NT) stencil_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(NT, 3) stencil_kernel(const StreamArgs a) {
   __shared__ __align__(16) uint8_t s_luts[AADG_MAX_OPS * 768];
   __shared__ float s_f[256];
   __shared__ unsigned int s_hist[MODE == MODE_STATS ? (NT / 32) * 768 : 1];
@@ -541,14 +557,11 @@ __global__ void __launch_bounds__(NT) stencil_kernel(const StreamArgs a) {
   const DevRow& row = s_row;
   const size_t plane = (size_t)H * W;
   const uint8_t* base = it.base < 0 ? a.src + (size_t)row.src * plane * 3 : a.scratch + (size_t)it.base * plane * 3;
-  const uint32_t* in = (const uint32_t*)base;
   const int wq = W >> 2;                        // quads per row
   const int row_words = wq * 3;
   const int RB = a.quads_per_cta;               // here: image rows per band
   const int strips = (wq + 31) >> 5, bands = (H + RB - 1) / RB;
-  const DevStep sharp = row.s[it.sharp];
-  const bool in01 = sharp.f >= 0.f && sharp.f <= 1.f;
-  const float k1 = __fdiv_rn(1.0f, 13.0f), k5 = __fdiv_rn(5.0f, 13.0f);
+  const float sf = row.s[it.sharp].f;
   const bool has_pre = it.sharp > it.s0, has_post = it.sharp + 1 < it.s1;
   unsigned int lsum = 0;
 
@@ -558,66 +571,82 @@ __global__ void __launch_bounds__(NT) stencil_kernel(const StreamArgs a) {
   if (band < bands && qx < wq) {
     const int x0 = qx << 2;
     const int y_begin = band * RB, y_end = min(H, y_begin + RB);
+    const uint32_t* colp = (const uint32_t*)base + qx * 3;
+    const bool has_left = qx > 0, has_right = qx + 1 < wq;
+    const bool xin0 = x0 >= 1, xin3 = x0 + 3 <= W - 2;            // pixels 1, 2 of a quad are never on the x border
 
-    // load image row yy (clamped: rows outside the image are only ever neighbours of pass-through border rows)
-    auto load_row = [&](int yy, SharpRow& R) {
-      const int yc = min(max(yy, 0), H - 1);
-      const uint32_t* p = in + (size_t)yc * row_words + qx * 3;
-      uint32_t w[5];
-      w[0] = qx > 0 ? __ldg(p - 1) : 0u;
+    uint32_t w[5];     // raw words of the next row to convert: loaded one iteration ahead (software prefetch)
+    // image rows are clamped: rows outside the image are only ever neighbours of pass-through border rows
+    auto fetch = [&](int yy) {
+      const uint32_t* p = colp + (size_t)min(max(yy, 0), H - 1) * row_words;
+      w[0] = has_left ? __ldg(p - 1) : 0u;
       w[1] = __ldg(p); w[2] = __ldg(p + 1); w[3] = __ldg(p + 2);
-      w[4] = qx + 1 < wq ? __ldg(p + 3) : 0u;
-      float f[6][3];
-#pragma unroll
-      for (int px = 0; px < 6; ++px) {
-        int v[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int k = 3 * (px - 1) + c + 4;          // byte index inside the 20 loaded bytes
-          v[c] = (w[k >> 2] >> (8 * (k & 3))) & 255;
-        }
-        if (has_pre)
-          for (int k = it.s0; k < it.sharp; ++k) apply_point(row.s[k], s_luts + k * 768, x0 - 1 + px, yc, v[0], v[1], v[2]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          f[px][c] = (float)v[c];
-          if (px >= 1 && px <= 4) R.c[px - 1][c] = v[c];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float l = __fmul_rn(f[i][c], k1), r = __fmul_rn(f[i + 2][c], k1);
-          R.A[i][c] = __fadd_rn(__fadd_rn(l, __fmul_rn(f[i + 1][c], k1)), r);
-          R.B[i][c] = __fadd_rn(__fadd_rn(l, __fmul_rn(f[i + 1][c], k5)), r);
-        }
+      w[4] = has_right ? __ldg(p + 3) : 0u;
     };
-
-    SharpRow up, mid, dn;                       // image rows y-1, y, y+1
-    load_row(y_begin - 1, up);
-    load_row(y_begin, mid);
-    for (int y = y_begin; y < y_end; ++y) {
-      load_row(y + 1, dn);
-      int vr[4], vg[4], vb[4];
-      const bool row_in = y >= 1 && y <= H - 2;
+    // the 20 bytes in w (image row yy; own byte j is byte 4 + j, its x neighbours are bytes j + 1 and j + 7)
+    auto convert = [&](int yy, SharpRow& R) {
+      if (has_pre) {                             // steps before the stencil, on all six pixels, written back into w
+        const int yc = min(max(yy, 0), H - 1);
+        uint32_t o[5] = {0u, 0u, 0u, 0u, 0u};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int x = x0 + i;
-        int v[3] = {mid.c[i][0], mid.c[i][1], mid.c[i][2]};
-        if (row_in && x >= 1 && x <= W - 2) {
+        for (int px = 0; px < 6; ++px) {
+          int v[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            float ss = __fadd_rn(0.5f, dn.A[i][c]);
-            ss = __fadd_rn(ss, mid.B[i][c]);
-            ss = __fadd_rn(ss, up.A[i][c]);
-            const int d = ss <= 0.f ? 0 : (ss >= 255.f ? 255 : (int)ss);
-            v[c] = blend_u8(d, v[c], sharp.f, in01);
+            const int k = 3 * px + c + 1;
+            v[c] = (w[k >> 2] >> (8 * (k & 3))) & 255;
+          }
+          for (int k = it.s0; k < it.sharp; ++k) apply_point(row.s[k], s_luts + k * 768, x0 - 1 + px, yc, v[0], v[1], v[2]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int k = 3 * px + c + 1;
+            o[k >> 2] |= (uint32_t)v[c] << (8 * (k & 3));
           }
         }
+#pragma unroll
+        for (int m = 0; m < 5; ++m) w[m] = o[m];
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const uint32_t xl = __funnelshift_r(w[m], w[m + 1], 8);          // bytes j + 1  (left neighbours)
+        const uint32_t xc = w[m + 1];                                     // bytes j + 4  (own)
+        const uint32_t xr = __funnelshift_r(w[m + 1], w[m + 2], 24);     // bytes j + 7  (right neighbours)
+        R.Ce[m] = __byte_perm(xc, 0u, 0x4240);
+        R.Co[m] = __byte_perm(xc, 0u, 0x4341);
+        R.He[m] = __byte_perm(xl, 0u, 0x4240) + R.Ce[m] + __byte_perm(xr, 0u, 0x4240);
+        R.Ho[m] = __byte_perm(xl, 0u, 0x4341) + R.Co[m] + __byte_perm(xr, 0u, 0x4341);
+      }
+    };
+    auto output = [&](int y, const SharpRow& up, const SharpRow& mid, const SharpRow& dn) {
+      int v[12];
+      const bool row_in = y >= 1 && y <= H - 2;
+#pragma unroll
+      for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+          const uint32_t C = par ? mid.Co[m] : mid.Ce[m];
+          const uint32_t V = par ? up.Ho[m] + mid.Ho[m] + dn.Ho[m] : up.He[m] + mid.He[m] + dn.He[m];
+          const uint32_t M = V + (C << 2) + 0x00060006u;                  // S + 5c + 6 per lane (<= 3321)
+#pragma unroll
+          for (int lane = 0; lane < 2; ++lane) {
+            const int j = 4 * m + par + 2 * lane;                           // byte index = 3 * pixel + channel
+            const int x = lane ? (int)(C >> 16) : (int)(C & 0xFFFFu);
+            const int d = lane ? (int)__umulhi(M & 0xFFFF0000u, 5042u) : (int)(((M & 0xFFFFu) * 5042u) >> 16);
+            // ImagingBlend: d + f * (x - d), clipped when f is outside [0, 1] (inside it the clip is the identity)
+            float t = __fadd_rn(i2f_small(d), __fmul_rn(sf, i2f_small(x - d)));
+            t = fminf(fmaxf(t, 0.f), 255.f);
+            const int px = j / 3;
+            const bool inside = row_in && (px == 0 ? xin0 : (px == 3 ? xin3 : true));
+            v[j] = inside ? (int)t : x;
+          }
+        }
+      int vr[4], vg[4], vb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int r = v[3 * i], g = v[3 * i + 1], b = v[3 * i + 2];
         if (has_post)
-          for (int k = it.sharp + 1; k < it.s1; ++k) apply_point(row.s[k], s_luts + k * 768, x, y, v[0], v[1], v[2]);
-        vr[i] = v[0]; vg[i] = v[1]; vb[i] = v[2];
+          for (int k = it.sharp + 1; k < it.s1; ++k) apply_point(row.s[k], s_luts + k * 768, x0 + i, y, r, g, b);
+        vr[i] = r; vg[i] = g; vb[i] = b;
       }
       const size_t q = (size_t)y * wq + qx;
       if (MODE == MODE_STATS) {
@@ -638,7 +667,24 @@ __global__ void __launch_bounds__(NT) stencil_kernel(const StreamArgs a) {
         __stcs((float4*)(o + plane), make_float4(s_f[vg[0]], s_f[vg[1]], s_f[vg[2]], s_f[vg[3]]));
         __stcs((float4*)(o + 2 * plane), make_float4(s_f[vb[0]], s_f[vb[1]], s_f[vb[2]], s_f[vb[3]]));
       }
-      up = mid; mid = dn;
+    };
+    // one image row per step: convert the prefetched row y+1, prefetch row y+2, emit row y.  The three row records
+    // rotate roles by NAME (three steps per loop trip), not by copying registers.
+    auto step = [&](int y, const SharpRow& up, const SharpRow& mid, SharpRow& dn) {
+      convert(y + 1, dn);
+      fetch(y + 2);
+      output(y, up, mid, dn);
+    };
+    SharpRow R0, R1, R2;
+    fetch(y_begin - 1); convert(y_begin - 1, R0);
+    fetch(y_begin); convert(y_begin, R1);
+    fetch(y_begin + 1);
+    for (int y = y_begin; y < y_end; y += 3) {
+      step(y, R0, R1, R2);
+      if (y + 1 >= y_end) break;
+      step(y + 1, R1, R2, R0);
+      if (y + 2 >= y_end) break;
+      step(y + 2, R2, R0, R1);
     }
   }
 
@@ -1008,7 +1054,8 @@ static int launch_stream(const PassArgs& base, const PassItem* d_items, int n, c
   // CTAs per image: enough CTAs for ~6 waves of 8 resident CTAs per SM when the batch is small, at least one
   // iteration's worth of quads each, at most 64 iterations (amortises the per-CTA table set-up)
   const int unit = NT * SQ;
-  long long want_ctas = (8LL * 6 * num_sms_u8() + n - 1) / n;
+  // a statistics pass pays a per-CTA histogram set-up and a 768-counter flush: far fewer, longer CTAs
+  long long want_ctas = ((MODE == MODE_STATS ? 4LL * 2 : 8LL * 6) * num_sms_u8() + n - 1) / n;
   long long per = (n_quads + want_ctas - 1) / want_ctas;
   per = std::max<long long>(unit, std::min<long long>(per, 64LL * unit));
   per = (per + unit - 1) / unit * unit;
@@ -1032,8 +1079,10 @@ static int launch_stencil(const PassArgs& base, const PassItem* d_items, int n, 
   const int wq = base.W / 4;
   const int strips = (wq + 31) / 32;
   // rows per warp-strip: 32 (6 % halo re-reads) when the batch alone fills the GPU, fewer rows (more warps) when it
-  // does not: aim at ~6 waves of 8 resident CTAs per SM, never below 8 rows
-  const long long want_warps = (8LL * 6 * num_sms_u8() * (NT / 32) + n - 1) / n;
+  // does not: aim at ~6 waves of the 3 resident CTAs per SM (2 waves for a statistics pass, whose per-CTA histogram
+  // set-up and flush cost as much as a few hundred pixels per thread), never below 8 rows
+  const long long waves = MODE == MODE_STATS ? 2 : 6;
+  const long long want_warps = (3LL * waves * num_sms_u8() * (NT / 32) + n - 1) / n;
   long long rb = ((long long)strips * base.H + want_warps - 1) / want_warps;
   rb = std::max<long long>(8, std::min<long long>(rb, 32));
   a.quads_per_cta = (int)rb;                                                         // image rows per band here

@@ -57,6 +57,18 @@ class ResidentPools:
                 out[b, d] = rng.choice(n, 1)[0]
         return out
 
+    def flat_indices(self, indices):
+        """indices [B, D] pool-local -> (flat [B*D] int64 indices into `self.images` / `self.masks`, domains list[B*D])
+        in collate order b*D + d.  The zero-copy form of a batch: SearchEngine.step(pools.images, pools.masks, domains,
+        src_index=flat) lets the augmentation kernels read the step's sources straight out of the resident pool."""
+        idx = np.asarray(indices, np.int64)
+        if idx.ndim != 2 or idx.shape[1] != self.n_domains:
+            raise ValueError("indices must be [B, %d]" % self.n_domains)
+        if (idx < 0).any() or (idx >= np.asarray(self.sizes)[None, :]).any():
+            raise IndexError("pool index out of range")
+        domains = [d for _ in range(idx.shape[0]) for d in range(self.n_domains)]
+        return (idx + self.offsets[None, :-1]).reshape(-1), domains
+
     def gather(self, indices):
         """indices [B, D] pool-local -> (images uint8 [B*D, H, W, 3], masks uint8 [B*D, H, W], domains list[B*D]) in
         collate order b*D + d; one device gather per tensor."""

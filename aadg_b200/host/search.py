@@ -55,34 +55,34 @@ def average_(flat):
     return flat
 
 
-def shutdown(engines=(), timeout_s=30.0):
+def shutdown(engines=(), timeout_s=20.0):
     """orderly end of a distributed run: captured graphs released, device drained, process group destroyed.  NCCL's
-    communicator teardown has been seen to wait forever when kernels of the communicator were captured into a CUDA graph;
-    the destroy call therefore runs under a watchdog and the process exits hard (status 0) if it does not return."""
+    communicator teardown has been seen to wait forever when kernels of the communicator were captured into a CUDA graph,
+    so the WHOLE teardown runs under a watchdog: if it has not finished after `timeout_s` the process exits hard with
+    status 0 (every result has been printed by then; the OS reclaims the device)."""
     import gc
     import os
     import sys
     import threading
+    if not (dist.is_available() and dist.is_initialized()):
+        for e in engines:
+            e.close()
+        return
+
+    def _bail():
+        sys.stdout.flush()
+        sys.stderr.write("aadg_b200: distributed teardown did not finish within %.0f s; exiting\n" % timeout_s)
+        sys.stderr.flush()
+        os._exit(0)
+    watchdog = threading.Timer(timeout_s, _bail)
+    watchdog.daemon = True
+    watchdog.start()
     for e in engines:
         e.close()
     gc.collect()
-    if not (dist.is_available() and dist.is_initialized()):
-        return
     torch.cuda.synchronize()
-    done = threading.Event()
-
-    def _destroy():
-        try:
-            dist.destroy_process_group()
-        finally:
-            done.set()
-    t = threading.Thread(target=_destroy, daemon=True)
-    t.start()
-    if not done.wait(timeout_s):
-        sys.stdout.flush()
-        sys.stderr.write("aadg_b200: destroy_process_group did not return within %.0f s; exiting\n" % timeout_s)
-        sys.stderr.flush()
-        os._exit(0)
+    dist.destroy_process_group()
+    watchdog.cancel()
 
 
 def shard_sources(n_sources, rank, world):
@@ -293,14 +293,25 @@ class SearchEngine:
             average_(self._dis_flat)
         self.dis_optimizer.step()
 
-    def step(self, src_images, src_masks, src_domains, rows=None, dc=None):
+    def step(self, src_images, src_masks, src_domains, rows=None, dc=None, src_index=None):
         """src_images uint8 [S,H,W,3] (CUDA), src_masks uint8 [S,H,W], src_domains int [S] (host).
-        Returns dict(seg_loss, dis_loss, dice [classes], n_images) of 0-d / small CUDA tensors."""
+        src_index (int [S], host): src_images / src_masks are a whole RESIDENT POOL and the step's S sources are its
+        entries src_index[0..S) (data.pool.ResidentPools.flat_indices) -- the augmentation kernels read them in place,
+        no gather, no copy.  Returns dict(seg_loss, dis_loss, dice [classes], n_images) of 0-d / small CUDA tensors."""
         if not self.searching:
             self.begin_search()
-        s, h, w, _ = src_images.shape
+        _, h, w, _ = src_images.shape
+        s = len(src_domains)
+        if src_index is None and src_images.shape[0] != s:
+            raise ValueError("%d source images but %d domain codes" % (src_images.shape[0], s))
         if rows is None:
             rows, _ = self.decision_rows(s, w, h)
+        if src_index is not None:
+            src_index = np.asarray(src_index, np.int64)
+            if src_index.shape != (s,) or src_index.min() < 0 or src_index.max() >= src_images.shape[0]:
+                raise IndexError("src_index must hold %d indices into the %d pool images" % (s, src_images.shape[0]))
+            rows = rows.copy()
+            rows["src"] = src_index[rows["src"]]
         if dc is None:
             dc = self.domain_codes(src_domains, self.M)
         max_cloud = self._global_max_cloud(src_domains)
@@ -324,12 +335,16 @@ class SearchEngine:
         return dict(seg_loss=out["loss"], dis_loss=dis_loss.detach(), dice=dice_from_counts(out["counts"]),
                     n_images=images.shape[0])
 
-    def pretrain_step(self, src_images, src_masks, src_domains):
+    def pretrain_step(self, src_images, src_masks, src_domains, src_index=None):
         """One step of the warm-up phase (`pretrain`, search_dg.py:22-100): the un-augmented `sample['image']` (only
         DGRandomScaleCrop / Normalize_dg / ToTensor), segmentation step, live discriminator step on the detached pooled
         features; no policies, no rewards.  Same argument / return shapes as `step`."""
-        s, h, w, _ = src_images.shape
+        _, h, w, _ = src_images.shape
+        s = len(src_domains)
         _, raws = self.decision_rows(s, w, h, policies=[[[]]])
+        if src_index is not None:          # the sources are entries of a resident pool (see step)
+            raws = raws.copy()
+            raws["src"] = np.asarray(src_index, np.int64)[raws["src"]]
         dc = self.domain_codes(src_domains, 1)
         dc_dev = torch.from_numpy(dc).to(src_images.device, non_blocking=True)
         images, labels, key = self._augment(src_images, src_masks, raws, "pretrain")

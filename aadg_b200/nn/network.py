@@ -32,6 +32,50 @@ GRAD_PAIRS = os.environ.get("AADG_GRAD_PAIRS", "0") != "0"   # measured: 1.7 ms/
 # are bound by writing their output, the statistics warps slow that epilogue down by more than a separate read-only pass
 # over the output costs (per-layer A/B, profiles/: 64->256 @128^2 1.68 ms fused vs 1.15 + 0.22 ms separate)
 UNFUSE_MAX_CIN = int(os.environ.get("AADG_UNFUSE_MAX_CIN", "256"))
+# Optional (AADG_WGRAD_SIDE=1): the weight gradient of a layer is off the backward pass's critical path (nothing reads dW
+# before the gradient exchange / the optimiser), so it can run on a SIDE stream, concurrently with the data gradient of
+# the same layer and the batch-norm backward of the next one; joined back before every gradient-ready hook and at the end
+# of the backward pass (works inside CUDA-graph capture: fork / join).  MEASURED NEUTRAL on the 144 x 512^2 ResNet-50 step
+# (89.7 vs 90.0 ms, graph and eager, profiles/README.md): the persistent convolution kernels own every SM's shared
+# memory, the element-wise passes they would overlap are HBM-bound like the weight gradient's own operand streams, and the
+# step has no idle pipe to fill.  Off by default.
+WGRAD_SIDE_STREAM = os.environ.get("AADG_WGRAD_SIDE", "0") != "0"
+
+
+class _Side:
+    streams = {}          # device index -> the side stream
+    pending = []          # tensors the side stream still reads (kept alive until the join)
+    forked = None         # the side stream with un-joined work
+    armed = False         # only a whole-network backward (loss_step / the autograd surface) forks: it also joins
+
+
+def on_side(fn, *keep):
+    """run fn() (kernel launches) on the side stream, ordered after everything enqueued so far on the current stream"""
+    if not (WGRAD_SIDE_STREAM and _Side.armed) or C.TIMING is not None:      # per-launch event timing wants one stream
+        fn()
+        return
+    dev = torch.cuda.current_device()
+    side = _Side.streams.get(dev)
+    if side is None:
+        side = _Side.streams[dev] = torch.cuda.Stream(device=dev)
+    ev = torch.cuda.Event()
+    ev.record()
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        fn()
+    _Side.pending.extend(keep)
+    _Side.forked = side
+
+
+def join_side():
+    """the current stream waits for the side stream's work; the tensors it was reading may be released afterwards"""
+    side = _Side.forked
+    if side is not None:
+        ev = torch.cuda.Event()
+        ev.record(side)
+        torch.cuda.current_stream().wait_event(ev)
+        _Side.forked = None
+    _Side.pending.clear()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -399,8 +443,11 @@ class ConvBN:
             n, h, w, _ = x.shape
             x4, d4 = x.view(n, h, w // P, 64), dpre.view(n, h, w // P, P * self.cout)
             real_flops = 2.0 * n * h * w * self.cout * self.cin * 9
-            dw4 = C.wgrad(x4, d4, 3, 3, 1, 1, 1, flops=real_flops)
-            self.packed.fold_grad(dw4, self.w.grad)
+            def packed_wgrad():
+                dw4 = C.wgrad(x4, d4, 3, 3, 1, 1, 1, flops=real_flops)
+                self.packed.fold_grad(dw4, self.w.grad)
+                _Side.pending.append(dw4)
+            on_side(packed_wgrad, x, dpre)
             if self.need_dgrad:
                 if dx is None:
                     dx = torch.empty(x.shape, dtype=BF16, device=x.device)
@@ -409,7 +456,7 @@ class ConvBN:
             else:
                 dx = None
             return (dx, dres) if want_dres else dx
-        C.wgrad(x, dpre, self.k, self.k, self.stride, self.pad, self.dil, out=self.w.grad)
+        on_side(lambda: C.wgrad(x, dpre, self.k, self.k, self.stride, self.pad, self.dil, out=self.w.grad), x, dpre)
         if self.need_dgrad:
             dx = C.dgrad(dpre, self.w.bf16_t, self.k, self.k, self.stride, self.pad, self.dil, x.shape[1:3], out=dx,
                          accumulate=accumulate)
@@ -437,7 +484,7 @@ class Depthwise3x3:
         """dx given with accumulate: the data gradient is added to it (fan-in of parallel branches, no separate add)"""
         x = self.ctx
         self.ctx = None
-        K.dwconv3x3_wgrad(x, dy, self.dil, self.w.grad, stride=self.stride)
+        on_side(lambda: K.dwconv3x3_wgrad(x, dy, self.dil, self.w.grad, stride=self.stride), x, dy)
         if dx is None:
             dx, accumulate = torch.empty(x.shape, dtype=BF16, device=x.device), False
         K.dwconv3x3(dy, self.w.data, self.dil, dx, backward_data=True, stride=self.stride, accumulate=accumulate)
@@ -628,7 +675,7 @@ class ResNetEncoder:
             K.add_(d, skips[0])
         dpre = torch.empty_like(pre)
         self.stem_bn.backward(d, pre, f1, dpre)
-        C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad)
+        on_side(lambda: C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad), col, dpre)
 
 
 class DepthwiseBN:
@@ -757,7 +804,7 @@ class MobileNetV2Encoder:
             d = blk.backward(d)
         dpre = torch.empty_like(pre)
         self.stem_bn.backward(d, pre, None, dpre, relu=True, relu6=True)
-        C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad)
+        on_side(lambda: C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad), col, dpre)
 
 
 class SeparableConvBN:
@@ -902,6 +949,7 @@ class _SegNetFunction(torch.autograd.Function):
         if dlogits is None:
             dlogits = torch.zeros((dec.shape[0], net.classes, ctx.z_shape[1] * 4, ctx.z_shape[2] * 4), device=dec.device)
         dz = K.upsample_logits_bwd(dlogits.float(), ctx.z_shape)
+        _Side.armed = True
         ddec = torch.empty(dec.shape, dtype=BF16, device=dec.device)
 
         def add_pooled(d_last):
@@ -917,6 +965,8 @@ class _SegNetFunction(torch.autograd.Function):
             K.seg_head_bwd(dz, dec, net.head_w.data, ddec, net.head_w.grad, net.head_b.grad)
             d_last, d_high = net.decoder.backward(ddec)
             net.encoder.backward(add_pooled(d_last), d_high)
+        join_side()
+        _Side.armed = False
         net.steps += 1
         if net.dropout_enabled:
             net.seed_dev += 1
@@ -1132,6 +1182,12 @@ class SegNet:
         Returns dict(loss [1] fp32 tensor, counts int32 [N,classes,3], pooled fp32 [N,C], logits or None)."""
         assert self.training
         n, _, hh, ww = x.shape
+        if on_ready is not None:        # a gradient is final once the side stream's weight gradients have joined
+            user_ready = on_ready
+
+            def on_ready(offset):
+                join_side()
+                user_ready(offset)
         dec, pooled = self.features(x)
         z = self._head(dec)
         loss_sum = torch.zeros(1, dtype=torch.float64, device=x.device)
@@ -1140,6 +1196,7 @@ class SegNet:
         K.seg_loss_fwd(z, target, thr, loss_sum, counts, logits)
         numel = float(n * self.classes * hh * ww)
         dz = K.seg_loss_bwd(z, target, 1.0 / numel)
+        _Side.armed = True
         ddec = torch.empty(dec.shape, dtype=BF16, device=x.device)
         if self.arch == "unet":
             K.seg_head3x3_bwd(dz, dec, self.head_w.data, ddec, self.head_w.grad, self.head_b.grad)
@@ -1153,6 +1210,8 @@ class SegNet:
             if on_ready is not None:
                 on_ready(first_offset(self.decoder))
             self.encoder.backward(d_last, d_high, on_ready=on_ready)
+        join_side()
+        _Side.armed = False
         if on_ready is not None:
             on_ready(0)
         self.steps += 1

@@ -306,19 +306,39 @@ def test_engine_vs_fp32_oracle_on_conditioned_weights(arch, encoder, classes, si
     e_dice = max(abs(dice[k].item() - want_dice[k]) for k in range(classes))
     t_dice = max(abs(twin_dice[k] - want_dice[k]) for k in range(classes))
     rows = grad_table(net, ref)
-    conditioned = {name for name, cos, _ in grad_table_torch(twin, ref) if cos >= 0.99}
-    judged = sorted((r for r in rows if r[0] in conditioned), key=lambda r: r[1])
+    twin_cos = {name: cos for name, cos, _ in grad_table_torch(twin, ref)}
+    # every parameter gradient: the engine is as close to the fp32 oracle as the bf16-storage oracle is (x3 + 0.02 in
+    # 1 - cosine).  Gradients that bf16 storage leaves well conditioned (twin cosine >= 0.99) are additionally held to 0.97.
+    offenders = sorted(((name, round(cos, 4), round(twin_cos.get(name, 1.0), 4)) for name, cos, _ in rows
+                        if (1 - cos) > 3 * (1 - twin_cos.get(name, 1.0)) + 0.02), key=lambda r: r[1])
+    judged = sorted((r for r in rows if twin_cos.get(r[0], 0.0) >= 0.99), key=lambda r: r[1])
+
+    def flat(table_names, getter):
+        return torch.cat([getter(nm).reshape(-1).double() for nm in table_names])
+    from test_nn_gpu import _my_grad_as_torch
+    names = [r[0] for r in rows]
+    rgrad = dict(ref.named_parameters())
+    tgrad = dict(twin.named_parameters())
+    g_ref = flat(names, lambda nm: rgrad[nm].grad)
+    g_eng = flat(names, lambda nm: _my_grad_as_torch(nm, net.named_params()[nm]))
+    g_twin = flat(names, lambda nm: tgrad[nm].grad)
+    cos_e = (g_eng @ g_ref / (g_eng.norm() * g_ref.norm())).item()
+    cos_t = (g_twin @ g_ref / (g_twin.norm() * g_ref.norm())).item()
     print("PARITY fp32-oracle (conditioned) %s/%s %d^2 n=%d: loss %.5f rel %.2e (bf16-storage oracle alone: %.2e) pooled "
-          "%.2e logits %.2e (oracle alone %.2e) dice abs %.2e (oracle alone %.2e) | %d of %d gradients well conditioned, "
-          "min cos %.4f %s" % (arch, encoder, size, n, loss, e_loss, t_loss, e_pool, e_logit, t_logit, e_dice, t_dice,
-                              len(judged), len(rows), judged[0][1], [(w[0], round(w[1], 4)) for w in judged[:3]]))
-    assert e_loss <= max(5e-4, 1.5 * t_loss), (e_loss, t_loss)
+          "%.2e logits %.2e (oracle alone %.2e) dice abs %.2e (oracle alone %.2e) | whole gradient cosine vs fp32: engine "
+          "%.5f, bf16-storage oracle %.5f | %d of %d gradients well conditioned under bf16 storage, engine min cos there "
+          "%.4f | offenders %s" % (arch, encoder, size, n, loss, e_loss, t_loss, e_pool, e_logit, t_logit, e_dice, t_dice,
+                                  cos_e, cos_t, len(judged), len(rows), judged[0][1] if judged else float("nan"),
+                                  offenders[:4]))
+    # (the loss is one scalar draw of the storage noise: x3; the logits are an L2 norm over millions of draws: x1.5)
+    assert e_loss <= max(5e-4, 3.0 * t_loss), (e_loss, t_loss)
     assert e_logit <= max(2e-2, 1.5 * t_logit), (e_logit, t_logit)
-    assert e_dice <= max(1e-3, 1.5 * t_dice), (e_dice, t_dice)
+    assert e_dice <= max(1e-3, 2.0 * t_dice), (e_dice, t_dice)
     if encoder != "mobilenet_v2":
         assert e_loss <= 5e-4 and e_logit <= 2e-2 and e_dice <= 1e-3
-    assert len(judged) >= 0.6 * len(rows), (len(judged), len(rows))
-    assert judged[0][1] >= 0.95, judged[:4]
+    assert (1 - cos_e) <= 2 * (1 - cos_t) + 2e-3, (cos_e, cos_t)
+    assert len(offenders) <= 0.02 * len(rows), offenders[:8]
+    assert not judged or judged[0][1] >= 0.97, judged[:4]
 
 
 def test_training_trajectory_50_steps_vs_fp32_oracle():

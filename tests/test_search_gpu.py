@@ -128,23 +128,27 @@ def test_cuda_graph_step_matches_eager_step():
     imgs, masks = fundus_batch(6, 64, 64, seed=11)
     x, m = torch.from_numpy(imgs).cuda(), torch.from_numpy(masks).cuda()
     curves = []
-    for graph in (False, True):
+    for graph in (False, False, True):      # two eager runs measure the engine's own run-to-run spread
         model = DeepLabV3Plus(encoder_name="resnet18", classes=2, seed=3)
         eng = SearchEngine(model, n_domains=3, M=6, crop=64, graph=graph, seed=21)
         eng.set_policies(parse_policies(random_policies(seed=3), _Cfg), epoch=0)
         losses = [float(eng.step(x, m, [0, 1, 2, 0, 1, 2])["seg_loss"]) for _ in range(6)]
-        curves.append((losses, eng.rewards.cpu().numpy().copy(), int(model.store.step_dev.item()), model.steps,
+        curves.append((np.array(losses), eng.rewards.cpu().numpy().copy(), int(model.store.step_dev.item()), model.steps,
                        int(model.seed_dev.item())))
         if graph:
             assert len(eng._graphs) == 1 and list(eng._graphs.values())[0][0] is not None
             assert list(eng._graphs.values())[0][0].launches > 100
-    (le, re_, se, te, de), (lg, rg, sg, tg, dg) = curves
-    print("GRAPH vs EAGER losses", le, lg)
+    (le, re_, se, te, de), (l2, r2, _, _, _), (lg, rg, sg, tg, dg) = curves
+    rel = lambda u, v: float(np.max(np.abs(u - v) / np.abs(v)))       # noqa: E731
+    print("GRAPH vs EAGER losses", le.tolist(), lg.tolist(), "| loss rel: graph-vs-eager %.2e eager-vs-eager %.2e | rewards rel: "
+          "graph-vs-eager %.2e eager-vs-eager %.2e" % (rel(lg, le), rel(l2, le), rel(rg, re_), rel(r2, re_)))
     assert (se, te, de) == (sg, tg, dg) == (6, 6, 0x5EED0000 + 3 + 6)
-    # step 0 runs eagerly in both engines: its difference is the engine's own run-to-run spread (fp32 atomics in the
-    # batch-norm statistics re-quantised by bf16 storage: measured 3e-4 on this 64^2 / 36-image configuration)
-    assert np.allclose(le, lg, rtol=2e-2) and abs(le[0] - lg[0]) <= 1e-3 * abs(le[0])
-    assert np.allclose(re_, rg, rtol=5e-2)
+    # step 0 runs eagerly in both engines; the engine is not bitwise reproducible (fp32 atomics in the batch-norm
+    # statistics, re-quantised by bf16 storage), so the yardstick is the spread of two EAGER runs (x4 + small floors):
+    # the rewards are Sinkhorn divergences between clouds of two points per domain, the most sensitive output there is
+    assert abs(le[0] - lg[0]) <= 1e-3 * abs(le[0])
+    assert rel(lg, le) <= max(4 * rel(l2, le), 1e-2), (rel(lg, le), rel(l2, le))
+    assert rel(rg, re_) <= max(4 * rel(r2, re_), 5e-2), (rel(rg, re_), rel(r2, re_))
     assert lg[-1] < lg[0]
 
 
@@ -222,3 +226,44 @@ def test_policy_call_shape_replays_the_reference_draws():
     multi = MultiPolicy(parsed, rng=(random.Random(5), np.random.RandomState(5)))
     outs = multi(x[0])
     assert len(outs) == len(parsed) and all(torch.equal(o[0], want[j]) and o[1] is None for j, o in enumerate(outs))
+
+
+def test_resident_pool_step_reads_sources_in_place():
+    """SURVEY 8f N4 on the device: a step fed from ResidentPools by INDEX (zero-copy: the uint8 bank reads the pool
+    entries in place) produces bit-identical augmented batches to the same step fed the gathered sources, the gather
+    itself equals numpy fancy indexing in the reference's collate order (b*D + d), and the whole step runs from it."""
+    from aadg_b200.data.policy import parse_policies
+    from aadg_b200.data.pool import ResidentPools
+    from aadg_b200.host.search import SearchEngine
+    from aadg_b200.nn import DeepLabV3Plus
+    from aadg_b200.synth import fundus_batch, random_policies
+    sizes = {"A": 5, "B": 4, "C": 6}
+    imgs, msks = {}, {}
+    for k, (name, n) in enumerate(sizes.items()):
+        imgs[name], msks[name] = fundus_batch(n, 64, 64, seed=40 + k)
+    pools = ResidentPools(imgs, msks, device="cuda")
+    np.random.seed(5)
+    idx = pools.sample_indices(2)                                  # [B=2, D=3]
+    gi, gm, dom = pools.gather(idx)
+    want_i = np.stack([imgs[n][idx[b, d]] for b in range(2) for d, n in enumerate(sizes)])
+    want_m = np.stack([msks[n][idx[b, d]] for b in range(2) for d, n in enumerate(sizes)])
+    assert np.array_equal(gi.cpu().numpy(), want_i) and np.array_equal(gm.cpu().numpy(), want_m) and dom == [0, 1, 2] * 2
+    flat, dom2 = pools.flat_indices(idx)
+    assert dom2 == dom and np.array_equal(pools.images[torch.from_numpy(flat).cuda()].cpu().numpy(), want_i)
+    parsed = parse_policies(random_policies(seed=3), _Cfg)
+    for crop in (None, 64):
+        model = DeepLabV3Plus(encoder_name="resnet18", classes=2, seed=3)
+        eng = SearchEngine(model, n_domains=3, M=6, crop=crop, seed=21)
+        eng.set_policies(parsed, epoch=0)
+        rows, _ = eng.decision_rows(6, 64, 64)
+        a_i, a_l, _ = eng._augment(gi, gm, rows, "search")
+        rows_pool = rows.copy()
+        rows_pool["src"] = flat[rows["src"]]
+        b_i, b_l, _ = eng._augment(pools.images, pools.masks, rows_pool, "search")
+        assert torch.equal(a_i, b_i) and torch.equal(a_l, b_l)
+        out = eng.step(pools.images, pools.masks, dom, src_index=flat)
+        assert np.isfinite(float(out["seg_loss"])) and out["n_images"] == 36
+        out = eng.pretrain_step(pools.images, pools.masks, dom, src_index=flat)
+        assert np.isfinite(float(out["seg_loss"])) and out["n_images"] == 6
+    with pytest.raises(IndexError):
+        eng.step(pools.images, pools.masks, dom, src_index=np.array([0, 1, 2, 3, 4, 99]))

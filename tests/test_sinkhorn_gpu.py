@@ -133,3 +133,17 @@ def test_large_properties_at_sweep_size(sk):
     diam = S.max_diameter(x.cpu().numpy(), y.cpu().numpy())
     sd, _ = sk.divergence_large(x, y, diameter=diam)
     assert abs(float(sd) - float(sxy)) <= 1e-5 * float(sxy)
+
+
+def test_kernels_pinned_to_exact_optimal_transport(sk):
+    """the independent pin of tests/test_oracle_sinkhorn.py applied to the KERNELS: the one-launch small path (N <= 64)
+    and the streamed large path against the assignment-problem optimum computed by scipy's Hungarian solver (shares no
+    code with the oracle or the kernels).  Exact to fp32 for 1 and 2 points; within 2 % beyond (the entropic blur)."""
+    from scipy.optimize import linear_sum_assignment
+    for n, d, tol in ((1, 16, 1e-5), (2, 16, 1e-5), (8, 128, 2e-2), (16, 64, 2e-2), (64, 128, 2e-2), (300, 128, 2e-2)):
+        x, y = feature_cloud(n, d, 0), feature_cloud(n, d, 2)
+        C = S.cosine_cost(x, y)
+        r, c = linear_sum_assignment(C)
+        exact = C[r, c].sum() / n
+        got = float(sk.divergence(dev(x), dev(y)))
+        assert abs(got - exact) <= tol * exact, (n, d, got, exact)
