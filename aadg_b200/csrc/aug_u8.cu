@@ -20,6 +20,7 @@
 //     explicit round-to-nearest intrinsics so nothing is contracted into an FMA.
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -98,6 +99,18 @@ __device__ __forceinline__ void apply_point(const DevStep& st, const uint8_t* lu
   } else if (st.kind == K_CUTOUT) {
     if (x >= st.p[0] && x <= st.p[2] && y >= st.p[1] && y <= st.p[3]) r = g = b = 127;
   }
+}
+
+// steps [k0,k1) on ONE pixel packed as r | g << 8 | b << 16, OUT OF LINE: the stencil kernel applies the steps around a
+// Sharpness from ten places inside a three-way unrolled row loop, and inlining the step interpreter there (times the
+// compiler's own unrolling of the step loop) grew the kernel to 175 KB of code -- it then stalled on instruction fetch
+// more than on anything else (ncu: stall_no_instruction 5.8 warps per issue, profiles/r02_ncu_aug_kernels.csv)
+__device__ __noinline__ uint32_t apply_steps_rgb(const DevRow* row, const uint8_t* luts, int k0, int k1, int x, int y,
+                                                 uint32_t rgb) {
+  int r = rgb & 255, g = (rgb >> 8) & 255, b = (rgb >> 16) & 255;
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) apply_point(row->s[k], luts + k * 768, x, y, r, g, b);
+  return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
 }
 
 // Pull evaluation of steps [s0,s1) (no SHARP inside) at output pixel (x,y): walks the gathers
@@ -458,11 +471,14 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs a) {
       vr[0] = w[u][0] & 255; vg[0] = (w[u][0] >> 8) & 255; vb[0] = (w[u][0] >> 16) & 255; vr[1] = w[u][0] >> 24;
       vg[1] = w[u][1] & 255; vb[1] = (w[u][1] >> 8) & 255; vr[2] = (w[u][1] >> 16) & 255; vg[2] = w[u][1] >> 24;
       vb[2] = w[u][2] & 255; vr[3] = (w[u][2] >> 8) & 255; vg[3] = (w[u][2] >> 16) & 255; vb[3] = w[u][2] >> 24;
-      if (!fast) {
+      if (!fast) {          // the step interpreter stays out of line (code size: see apply_steps_rgb)
         const int y = q / wq, x0 = (q - y * wq) << 2;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          for (int k = it.s0; k < it.s1; ++k) apply_point(row.s[k], s_luts + k * 768, x0 + i, y, vr[i], vg[i], vb[i]);
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t rgb = apply_steps_rgb(&s_row, s_luts, it.s0, it.s1, x0 + i, y,
+                                               (uint32_t)vr[i] | ((uint32_t)vg[i] << 8) | ((uint32_t)vb[i] << 16));
+          vr[i] = rgb & 255; vg[i] = (rgb >> 8) & 255; vb[i] = (rgb >> 16) & 255;
+        }
       }
       if (MODE == MODE_STATS) {
         unsigned int* hh = s_hist + (tid >> 5) * 768;
@@ -590,17 +606,17 @@ __global__ void __launch_bounds__(NT, 3) stencil_kernel(const StreamArgs a) {
         uint32_t o[5] = {0u, 0u, 0u, 0u, 0u};
 #pragma unroll
         for (int px = 0; px < 6; ++px) {
-          int v[3];
+          uint32_t rgb = 0;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const int k = 3 * px + c + 1;
-            v[c] = (w[k >> 2] >> (8 * (k & 3))) & 255;
+            rgb |= ((w[k >> 2] >> (8 * (k & 3))) & 255u) << (8 * c);
           }
-          for (int k = it.s0; k < it.sharp; ++k) apply_point(row.s[k], s_luts + k * 768, x0 - 1 + px, yc, v[0], v[1], v[2]);
+          rgb = apply_steps_rgb(&s_row, s_luts, it.s0, it.sharp, x0 - 1 + px, yc, rgb);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const int k = 3 * px + c + 1;
-            o[k >> 2] |= (uint32_t)v[c] << (8 * (k & 3));
+            o[k >> 2] |= ((rgb >> (8 * c)) & 255u) << (8 * (k & 3));
           }
         }
 #pragma unroll
@@ -644,8 +660,11 @@ __global__ void __launch_bounds__(NT, 3) stencil_kernel(const StreamArgs a) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         int r = v[3 * i], g = v[3 * i + 1], b = v[3 * i + 2];
-        if (has_post)
-          for (int k = it.sharp + 1; k < it.s1; ++k) apply_point(row.s[k], s_luts + k * 768, x0 + i, y, r, g, b);
+        if (has_post) {
+          const uint32_t rgb = apply_steps_rgb(&s_row, s_luts, it.sharp + 1, it.s1, x0 + i, y,
+                                               (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16));
+          r = rgb & 255; g = (rgb >> 8) & 255; b = (rgb >> 16) & 255;
+        }
         vr[i] = r; vg[i] = g; vb[i] = b;
       }
       const size_t q = (size_t)y * wq + qx;
@@ -895,7 +914,9 @@ struct Plan {
   std::vector<PassItem> mat[AADG_MAX_OPS + 1];        // materialise before step k
   std::vector<PassItem> stat[AADG_MAX_OPS];           // statistics pass feeding step k
   std::vector<LutItem> lut[AADG_MAX_OPS];             // tables of step k
-  std::vector<PassItem> fin;                          // final pass per row
+  std::vector<PassItem> fin;                          // final pass per row that waits for statistics / a materialised image
+  std::vector<PassItem> fin_ind;                      // final pass per INDEPENDENT row (no statistics op, one pass)
+  std::vector<LutItem> lut_ind;                       // tables of the independent rows (any step: none needs statistics)
   int n_stat_slots = 0;
   int n_scratch = 0;
 };
@@ -985,12 +1006,17 @@ static int compile(const aadg_aug_row_t* in, int n_rows, int n_src, Plan& pl) {
           st.p[1] = it.out; st.p[2] = 0;
         }
       }
-      if (st.kind == K_LUT) pl.lut[k].push_back(LutItem{r, k});
-      else all_lut = false;
+      if (st.kind != K_LUT) all_lut = false;
     }
+    // an INDEPENDENT row needs no statistics and no materialised intermediate: its tables and its single pass can run
+    // while the other rows' statistics -> tables chain is still in flight
+    bool independent = base < 0;
+    for (int k = 0; k < a.n_ops; ++k) independent = independent && !is_stat_op(a.op[k]);
+    for (int k = 0; k < a.n_ops; ++k)
+      if (d.s[k].kind == K_LUT) (independent ? pl.lut_ind : pl.lut[k]).push_back(LutItem{r, k});
     PassItem it = item(a.n_ops);
     it.out = r;
-    pl.fin.push_back(it);
+    (independent ? pl.fin_ind : pl.fin).push_back(it);
   }
   // own statistics slots follow the per-source ones
   int next = pl.n_stat_slots;
@@ -1109,6 +1135,29 @@ static int launch_pass(const PassArgs& base, const PassItem* d_items, int n, cud
   return check_launch("aug_u8 pass kernel");
 }
 
+// auxiliary stream (+ fork / join events) per device for the independent rows' chain
+struct AuxStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static AuxStream* aux_stream() {
+  static AuxStream table[64];
+  static bool made[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!made[dev]) {
+    AuxStream x{};
+    if (cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    table[dev] = x;
+    made[dev] = true;
+  }
+  return &table[dev];
+}
+static bool overlap_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AADG_U8_OVERLAP"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
 // mode: 0 = uint8 HWC images (+ optional masks), 1 = float32 CHW images (+ optional labels)
 static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_aug_row_t* rows,
                int n_rows, int n_src, int H, int W, int mode, int dataset, uint8_t* out_u8,
@@ -1143,7 +1192,7 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
     for (const PassItem& it : v) { r.stream += cls(it) == 0; r.stencil += cls(it) == 1; }
     return r;
   };
-  const Split ns_src = split(pl.src_stats), ns_fin = split(pl.fin);
+  const Split ns_src = split(pl.src_stats), ns_fin = split(pl.fin), ns_ind = split(pl.fin_ind);
   Split ns_mat[AADG_MAX_OPS], ns_stat[AADG_MAX_OPS];
   for (int k = 0; k < AADG_MAX_OPS; ++k) { ns_mat[k] = split(pl.mat[k]); ns_stat[k] = split(pl.stat[k]); }
   // one host blob -> one copy: rows, then every launch's item list back to back
@@ -1157,8 +1206,12 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
     o_stat[k] = items.size(); items.insert(items.end(), pl.stat[k].begin(), pl.stat[k].end());
     o_lut[k] = litems.size(); litems.insert(litems.end(), pl.lut[k].begin(), pl.lut[k].end());
   }
-  size_t o_fin = items.size();
+  const size_t o_fin = items.size();
   items.insert(items.end(), pl.fin.begin(), pl.fin.end());
+  const size_t o_ind = items.size();
+  items.insert(items.end(), pl.fin_ind.begin(), pl.fin_ind.end());
+  const size_t o_lut_ind = litems.size();
+  litems.insert(litems.end(), pl.lut_ind.begin(), pl.lut_ind.end());
   AADG_REQUIRE(items.size() <= L.n_items && litems.size() <= L.n_lut_items, "internal: plan overflow");
 
   AADG_CUDA_TRY(cudaMemcpyAsync(w + L.rows, pl.rows.data(), sizeof(DevRow) * n_rows, cudaMemcpyHostToDevice, st));
@@ -1181,23 +1234,80 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
   a.aligned = ((W * 3) % 16 == 0) && (((uintptr_t)src_images & 15) == 0);
   const PassItem* d_items = (const PassItem*)(w + L.items);
   const LutItem* d_litems = (const LutItem*)(w + L.lut_items);
+  AADG_REQUIRE(mode != 0 || out_u8, "null out_u8");
+  AADG_REQUIRE(!(out_masks || out_labels) || src_masks, "masks / labels requested without src_masks");
+  AADG_REQUIRE(!out_labels || ((((uintptr_t)src_masks & 3) == 0) && ((size_t)H * W) % 4 == 0),
+               "label path needs 4-byte aligned masks and H*W %% 4 == 0");
 
   // a list = [pointwise | stencil | tiled]: up to three launches
-#define AADG_U8_LAUNCH(MODE, ARGS, OFF, NS, N)                                                              \
+#define AADG_U8_LAUNCH(MODE, ARGS, OFF, NS, N, STREAM)                                                      \
   {                                                                                                         \
-    rc = launch_stream<MODE>(ARGS, d_items + (OFF), (NS).stream, st);                                       \
+    rc = launch_stream<MODE>(ARGS, d_items + (OFF), (NS).stream, STREAM);                                   \
     if (rc) return rc;                                                                                      \
-    rc = launch_stencil<MODE>(ARGS, d_items + (OFF) + (NS).stream, (NS).stencil, st);                       \
+    rc = launch_stencil<MODE>(ARGS, d_items + (OFF) + (NS).stream, (NS).stencil, STREAM);                   \
     if (rc) return rc;                                                                                      \
-    rc = launch_pass<MODE>(ARGS, d_items + (OFF) + (NS).stream + (NS).stencil, (N) - (NS).stream - (NS).stencil, st); \
+    rc = launch_pass<MODE>(ARGS, d_items + (OFF) + (NS).stream + (NS).stencil, (N) - (NS).stream - (NS).stencil, STREAM); \
     if (rc) return rc;                                                                                      \
   }
-  AADG_U8_LAUNCH(MODE_STATS, a, o_src, ns_src, (int)pl.src_stats.size())
+  auto final_pass = [&](size_t off, const Split& ns, int n, cudaStream_t s_) -> int {
+    if (n == 0) return AADG_OK;
+    PassArgs af = a;
+    if (mode == 0) {
+      af.out_u8 = out_u8;
+      AADG_U8_LAUNCH(MODE_U8, af, off, ns, n, s_)
+    } else if (out_f32) {
+      af.out_f32 = out_f32;
+      AADG_U8_LAUNCH(MODE_F32, af, off, ns, n, s_)
+    }
+    return AADG_OK;
+  };
+
+  // Two dependency chains share nothing but the uploaded tables above:
+  //   (A) rows with a statistics op or a materialised intermediate: source histograms -> [materialise -> statistics ->
+  //       tables] per step -> final pass.  Small, latency-bound launches (shared-memory atomics, a few images each).
+  //   (B) INDEPENDENT rows (about half of a search batch): tables -> final pass, plus the masks / labels of every row.
+  //       Large, HBM-bound launches.
+  // (B) runs on an auxiliary stream forked from and joined back into the caller's stream, so the bandwidth-bound bulk
+  // overlaps the latency-bound chain instead of queueing behind it (capture-safe: plain event fork / join).
+  const bool have_b = !pl.fin_ind.empty() || out_masks || out_labels;
+  const bool have_a = !pl.fin.empty() || !pl.src_stats.empty();
+  cudaStream_t sb = st;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (have_a && have_b && overlap_enabled()) {
+    AuxStream* ax = aux_stream();
+    if (ax) {
+      sb = ax->stream; ev_fork = ax->fork; ev_join = ax->join;
+      AADG_CUDA_TRY(cudaEventRecord(ev_fork, st));
+      AADG_CUDA_TRY(cudaStreamWaitEvent(sb, ev_fork, 0));
+    }
+  }
+  // ---- chain (B) ----
+  if (!pl.lut_ind.empty()) {
+    lut_kernel<<<(unsigned)pl.lut_ind.size(), 256, 0, sb>>>(a.rows, d_litems + o_lut_ind, (uint8_t*)(w + L.luts), a.stats, H * W);
+    rc = check_launch("aug_u8 lut kernel");
+    if (rc) return rc;
+  }
+  rc = final_pass(o_ind, ns_ind, (int)pl.fin_ind.size(), sb);
+  if (rc) return rc;
+  if (mode == 0 && out_masks) {
+    dim3 grid(std::min((H * W + 255) / 256, 1024), n_rows);
+    mask_kernel<<<grid, 256, 0, sb>>>(a.rows, src_masks, out_masks, n_rows, H, W);
+    rc = check_launch("aug_u8 mask kernel");
+    if (rc) return rc;
+  }
+  if (mode != 0 && out_labels) {
+    dim3 grid(std::min((H * W / 4 + 255) / 256, 512), n_rows);
+    label_kernel<<<grid, 256, 0, sb>>>(a.rows, src_masks, out_labels, H, W, dataset);
+    rc = check_launch("aug_u8 label kernel");
+    if (rc) return rc;
+  }
+  // ---- chain (A) ----
+  AADG_U8_LAUNCH(MODE_STATS, a, o_src, ns_src, (int)pl.src_stats.size(), st)
   for (int k = 0; k < AADG_MAX_OPS; ++k) {
     PassArgs am = a;
     am.out_u8 = (uint8_t*)(w + L.scratch);
-    AADG_U8_LAUNCH(MODE_U8, am, o_mat[k], ns_mat[k], (int)pl.mat[k].size())
-    AADG_U8_LAUNCH(MODE_STATS, a, o_stat[k], ns_stat[k], (int)pl.stat[k].size())
+    AADG_U8_LAUNCH(MODE_U8, am, o_mat[k], ns_mat[k], (int)pl.mat[k].size(), st)
+    AADG_U8_LAUNCH(MODE_STATS, a, o_stat[k], ns_stat[k], (int)pl.stat[k].size(), st)
     if (!pl.lut[k].empty()) {
       lut_kernel<<<(unsigned)pl.lut[k].size(), 256, 0, st>>>(a.rows, d_litems + o_lut[k], (uint8_t*)(w + L.luts),
                                                             a.stats, H * W);
@@ -1205,31 +1315,11 @@ static int run(const uint8_t* src_images, const uint8_t* src_masks, const aadg_a
       if (rc) return rc;
     }
   }
-  if (mode == 0) {
-    AADG_REQUIRE(out_u8, "null out_u8");
-    PassArgs af = a;
-    af.out_u8 = out_u8;
-    AADG_U8_LAUNCH(MODE_U8, af, o_fin, ns_fin, n_rows)
-    if (out_masks) {
-      AADG_REQUIRE(src_masks, "out_masks requested without src_masks");
-      dim3 grid(std::min((H * W + 255) / 256, 1024), n_rows);
-      mask_kernel<<<grid, 256, 0, st>>>(a.rows, src_masks, out_masks, n_rows, H, W);
-      rc = check_launch("aug_u8 mask kernel");
-    }
-  } else {
-    if (out_f32) {
-      PassArgs af = a;
-      af.out_f32 = out_f32;
-      AADG_U8_LAUNCH(MODE_F32, af, o_fin, ns_fin, n_rows)
-    }
-    if (out_labels) {
-      AADG_REQUIRE(src_masks, "out_labels requested without src_masks");
-      AADG_REQUIRE(((uintptr_t)src_masks & 3) == 0 && ((size_t)H * W) % 4 == 0,
-                   "label path needs 4-byte aligned masks and H*W %% 4 == 0");
-      dim3 grid(std::min((H * W / 4 + 255) / 256, 512), n_rows);
-      label_kernel<<<grid, 256, 0, st>>>(a.rows, src_masks, out_labels, H, W, dataset);
-      rc = check_launch("aug_u8 label kernel");
-    }
+  rc = final_pass(o_fin, ns_fin, (int)pl.fin.size(), st);
+  if (rc) return rc;
+  if (ev_join) {
+    AADG_CUDA_TRY(cudaEventRecord(ev_join, sb));
+    AADG_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));
   }
   return rc;
 }

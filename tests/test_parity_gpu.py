@@ -246,6 +246,121 @@ def test_every_layer_teacher_forced_vs_bf16_storage_oracle(arch, encoder, classe
     assert not bad, bad[:6]
 
 
+def backward_layer_residuals(arch, encoder, classes, size, n, dataset):
+    """The BACKWARD kernels of every convolution / depthwise convolution of the engine at the real shapes, teacher-forced:
+    fed the bf16-storage oracle's own layer input x and its own gradient dy of the layer output (rounded to bf16, as the
+    engine stores gradients) and compared with the exact (float64) data and weight gradients of those very tensors:
+    [(relative L2 residual, kind, layer, shapes)].  Identical inputs and masks on both sides, so the residual is fp32
+    accumulation order: weight gradients are fp32 outputs; data gradients are compared after rounding the exact result
+    to bf16 too, so only elements that land on the other side of a rounding boundary differ.  A wrong tap, border, stride,
+    split or tile choice shows as >= 1e-2."""
+    from aadg_b200.nn import network as NW
+    from aadg_b200.ops import conv as C
+    from aadg_b200.ops import nn as K
+    x, target = make_data(n, size, classes, dataset=dataset)
+    ref, twin, net = make_models(arch, encoder, classes)
+    mods = dict(twin.named_modules())
+    io, gout = {}, {}
+    for name, m in mods.items():
+        if isinstance(m, torch.nn.Conv2d):
+            m.register_forward_hook(lambda mod, inp, out, name=name: io.__setitem__(name, inp[0].detach()))
+            m.register_full_backward_hook(lambda mod, gi, go, name=name: gout.__setitem__(name, go[0].detach()))
+    logits, _ = twin(x)
+    F.binary_cross_entropy(torch.sigmoid(logits), target).backward()
+    rows, seen = [], set()
+
+    def exact(m, xin, dy, need_dx):
+        w64 = (m.weight.detach().to(BF) if m.groups == 1 else m.weight.detach()).double()
+        dw = torch.nn.grad.conv2d_weight(xin.double(), w64.shape, dy.double(), m.stride, m.padding, m.dilation, m.groups)
+        dx = torch.nn.grad.conv2d_input(xin.shape, w64, dy.double(), m.stride, m.padding, m.dilation, m.groups) \
+            if need_dx else None
+        return dw, dx
+
+    def walk(o):
+        if id(o) in seen:
+            return
+        seen.add(id(o))
+        if isinstance(o, NW.ConvBN):
+            cname = o.w.name[:-len(".weight")]
+            if cname in gout:
+                m = mods[cname]
+                xin, dy = io[cname], gout[cname].to(BF).float()
+                if float(dy.abs().max()) > 0:
+                    dw64, dx64 = exact(m, xin, dy, o.need_dgrad)
+                    xi, dyi = nhwc(xin).to(BF), nhwc(dy).to(BF)
+                    P = o._pack_factor(xi)
+                    nb, h, w_, _ = xi.shape
+                    if P:
+                        if o.packed is None:
+                            o.packed = NW.PackedTaps(o.cout, o.cin, P, xi.device)
+                        x4, d4 = xi.view(nb, h, w_ // P, 64), dyi.view(nb, h, w_ // P, P * o.cout)
+                        dw = torch.zeros((9, o.cout, o.cin), dtype=torch.float32, device=xi.device)
+                        o.packed.fold_grad(C.wgrad(x4, d4, 3, 3, 1, 1, 1), dw)
+                        dx = C.dgrad(d4, o.packed.expand_t(o.w.bf16), 3, 3, 1, 1, 1, (h, w_ // P)).view(nb, h, w_, o.cin) \
+                            if o.need_dgrad else None
+                    else:
+                        dw = C.wgrad(xi, dyi, o.k, o.k, o.stride, o.pad, o.dil)
+                        dx = C.dgrad(dyi, o.w.bf16_t, o.k, o.k, o.stride, o.pad, o.dil, (h, w_)) if o.need_dgrad else None
+                    note = "%s k%d s%d d%d%s" % (tuple(xin.shape), o.k, o.stride, o.dil, " pixel-packed x%d" % P if P else "")
+                    dw_t = dw.reshape(o.k, o.k, o.cout, o.cin).permute(2, 3, 0, 1)
+                    rows.append((l2err(dw_t, dw64), "wgrad", cname, note))
+                    if dx is not None:
+                        rows.append((l2err(nchw(dx), dx64.to(BF)), "dgrad", cname, note))
+        elif isinstance(o, NW.Depthwise3x3):
+            cname = o.w.name[:-len(".weight")]
+            if cname in gout:
+                m = mods[cname]
+                xin, dy = io[cname], gout[cname].to(BF).float()
+                dw64, dx64 = exact(m, xin, dy, True)
+                xi, dyi = nhwc(xin).to(BF), nhwc(dy).to(BF)
+                dw = torch.zeros((9, o.c), dtype=torch.float32, device=xi.device)
+                K.dwconv3x3_wgrad(xi, dyi, o.dil, dw, stride=o.stride)
+                dx = torch.empty(xi.shape, dtype=BF, device=xi.device)
+                K.dwconv3x3(dyi, o.w.data, o.dil, dx, backward_data=True, stride=o.stride)
+                note = "%s s%d d%d" % (tuple(xin.shape), o.stride, o.dil)
+                rows.append((l2err(dw.t().reshape(o.c, 1, 3, 3), dw64), "dw wgrad", cname, note))
+                rows.append((l2err(nchw(dx), dx64.to(BF)), "dw dgrad", cname, note))
+        if isinstance(o, (list, tuple)):
+            for i in o:
+                walk(i)
+        elif hasattr(o, "__dict__") and not isinstance(o, (NW.ParamStore, NW.Param, torch.Tensor)):
+            for v in vars(o).values():
+                walk(v)
+    walk(net.encoder)
+    walk(net.decoder)
+    if hasattr(net.encoder, "stem_w"):               # stem weight gradient: a 1x1 GEMM over the im2col patches
+        cname = net.encoder.stem_w.name[:-len(".weight")]
+        m = mods[cname]
+        xin, dy = io[cname], gout[cname].to(BF).float()
+        dw64, _ = exact(m, xin.to(BF).float(), dy, False)
+        if encoder == "mobilenet_v2":
+            col = K.im2col_stem(xin.contiguous(), 3, 3, 2, 1, 3 * NW.MBV2_STEM_RP, row_pitch=NW.MBV2_STEM_RP)
+            dw = NW.stem_unpack_rows(C.wgrad(col, nhwc(dy).to(BF), 1, 1, 1, 0, 1), 3, 3, NW.MBV2_STEM_RP)
+        else:
+            col = K.im2col_stem(xin.contiguous(), 7, 7, 2, 3, NW.STEM_KP, row_pitch=NW.STEM_RP)
+            dw = NW.stem_unpack(C.wgrad(col, nhwc(dy).to(BF), 1, 1, 1, 0, 1))
+        rows.append((l2err(dw, dw64), "stem wgrad", cname, str(tuple(xin.shape))))
+    rows.sort(reverse=True)
+    return rows
+
+
+@pytest.mark.parametrize("arch,encoder,classes,size,n,dataset", LAYER_CASES)
+def test_every_layer_backward_teacher_forced_vs_float64(arch, encoder, classes, size, n, dataset):
+    """backward implementation parity, layer by layer at the real shapes (tile selection, splits, halo and packed variants
+    included): weight gradients within 2e-3 and (bf16-rounded) data gradients within 1e-3 relative L2 of the exact
+    float64 gradients of the same bf16 tensors."""
+    rows = backward_layer_residuals(arch, encoder, classes, size, n, dataset)
+    assert len(rows) >= 60, len(rows)
+    worst = {}
+    for r in rows:
+        worst.setdefault(r[1], r)
+    print("LAYERS-BWD %s/%s %d^2 n=%d: %d checks; worst per kind: %s" %
+          (arch, encoder, size, n, len(rows), {k: ("%.2e" % v[0], v[2]) for k, v in worst.items()}))
+    tol = {"wgrad": 2e-3, "stem wgrad": 2e-3, "dw wgrad": 2e-3, "dgrad": 1e-3, "dw dgrad": 1e-3}
+    bad = [r for r in rows if r[0] > tol[r[1]]]
+    assert not bad, bad[:6]
+
+
 @pytest.mark.parametrize("arch,encoder,classes,size,n,dataset", CASES)
 def test_engine_within_the_bf16_noise_envelope_at_random_init(arch, encoder, classes, size, n, dataset):
     """Whole network at random initialisation.  bf16 storage re-quantises every layer, so ANY difference in fp32
@@ -409,7 +524,7 @@ def test_autograd_surface_runs_the_reference_training_lines():
               (step, rel, spread, cos, cos_spread, ratio))
         assert rel <= max(4 * spread, 5e-4 if step == 0 else 5e-3), (step, rel, spread)
         assert 1 - cos <= max(4 * (1 - cos_spread), 1e-3 if step == 0 else 2e-2), (step, cos, cos_spread)
-        assert abs(ratio - 1) <= 0.05, (step, ratio)
+        assert abs(ratio - 1) <= (0.05 if step == 0 else 0.25), (step, ratio)      # later steps: weights have diverged
         for name, leaf in b.named_parameters():
             assert leaf.grad is not None and leaf.grad.data_ptr() == b.named_params()[name].grad.data_ptr()
         model_optimizer.step()
