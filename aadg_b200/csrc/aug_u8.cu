@@ -113,6 +113,43 @@ __device__ __noinline__ uint32_t apply_steps_rgb(const DevRow* row, const uint8_
   return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
 }
 
+// the same for a QUAD (four consecutive pixels of one image row = three 32-bit words, bytes r0 g0 b0 r1 | g1 b1 r2 g2 |
+// b2 r3 g3 b3): one call and one decode of every step per four pixels
+struct Quad { uint32_t w0, w1, w2; };
+__device__ __noinline__ Quad apply_steps_quad(const DevRow* row, const uint8_t* luts, int k0, int k1, int x0, int y, Quad q) {
+  int r[4], g[4], b[4];
+  r[0] = q.w0 & 255; g[0] = (q.w0 >> 8) & 255; b[0] = (q.w0 >> 16) & 255; r[1] = q.w0 >> 24;
+  g[1] = q.w1 & 255; b[1] = (q.w1 >> 8) & 255; r[2] = (q.w1 >> 16) & 255; g[2] = q.w1 >> 24;
+  b[2] = q.w2 & 255; r[3] = (q.w2 >> 8) & 255; g[3] = (q.w2 >> 16) & 255; b[3] = q.w2 >> 24;
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    const DevStep& st = row->s[k];
+    if (st.kind == K_LUT) {
+      const uint8_t* lut = luts + k * 768;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { r[i] = lut[r[i]]; g[i] = lut[256 + g[i]]; b[i] = lut[512 + b[i]]; }
+    } else if (st.kind == K_COLOR) {
+      const float f = st.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int l = luma_u8(r[i], g[i], b[i]);
+        r[i] = blend_u8(l, r[i], f, false); g[i] = blend_u8(l, g[i], f, false); b[i] = blend_u8(l, b[i], f, false);
+      }
+    } else if (st.kind == K_CUTOUT) {
+      if (y >= st.p[1] && y <= st.p[3]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (x0 + i >= st.p[0] && x0 + i <= st.p[2]) r[i] = g[i] = b[i] = 127;
+      }
+    }
+  }
+  Quad o;
+  o.w0 = r[0] | (g[0] << 8) | (b[0] << 16) | (r[1] << 24);
+  o.w1 = g[1] | (b[1] << 8) | (r[2] << 16) | (g[2] << 24);
+  o.w2 = b[2] | (r[3] << 8) | (g[3] << 16) | (b[3] << 24);
+  return o;
+}
+
 // Pull evaluation of steps [s0,s1) (no SHARP inside) at output pixel (x,y): walks the gathers
 // backwards to find the source pixel, then applies the pointwise steps forwards.
 __device__ __forceinline__ void eval_gather(const DevRow& row, const uint8_t* luts, int s0, int s1,
@@ -467,19 +504,15 @@ __global__ void __launch_bounds__(NT) stream_kernel(const StreamArgs a) {
       const int q = q0 + u * NT;
       if (q >= q_end) break;
       // bytes: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+      if (!fast) {          // the step interpreter stays out of line (code size: see apply_steps_rgb)
+        const int y = q / wq, x0 = (q - y * wq) << 2;
+        const Quad o = apply_steps_quad(&s_row, s_luts, it.s0, it.s1, x0, y, Quad{w[u][0], w[u][1], w[u][2]});
+        w[u][0] = o.w0; w[u][1] = o.w1; w[u][2] = o.w2;
+      }
       int vr[4], vg[4], vb[4];
       vr[0] = w[u][0] & 255; vg[0] = (w[u][0] >> 8) & 255; vb[0] = (w[u][0] >> 16) & 255; vr[1] = w[u][0] >> 24;
       vg[1] = w[u][1] & 255; vb[1] = (w[u][1] >> 8) & 255; vr[2] = (w[u][1] >> 16) & 255; vg[2] = w[u][1] >> 24;
       vb[2] = w[u][2] & 255; vr[3] = (w[u][2] >> 8) & 255; vg[3] = (w[u][2] >> 16) & 255; vb[3] = w[u][2] >> 24;
-      if (!fast) {          // the step interpreter stays out of line (code size: see apply_steps_rgb)
-        const int y = q / wq, x0 = (q - y * wq) << 2;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t rgb = apply_steps_rgb(&s_row, s_luts, it.s0, it.s1, x0 + i, y,
-                                               (uint32_t)vr[i] | ((uint32_t)vg[i] << 8) | ((uint32_t)vb[i] << 16));
-          vr[i] = rgb & 255; vg[i] = (rgb >> 8) & 255; vb[i] = (rgb >> 16) & 255;
-        }
-      }
       if (MODE == MODE_STATS) {
         unsigned int* hh = s_hist + (tid >> 5) * 768;
 #pragma unroll
@@ -601,26 +634,14 @@ __global__ void __launch_bounds__(NT, 3) stencil_kernel(const StreamArgs a) {
     };
     // the 20 bytes in w (image row yy; own byte j is byte 4 + j, its x neighbours are bytes j + 1 and j + 7)
     auto convert = [&](int yy, SharpRow& R) {
-      if (has_pre) {                             // steps before the stencil, on all six pixels, written back into w
-        const int yc = min(max(yy, 0), H - 1);
-        uint32_t o[5] = {0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int px = 0; px < 6; ++px) {
-          uint32_t rgb = 0;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int k = 3 * px + c + 1;
-            rgb |= ((w[k >> 2] >> (8 * (k & 3))) & 255u) << (8 * c);
-          }
-          rgb = apply_steps_rgb(&s_row, s_luts, it.s0, it.sharp, x0 - 1 + px, yc, rgb);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int k = 3 * px + c + 1;
-            o[k >> 2] |= ((rgb >> (8 * c)) & 255u) << (8 * (k & 3));
-          }
-        }
-#pragma unroll
-        for (int m = 0; m < 5; ++m) w[m] = o[m];
+      if (has_pre) {          // steps before the stencil on all six pixels, written back into w: the own quad (bytes
+        const int yc = min(max(yy, 0), H - 1);       // 4..15 = w[1..3]) in one call, the two neighbours one by one
+        const Quad o = apply_steps_quad(&s_row, s_luts, it.s0, it.sharp, x0, yc, Quad{w[1], w[2], w[3]});
+        w[1] = o.w0; w[2] = o.w1; w[3] = o.w2;
+        const uint32_t lft = apply_steps_rgb(&s_row, s_luts, it.s0, it.sharp, x0 - 1, yc, w[0] >> 8);          // bytes 1..3
+        w[0] = (w[0] & 0xFFu) | (lft << 8);
+        const uint32_t rgt = apply_steps_rgb(&s_row, s_luts, it.s0, it.sharp, x0 + 4, yc, w[4] & 0xFFFFFFu);   // bytes 16..18
+        w[4] = (w[4] & 0xFF000000u) | rgt;
       }
 #pragma unroll
       for (int m = 0; m < 3; ++m) {
@@ -656,17 +677,18 @@ __global__ void __launch_bounds__(NT, 3) stencil_kernel(const StreamArgs a) {
             v[j] = inside ? (int)t : x;
           }
         }
+      if (has_post) {
+        Quad o;
+        o.w0 = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        o.w1 = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+        o.w2 = v[8] | (v[9] << 8) | (v[10] << 16) | (v[11] << 24);
+        o = apply_steps_quad(&s_row, s_luts, it.sharp + 1, it.s1, x0, y, o);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) v[j] = ((j < 4 ? o.w0 : (j < 8 ? o.w1 : o.w2)) >> (8 * (j & 3))) & 255;
+      }
       int vr[4], vg[4], vb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int r = v[3 * i], g = v[3 * i + 1], b = v[3 * i + 2];
-        if (has_post) {
-          const uint32_t rgb = apply_steps_rgb(&s_row, s_luts, it.sharp + 1, it.s1, x0 + i, y,
-                                               (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16));
-          r = rgb & 255; g = (rgb >> 8) & 255; b = (rgb >> 16) & 255;
-        }
-        vr[i] = r; vg[i] = g; vb[i] = b;
-      }
+      for (int i = 0; i < 4; ++i) { vr[i] = v[3 * i]; vg[i] = v[3 * i + 1]; vb[i] = v[3 * i + 2]; }
       const size_t q = (size_t)y * wq + qx;
       if (MODE == MODE_STATS) {
         unsigned int* hh = s_hist + (tid >> 5) * 768;
