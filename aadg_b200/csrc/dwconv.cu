@@ -335,6 +335,184 @@ __global__ void __launch_bounds__(256) direct_wgrad_kernel(const __grid_constant
   }
 }
 
+// ---- dilation > 1, persistent + pipelined (round 2) ----------------------------------------------------------------
+// direct_kernel / direct_wgrad_kernel serialise copy -> compute per CTA and rely on three co-resident CTAs to overlap
+// them: 0.53 ms per launch on the 144 x 32 x 32 x 2048 ASPP tensor against 0.19 ms of HBM time.  Here ONE CTA of 512
+// threads per SM walks a contiguous range of (channel chunk, image) items with a ring of `stages` whole-image tiles:
+// the TMA copies of the next items are in flight while the current one is computed, the filter taps are re-read only
+// when the chunk changes (items are ordered image-fastest), and the weight gradient keeps its 9 x 8 partial sums in
+// registers across all images of a chunk.
+constexpr int DP_THREADS = 512;
+
+struct ItemRange { long long i0, i1; };
+__device__ __forceinline__ ItemRange my_items(long long total) {
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long i0 = (long long)blockIdx.x * per;
+  return ItemRange{i0, i0 + per < total ? i0 + per : total};
+}
+
+__global__ void __launch_bounds__(DP_THREADS, 1) direct_p_kernel(const __grid_constant__ CUtensorMap tmX, const Args a,
+                                                                 int chunks, int stages, int tile_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = align128(smem_raw);
+  uint64_t* full = (uint64_t*)(tiles + (size_t)stages * tile_bytes);
+  const int HW = a.H * a.W;
+  const ItemRange R = my_items((long long)chunks * a.N);
+  if (R.i0 >= R.i1) return;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long item, int s) {
+    const int chunk = (int)(item / a.N), n = (int)(item - (long long)chunk * a.N);
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(HW * D_CB * 2));
+    tc::tma_load_4d(tiles + (size_t)s * tile_bytes, &tmX, &full[s], chunk * D_CB, 0, 0, n);
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < stages && R.i0 + s < R.i1; ++s) issue(R.i0 + s, s);
+  const int g = threadIdx.x & 3;
+  int cur_chunk = -1;
+  float wt[9][8];
+  for (long long item = R.i0; item < R.i1; ++item) {
+    const int k = (int)(item - R.i0), s = k % stages;
+    const uint32_t phase = (uint32_t)(k / stages) & 1u;
+    const int chunk = (int)(item / a.N), n = (int)(item - (long long)chunk * a.N);
+    const int c = chunk * D_CB + g * 8;
+    if (chunk != cur_chunk) {
+      cur_chunk = chunk;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (c < a.C) load_w8(a.w + (size_t)(a.flip ? 8 - t : t) * a.C + c, wt[t]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wt[t][i] = 0.f;
+        }
+      }
+    }
+    mbar_wait(&full[s], phase);
+    const uint4* img = reinterpret_cast<const uint4*>(tiles + (size_t)s * tile_bytes) + g;     // pixel stride = 4 uint4
+    for (int p = threadIdx.x >> 2; p < HW; p += DP_THREADS / 4) {
+      const int oy = p / a.W, ox = p - oy * a.W;
+      float acc[8] = {};
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int iy = oy + (r - 1) * a.dil;
+        if (iy < 0 || iy >= a.H) continue;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int ix = ox + (q - 1) * a.dil;
+          if (ix < 0 || ix >= a.W) continue;
+          float v[8];
+          unpack8(img[(iy * a.W + ix) * 4], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(wt[r * 3 + q][e], v[e], acc[e]);
+        }
+      }
+      if (c < a.C) {
+        uint4* dst = reinterpret_cast<uint4*>(a.y + ((size_t)n * HW + p) * a.ldy + c);
+        if (a.accumulate) {
+          float prev[8];
+          unpack8(*dst, prev);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += prev[e];
+        }
+        *dst = pack8(acc);
+      }
+    }
+    fence_proxy_async();      // the generic reads of this stage are ordered before the bulk copy that refills it
+    __syncthreads();
+    if (threadIdx.x == 0 && item + stages < R.i1) issue(item + stages, s);
+  }
+}
+
+__global__ void __launch_bounds__(DP_THREADS, 1) direct_p_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const Args a,
+                                                                       int chunks, int stages, int tile_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = align128(smem_raw);
+  uint64_t* full = (uint64_t*)(tiles + (size_t)stages * tile_bytes);
+  float* red = (float*)(full + stages);                   // [9][D_CB]
+  const int HW = a.H * a.W;
+  const ItemRange R = my_items((long long)chunks * a.N);
+  if (R.i0 >= R.i1) return;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 9 * D_CB; i += DP_THREADS) red[i] = 0.f;
+  __syncthreads();
+  auto issue = [&](long long item, int s) {
+    const int chunk = (int)(item / a.N), n = (int)(item - (long long)chunk * a.N);
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(HW * D_CB * 2));
+    tc::tma_load_4d(tiles + (size_t)s * tile_bytes, &tmX, &full[s], chunk * D_CB, 0, 0, n);
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < stages && R.i0 + s < R.i1; ++s) issue(R.i0 + s, s);
+  const int g = threadIdx.x & 3;
+  float acc[9][8] = {};
+  // flush the partial sums of channel chunk `chunk`: registers -> shared (atomics) -> one global atomic per entry
+  auto flush = [&](int chunk) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { atomicAdd(&red[t * D_CB + g * 8 + e], acc[t][e]); acc[t][e] = 0.f; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * D_CB; i += DP_THREADS) {
+      const int t = i / D_CB, cc = chunk * D_CB + i % D_CB;
+      if (cc < a.C) atomicAdd(&a.dwgt[(size_t)t * a.C + cc], red[i]);
+      red[i] = 0.f;
+    }
+    __syncthreads();
+  };
+  int cur_chunk = (int)(R.i0 / a.N);
+  for (long long item = R.i0; item < R.i1; ++item) {
+    const int k = (int)(item - R.i0), s = k % stages;
+    const uint32_t phase = (uint32_t)(k / stages) & 1u;
+    const int chunk = (int)(item / a.N), n = (int)(item - (long long)chunk * a.N);
+    if (chunk != cur_chunk) { flush(cur_chunk); cur_chunk = chunk; }
+    const int c = chunk * D_CB + g * 8;
+    const bf16* dyn = a.dy + (size_t)n * HW * a.lddy + c;
+    int p = threadIdx.x >> 2;
+    uint4 dnext = make_uint4(0, 0, 0, 0);
+    if (p < HW && c < a.C) dnext = __ldg(reinterpret_cast<const uint4*>(dyn + (size_t)p * a.lddy));
+    mbar_wait(&full[s], phase);
+    const uint4* img = reinterpret_cast<const uint4*>(tiles + (size_t)s * tile_bytes) + g;
+    for (; p < HW; p += DP_THREADS / 4) {
+      float d[8];
+      unpack8(dnext, d);
+      if (p + DP_THREADS / 4 < HW && c < a.C)
+        dnext = __ldg(reinterpret_cast<const uint4*>(dyn + (size_t)(p + DP_THREADS / 4) * a.lddy));
+      const int oy = p / a.W, ox = p - oy * a.W;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int iy = oy + (r - 1) * a.dil;
+        if (iy < 0 || iy >= a.H) continue;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int ix = ox + (q - 1) * a.dil;
+          if (ix < 0 || ix >= a.W) continue;
+          float v[8];
+          unpack8(img[(iy * a.W + ix) * 4], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[r * 3 + q][e] = fmaf(d[e], v[e], acc[r * 3 + q][e]);
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0 && item + stages < R.i1) issue(item + stages, s);
+  }
+  flush(cur_chunk);
+}
+
+static int tuning_direct_p() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AADG_DW_DIRECT_P"); v = e ? atoi(e) : 1; }
+  return v;
+}
+// stages x whole-image tiles within ~200 KB of shared memory (at least 2, at most 6)
+static int direct_p_stages(int tile_bytes) { return std::max(2, std::min(6, (200 * 1024) / tile_bytes)); }
+
 static int num_sms() {
   static int v = 0;
   if (!v) {
@@ -405,6 +583,17 @@ int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const flo
     CUtensorMap m;
     int rc = make_x_map(&m, x, n, h, w, c, ldx, D_CB, w, h);
     if (rc) return rc;
+    if (tuning_direct_p()) {
+      const int tile_bytes = h * w * D_CB * 2, stages = direct_p_stages(tile_bytes);
+      const int chunks = (c + D_CB - 1) / D_CB;
+      const int smem_p = stages * tile_bytes + 128 + 8 * stages + 64;
+      static bool set_p = false;
+      if (!set_p) { rc = set_smem(direct_p_kernel, 204 * 1024); if (rc) return rc; set_p = true; }
+      const long long total = (long long)chunks * n;
+      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(total, num_sms())));
+      direct_p_kernel<<<grid, DP_THREADS, smem_p, st>>>(m, a, chunks, stages, tile_bytes);
+      return check_launch("dwconv3x3 direct (persistent)");
+    }
     const int smem = h * w * D_CB * 2 + 128 + 64;
     static bool set = false;
     if (!set) { rc = set_smem(direct_kernel, D_MAX_PIX * D_CB * 2 + 128 + 64); if (rc) return rc; set = true; }
@@ -448,6 +637,17 @@ int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, con
     CUtensorMap m;
     int rc = make_x_map(&m, x, n, h, w, c, ldx, D_CB, w, h);
     if (rc) return rc;
+    if (tuning_direct_p()) {
+      const int tile_bytes = h * w * D_CB * 2, stages = direct_p_stages(tile_bytes);
+      const int chunks = (c + D_CB - 1) / D_CB;
+      const int smem_p = stages * tile_bytes + 128 + 8 * stages + 9 * D_CB * 4 + 64;
+      static bool set_p = false;
+      if (!set_p) { rc = set_smem(direct_p_wgrad_kernel, 204 * 1024); if (rc) return rc; set_p = true; }
+      const long long total = (long long)chunks * n;
+      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(total, num_sms())));
+      direct_p_wgrad_kernel<<<grid, DP_THREADS, smem_p, st>>>(m, a, chunks, stages, tile_bytes);
+      return check_launch("dwconv3x3 direct wgrad (persistent)");
+    }
     const int smem = h * w * D_CB * 2 + 128 + 64 + 9 * D_CB * 4;
     static bool set = false;
     if (!set) { rc = set_smem(direct_wgrad_kernel, D_MAX_PIX * D_CB * 2 + 128 + 64 + 9 * D_CB * 4); if (rc) return rc; set = true; }
