@@ -344,12 +344,10 @@ __global__ void __launch_bounds__(256) direct_wgrad_kernel(const __grid_constant
 // registers across all images of a chunk.
 constexpr int DP_THREADS = 512;
 
-struct ItemRange { long long i0, i1; };
-__device__ __forceinline__ ItemRange my_items(long long total) {
-  const long long per = (total + gridDim.x - 1) / gridDim.x;
-  const long long i0 = (long long)blockIdx.x * per;
-  return ItemRange{i0, i0 + per < total ? i0 + per : total};
-}
+// item k of CTA b is item number b + k * gridDim.x, channel chunk FASTEST (chunk = item % chunks, image = item / chunks):
+// at any moment the CTAs of the grid read adjacent 64-byte channel slices of the same pixel rows, i.e. whole DRAM pages
+// (a contiguous range of images per CTA scattered every CTA's 64-byte reads over its own pages: 2x slower).  The host
+// sizes the grid as a multiple of `chunks` when it can, so a CTA keeps its chunk (taps loaded once, one flush).
 
 __global__ void __launch_bounds__(DP_THREADS, 1) direct_p_kernel(const __grid_constant__ CUtensorMap tmX, const Args a,
                                                                  int chunks, int stages, int tile_bytes) {
@@ -357,27 +355,31 @@ __global__ void __launch_bounds__(DP_THREADS, 1) direct_p_kernel(const __grid_co
   uint8_t* tiles = align128(smem_raw);
   uint64_t* full = (uint64_t*)(tiles + (size_t)stages * tile_bytes);
   const int HW = a.H * a.W;
-  const ItemRange R = my_items((long long)chunks * a.N);
-  if (R.i0 >= R.i1) return;
+  const long long total = (long long)chunks * a.N;
+  const long long G = gridDim.x;
+  if ((long long)blockIdx.x >= total) return;
+  const int n_mine = (int)((total - blockIdx.x + G - 1) / G);
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  auto issue = [&](long long item, int s) {
-    const int chunk = (int)(item / a.N), n = (int)(item - (long long)chunk * a.N);
+  auto issue = [&](int k, int s) {
+    const long long item = (long long)blockIdx.x + (long long)k * G;
+    const int n = (int)(item / chunks), chunk = (int)(item - (long long)n * chunks);
     mbar_arrive_expect_tx(&full[s], (uint32_t)(HW * D_CB * 2));
     tc::tma_load_4d(tiles + (size_t)s * tile_bytes, &tmX, &full[s], chunk * D_CB, 0, 0, n);
   };
   if (threadIdx.x == 0)
-    for (int s = 0; s < stages && R.i0 + s < R.i1; ++s) issue(R.i0 + s, s);
+    for (int s = 0; s < stages && s < n_mine; ++s) issue(s, s);
   const int g = threadIdx.x & 3;
   int cur_chunk = -1;
   float wt[9][8];
-  for (long long item = R.i0; item < R.i1; ++item) {
-    const int k = (int)(item - R.i0), s = k % stages;
+  for (int k = 0; k < n_mine; ++k) {
+    const int s = k % stages;
     const uint32_t phase = (uint32_t)(k / stages) & 1u;
-    const int chunk = (int)(item / a.N), n = (int)(item - (long long)chunk * a.N);
+    const long long item = (long long)blockIdx.x + (long long)k * G;
+    const int n = (int)(item / chunks), chunk = (int)(item - (long long)n * chunks);
     const int c = chunk * D_CB + g * 8;
     if (chunk != cur_chunk) {
       cur_chunk = chunk;
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) direct_p_kernel(const __grid_co
     }
     fence_proxy_async();      // the generic reads of this stage are ordered before the bulk copy that refills it
     __syncthreads();
-    if (threadIdx.x == 0 && item + stages < R.i1) issue(item + stages, s);
+    if (threadIdx.x == 0 && k + stages < n_mine) issue(k + stages, s);
   }
 }
 
@@ -433,21 +435,24 @@ __global__ void __launch_bounds__(DP_THREADS, 1) direct_p_wgrad_kernel(const __g
   uint64_t* full = (uint64_t*)(tiles + (size_t)stages * tile_bytes);
   float* red = (float*)(full + stages);                   // [9][D_CB]
   const int HW = a.H * a.W;
-  const ItemRange R = my_items((long long)chunks * a.N);
-  if (R.i0 >= R.i1) return;
+  const long long total = (long long)chunks * a.N;
+  const long long G = gridDim.x;
+  if ((long long)blockIdx.x >= total) return;
+  const int n_mine = (int)((total - blockIdx.x + G - 1) / G);
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 9 * D_CB; i += DP_THREADS) red[i] = 0.f;
   __syncthreads();
-  auto issue = [&](long long item, int s) {
-    const int chunk = (int)(item / a.N), n = (int)(item - (long long)chunk * a.N);
+  auto issue = [&](int k, int s) {
+    const long long item = (long long)blockIdx.x + (long long)k * G;
+    const int n = (int)(item / chunks), chunk = (int)(item - (long long)n * chunks);
     mbar_arrive_expect_tx(&full[s], (uint32_t)(HW * D_CB * 2));
     tc::tma_load_4d(tiles + (size_t)s * tile_bytes, &tmX, &full[s], chunk * D_CB, 0, 0, n);
   };
   if (threadIdx.x == 0)
-    for (int s = 0; s < stages && R.i0 + s < R.i1; ++s) issue(R.i0 + s, s);
+    for (int s = 0; s < stages && s < n_mine; ++s) issue(s, s);
   const int g = threadIdx.x & 3;
   float acc[9][8] = {};
   // flush the partial sums of channel chunk `chunk`: registers -> shared (atomics) -> one global atomic per entry
@@ -464,11 +469,12 @@ __global__ void __launch_bounds__(DP_THREADS, 1) direct_p_wgrad_kernel(const __g
     }
     __syncthreads();
   };
-  int cur_chunk = (int)(R.i0 / a.N);
-  for (long long item = R.i0; item < R.i1; ++item) {
-    const int k = (int)(item - R.i0), s = k % stages;
+  int cur_chunk = (int)(blockIdx.x % chunks);
+  for (int k = 0; k < n_mine; ++k) {
+    const int s = k % stages;
     const uint32_t phase = (uint32_t)(k / stages) & 1u;
-    const int chunk = (int)(item / a.N), n = (int)(item - (long long)chunk * a.N);
+    const long long item = (long long)blockIdx.x + (long long)k * G;
+    const int n = (int)(item / chunks), chunk = (int)(item - (long long)n * chunks);
     if (chunk != cur_chunk) { flush(cur_chunk); cur_chunk = chunk; }
     const int c = chunk * D_CB + g * 8;
     const bf16* dyn = a.dy + (size_t)n * HW * a.lddy + c;
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) direct_p_wgrad_kernel(const __g
     }
     fence_proxy_async();
     __syncthreads();
-    if (threadIdx.x == 0 && item + stages < R.i1) issue(item + stages, s);
+    if (threadIdx.x == 0 && k + stages < n_mine) issue(k + stages, s);
   }
   flush(cur_chunk);
 }
@@ -590,7 +596,9 @@ int aadg_dwconv3x3(const void* x, int n, int h, int w, int c, int ldx, const flo
       static bool set_p = false;
       if (!set_p) { rc = set_smem(direct_p_kernel, 204 * 1024); if (rc) return rc; set_p = true; }
       const long long total = (long long)chunks * n;
-      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(total, num_sms())));
+      long long g = std::min<long long>(total, num_sms());
+      if (chunks <= g) g = g / chunks * chunks;           // a CTA keeps its channel chunk
+      dim3 grid((unsigned)std::max<long long>(1, g));
       direct_p_kernel<<<grid, DP_THREADS, smem_p, st>>>(m, a, chunks, stages, tile_bytes);
       return check_launch("dwconv3x3 direct (persistent)");
     }
@@ -644,7 +652,9 @@ int aadg_dwconv3x3_wgrad(const void* x, int n, int h, int w, int c, int ldx, con
       static bool set_p = false;
       if (!set_p) { rc = set_smem(direct_p_wgrad_kernel, 204 * 1024); if (rc) return rc; set_p = true; }
       const long long total = (long long)chunks * n;
-      dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(total, num_sms())));
+      long long g = std::min<long long>(total, num_sms());
+      if (chunks <= g) g = g / chunks * chunks;           // a CTA keeps its channel chunk: one flush
+      dim3 grid((unsigned)std::max<long long>(1, g));
       direct_p_wgrad_kernel<<<grid, DP_THREADS, smem_p, st>>>(m, a, chunks, stages, tile_bytes);
       return check_launch("dwconv3x3 direct wgrad (persistent)");
     }

@@ -518,7 +518,8 @@ def run_ours(a):
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")))
         if tj.get("conv_launches_per_step") == n_conv and tj.get("workload") == workload_config(a, 1)["workload"]:
             traffic = tj["dram_bytes_per_launch_avg"]
-            traffic_note = "avg DRAM bytes per conv launch, ncu --set full of the same command (profiles/r02_conv_traffic.json)"
+            traffic_note = ("avg DRAM bytes (dram__bytes_read + write) per conv call from an ncu capture of the same command's "
+                            "conv kernels (profiles/r02_conv_traffic.json; used because its launch list matches this run's)")
     except Exception:
         pass
     roof = {"bound": "tensor", "kernel": "aadg::tc::igemm_p_kernel / wgrad_kernel (all conv fprop+dgrad+wgrad launches)",
