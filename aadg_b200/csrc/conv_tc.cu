@@ -1269,11 +1269,57 @@ int aadg_conv_dgrad_bf16(const void* dy, int n, int ho, int wo, int cout, int ld
 
 /* dw[r*S+s][co][ci] += sum_{n,oy,ox} dy[n,oy,ox,co] * x[n, oy*stride-pad+r*dil, ox*stride-pad+s*dil, ci]
  * (fp32, accumulated: zero dw first for a fresh gradient). */
+static int wgrad_impl(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo, int cout,
+                      int lddy, int r, int s, int stride, int pad, int dil, float* dw, void* stream);
+
 int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo,
                          int cout, int lddy, int r, int s, int stride, int pad, int dil, float* dw, void* stream) {
   ConvGeom g{n, h, w, cin, ldx, ho, wo, cout, lddy, r, s, stride, pad, dil};
   int rc = check_geom(g);
   if (rc) return rc;
+  return wgrad_impl(x, n, h, w, cin, ldx, dy, ho, wo, cout, lddy, r, s, stride, pad, dil, dw, stream);
+}
+
+/* "Window" convolutions: a VALID (no padding), stride-1 convolution whose input pixel pitch `ldx` may be SMALLER than
+ * `cin`, i.e. every input "pixel" is a window of cin consecutive elements that overlaps its neighbours (the tensor map
+ * simply has a dimension whose stride is shorter than the extent of the dimension below it).  The caller chooses the
+ * output extent ho <= h - r + 1, wo <= w - s + 1 and guarantees that the windows it reaches stay inside the allocation
+ * (windows of the last pixels run past the tensor's nominal end by cin - ldx elements).  Used by the ResNet stem: the
+ * 7x7 / stride-2 convolution of models/__init__.py:17-23 (smp encoder conv1) over the space-to-depth image of
+ * aadg_stem_s2d is r = 4, s = 1, cin = 64, ldx = 16.  stat_sum / stat_sq optional (fused batch-norm statistics). */
+int aadg_conv_fprop_windows_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* wgt, int cout, int r,
+                                 int s, void* y, int ho, int wo, int ldy, float* stat_sum, float* stat_sq, void* stream) {
+  AADG_REQUIRE(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && r > 0 && s > 0 && r * s <= MAX_TAPS, "bad window-conv sizes");
+  AADG_REQUIRE(ho > 0 && wo > 0 && ho <= h - r + 1 && wo <= w - s + 1, "output %dx%d does not fit a valid %dx%d filter on %dx%d",
+               ho, wo, r, s, h, w);
+  AADG_REQUIRE((stat_sum == nullptr) == (stat_sq == nullptr), "pass both statistics buffers or neither");
+  Taps taps{};
+  taps.n = r * s;
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < s; ++j) {
+      taps.dy[i * s + j] = (short)i;
+      taps.dx[i * s + j] = (short)j;
+      taps.w[i * s + j] = (short)(i * s + j);
+    }
+  return launch_igemm(x, n, h, w, cin, ldx, 1, wgt, r * s, cout, taps, wo, ho, y, ho, wo, ldy, 0, 1, 0, 0, 0,
+                      (cudaStream_t)stream, stat_sum, stat_sq);
+}
+
+/* dw[t][co][k] += sum over output pixels of dy[n,oy,ox,co] * x_window[n, oy + i, ox + j][k], t = i*s + j: the weight
+ * gradient of aadg_conv_fprop_windows_bf16 (same geometry contract) */
+int aadg_conv_wgrad_windows_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo,
+                                 int cout, int lddy, int r, int s, float* dw, void* stream) {
+  AADG_REQUIRE(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && r > 0 && s > 0 && r * s <= MAX_TAPS, "bad window-conv sizes");
+  AADG_REQUIRE(ho > 0 && wo > 0 && ho <= h - r + 1 && wo <= w - s + 1, "output %dx%d does not fit a valid %dx%d filter on %dx%d",
+               ho, wo, r, s, h, w);
+  return wgrad_impl(x, n, h, w, cin, ldx, dy, ho, wo, cout, lddy, r, s, 1, 0, 1, dw, stream);
+}
+
+}  // extern "C"
+
+static int wgrad_impl(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo, int cout,
+                      int lddy, int r, int s, int stride, int pad, int dil, float* dw, void* stream) {
+  int rc = AADG_OK;
   AADG_REQUIRE(ldx % 8 == 0 && lddy % 8 == 0 && cin % 8 == 0 && cout % 8 == 0, "channels must be multiples of 8");
   AADG_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dw & 15) == 0 && cin % 4 == 0,
                "tensors must be 16-byte aligned");
@@ -1311,13 +1357,20 @@ int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, c
         ha.row_of_tap[t] = (short)q;
       }
       const int span = dx1 - dx0;
-      const int passes = (a.taps.n + 7) / 8;                     // 512 TMEM columns = 8 taps x 64
-      const int tpp = (a.taps.n + passes - 1) / passes;          // balanced: 3x3 -> 5 + 4
-      // a pass may touch at most 3 distinct rows (its shared-memory stage holds three)
-      for (int p = 0; ok && p < passes; ++p) {
-        const int t0 = p * tpp, t1 = std::min(a.taps.n, t0 + tpp);
-        if (ha.row_of_tap[t1 - 1] - ha.row_of_tap[t0] + 1 > 3 || ha.row_of_tap[t1 - 1] < ha.row_of_tap[t0]) ok = false;
+      // 512 TMEM columns = 8 taps x 64 per pass, taps balanced over the passes (3x3 -> 5 + 4); a pass may touch at most
+      // 3 distinct rows (its shared-memory stage holds three): more passes until that holds (4x1 -> 2 + 2)
+      int passes = (a.taps.n + 7) / 8, tpp = a.taps.n;
+      for (; ok && passes <= a.taps.n; ++passes) {
+        tpp = (a.taps.n + passes - 1) / passes;
+        bool fits = true;
+        for (int p = 0; p * tpp < a.taps.n; ++p) {
+          const int t0 = p * tpp, t1 = std::min(a.taps.n, t0 + tpp);
+          if (ha.row_of_tap[t1 - 1] - ha.row_of_tap[t0] + 1 > 3 || ha.row_of_tap[t1 - 1] < ha.row_of_tap[t0]) fits = false;
+        }
+        if (fits) break;
       }
+      if (passes > a.taps.n) ok = false;
+      passes = (a.taps.n + tpp - 1) / tpp;
       const int row_bytes = (int)align_up((size_t)(WH_PIX + span) * 128, 1024);
       const int smem = WH_STAGES * (WH_A_BYTES + 3 * row_bytes) + 1024 + 256;
       if (ok && WH_PIX + span <= 256 && smem <= 227 * 1024) {
@@ -1397,5 +1450,3 @@ int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, c
   if (stages == 3) return launch_wgrad_t<128, 3>(mDY, mX, a, grid, (cudaStream_t)stream);
   return launch_wgrad_t<128, 4>(mDY, mX, a, grid, (cudaStream_t)stream);
 }
-
-}  // extern "C"

@@ -915,6 +915,47 @@ __global__ void im2col_stem_kernel(const float* img, int N, int H, int W, int R,
   }
 }
 
+// ---- stem input in space-to-depth form ------------------------------------------------------------------------------
+// A 7x7 / stride-2 / pad-3 convolution over 3 channels is a 4x4 / stride-1 convolution over the 2x2 space-to-depth image
+// (12 channels, padded to 16): s2d pixel (Y, X) holds input pixels (2Y+py, 2X+px), channel (py*2 + px)*3 + c.  Written
+// here as bf16 [N, H/2 + 3, W/2 + 3, 16] with TWO zero rows / columns before and ONE after the image, so that output
+// pixel (oy, ox) needs the s2d rows oy..oy+3 and, in each, the FOUR CONSECUTIVE s2d pixels ox..ox+3 = 64 contiguous
+// bf16 = one 128-byte row of a tcgen05 A tile.  The convolution kernel reads those windows straight out of this buffer
+// with an overlapping tensor map (pixel pitch 16 elements, 64 "channels": aadg_conv_fprop_windows_bf16) -- the
+// 3.17 GB im2col patch buffer of round 1 (written once, read twice per step) is gone; this buffer is 0.3 GB.
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ img, int N, int H, int W,
+                                                       bf16* __restrict__ out) {
+  const int Hs = H / 2 + 3, Ws = W / 2 + 3;
+  const long long total = (long long)N * Hs * Ws;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int xs = (int)(e % Ws);
+    const long long q = e / Ws;
+    const int ys = (int)(q % Hs), n = (int)(q / Hs);
+    const int Y = ys - 2, X = xs - 2;
+    uint32_t wv[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (Y >= 0 && Y < H / 2 && X >= 0 && X < W / 2) {
+      float v[12];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(img + (((size_t)n * 3 + c) * H + 2 * Y + py) * W + 2 * X));
+          v[(py * 2 + 0) * 3 + c] = t.x;
+          v[(py * 2 + 1) * 3 + c] = t.y;
+        }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        wv[k] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + e * 16);
+    dst[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    dst[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+  }
+}
+
+
 // Row-pitched patch layout k = r*RP + s*3 + c (RP a multiple of 8, >= 3*S): the 3*S values of one filter row are
 // contiguous in an [x][c]-interleaved staged image row, so a (pixel, filter row) unit is a copy of RP/2 32-bit
 // words from shared memory (tail masked to zero) into RP/8 aligned 16-byte stores -- no per-element index table.
@@ -1318,6 +1359,16 @@ int aadg_im2col_stem_rows(const float* img, int n, int h, int w, int r, int s, i
   im2col_rows_kernel<<<n * ho, 256, smem, (cudaStream_t)stream>>>(img, n, h, w, r, s, stride, pad, ho, wo, row_pitch, kp,
                                                                  (bf16*)col);
   return check_launch("im2col rows");
+}
+
+/* fp32 NCHW image [n,3,h,w] (h, w even) -> bf16 space-to-depth stem input [n, h/2+3, w/2+3, 16] with its zero border
+ * (see stem_s2d_kernel); `out` must have 64 spare elements after the tensor (the last overlapping windows end there) */
+int aadg_stem_s2d(const float* img, int n, int h, int w, void* out, void* stream) {
+  AADG_REQUIRE(img && out && n > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "stem input must be [n,3,h,w] with even h, w");
+  AADG_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)img & 7) == 0, "stem tensors must be 16-byte (out) / 8-byte (img) aligned");
+  const long long total = (long long)n * (h / 2 + 3) * (w / 2 + 3);
+  stem_s2d_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(img, n, h, w, (bf16*)out);
+  return check_launch("stem space-to-depth");
 }
 
 int aadg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count, float lr,

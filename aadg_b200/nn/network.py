@@ -592,21 +592,54 @@ RESNETS = {
     "resnet34": (BasicBlock, [3, 4, 6, 3]),
     "resnet50": (Bottleneck, [3, 4, 6, 3]),
 }
-STEM_RP = 24    # stem patch layout k = r*24 + s*3 + c: 21 values of a filter row + 3 zeros (16-byte aligned rows)
+STEM_RP = 24    # im2col patch layout k = r*24 + s*3 + c (K.im2col_stem; the ResNet stem no longer uses it)
 STEM_KP = 7 * STEM_RP
 
 
+def _stem_maps():
+    """index maps between torch [64,3,7,7] stem weights and the window layout [4, 64, 64] of the space-to-depth stem
+    (K.stem_s2d + C.fprop_windows): tap t = s2d row offset, k = j*16 + (py*2 + px)*3 + c with j = s2d pixel inside the
+    four-pixel window; filter row r = 2t + py - 1, filter column s = 2j + px - 1 (entries with r or s = -1, and the
+    padding channels 12..15, carry no weight).  Returns (flat index into [3,7,7] per (t,k) or -1, validity mask)."""
+    idx = np.full((4, 64), -1, np.int64)
+    for t in range(4):
+        for j in range(4):
+            for py in range(2):
+                for px in range(2):
+                    r, s_ = 2 * t + py - 1, 2 * j + px - 1
+                    if r < 0 or s_ < 0:
+                        continue
+                    for c in range(3):
+                        idx[t, j * 16 + (py * 2 + px) * 3 + c] = (c * 7 + r) * 7 + s_
+    return idx
+
+
+_STEM_IDX = _stem_maps()
+
+
 def stem_pack(w):
-    """torch [64,3,7,7] -> [1,64,STEM_KP] in the row-pitched patch order of K.im2col_stem(row_pitch=STEM_RP)."""
+    """torch [64,3,7,7] -> [4, 64, 64] window layout (zeros where no filter tap lands)."""
     co = w.shape[0]
-    v = w.permute(0, 2, 3, 1).reshape(co, 7, 21)
-    return torch.cat([v, torch.zeros(co, 7, STEM_RP - 21, dtype=w.dtype, device=w.device)], 2).reshape(1, co, STEM_KP)
+    idx = torch.from_numpy(_STEM_IDX).to(w.device)
+    flat = torch.cat([w.reshape(co, 147), torch.zeros(co, 1, dtype=w.dtype, device=w.device)], 1)     # [-1] -> 0
+    out = flat[:, idx.reshape(-1)].reshape(co, 4, 64)          # index -1 picks the appended zero
+    return out.permute(1, 0, 2).contiguous()
 
 
 def stem_unpack(d):
-    """[1,64,STEM_KP] -> torch [64,3,7,7]"""
+    """[4, 64, 64] (weights or their gradient) -> torch [64,3,7,7]; every filter tap appears exactly once"""
     co = d.shape[1]
-    return d[0].reshape(co, 7, STEM_RP)[:, :, :21].reshape(co, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+    idx = torch.from_numpy(_STEM_IDX).to(d.device).reshape(-1)
+    valid = idx >= 0
+    out = torch.zeros(co, 147, dtype=d.dtype, device=d.device)
+    out[:, idx[valid]] = d.permute(1, 0, 2).reshape(co, 256)[:, valid]
+    return out.reshape(co, 3, 7, 7)
+
+
+def stem_mask(device):
+    """1 where a window-layout entry carries a filter tap, 0 elsewhere ([4, 1, 64]): the weight gradient of the window
+    convolution is dense, the entries that are structurally zero must stay zero"""
+    return torch.from_numpy((_STEM_IDX >= 0).astype(np.float32)).to(device).reshape(4, 1, 64)
 
 
 class ResNetEncoder:
@@ -619,7 +652,8 @@ class ResNetEncoder:
 
         def stem_init(shape):
             return stem_pack(kaiming_fan_out((64, 3, 7, 7)))
-        self.stem_w = store.add("encoder.conv1.weight", (1, 64, STEM_KP), "conv_nt", stem_init)
+        self.stem_w = store.add("encoder.conv1.weight", (4, 64, 64), "conv_nt", stem_init)
+        self.stem_mask = stem_mask(store.device)
         self.stem_bn = BatchNorm(store, "encoder.bn1", 64)
         self.blocks = []
         cin = 64
@@ -638,10 +672,28 @@ class ResNetEncoder:
             self.blocks.append(stage)
             self.out_channels.append(cin)
 
+    def stem_fprop(self, img, stats=None):
+        """conv1 (7x7 / stride 2 / pad 3, 3 -> 64) as a 4x1 window convolution over the space-to-depth image: returns
+        (window view kept for the weight gradient, pre-activation bf16 [N,H/2,W/2,64])"""
+        n, _, h, w = img.shape
+        _, xw = K.stem_s2d(img)
+        pre = C.fprop_windows(xw, self.stem_w.bf16, 4, 1, h // 2, w // 2, stats=stats,
+                              flops=2.0 * n * (h // 2) * (w // 2) * 64 * 147)       # the layer's own FLOPs
+        return xw, pre
+
+    def stem_wgrad(self, xw, dpre, out=None):
+        """weight gradient of conv1 in the window layout [4,64,64] (structural zeros masked), accumulated into `out`"""
+        n, ho, wo, _ = dpre.shape
+        dw = C.wgrad_windows(xw, dpre, 4, 1, flops=2.0 * n * ho * wo * 64 * 147)
+        dw.mul_(self.stem_mask)
+        if out is None:
+            return dw
+        out.add_(dw)
+        return out
+
     def forward(self, img, training):
-        col = K.im2col_stem(img, 7, 7, 2, 3, STEM_KP, row_pitch=STEM_RP)
         fused = training and FUSE_BN_STATS
-        pre = C.fprop(col, self.stem_w.bf16, 1, 1, stats=self.stem_bn.stats_buffers() if fused else None)
+        col, pre = self.stem_fprop(img, stats=self.stem_bn.stats_buffers() if fused else None)
         f1 = torch.empty_like(pre)
         self.stem_bn.forward(pre, f1, training, have_stats=fused)
         pooled, arg = K.maxpool_fwd(f1)
@@ -675,7 +727,7 @@ class ResNetEncoder:
             K.add_(d, skips[0])
         dpre = torch.empty_like(pre)
         self.stem_bn.backward(d, pre, f1, dpre)
-        on_side(lambda: C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=self.stem_w.grad), col, dpre)
+        on_side(lambda: self.stem_wgrad(col, dpre, out=self.stem_w.grad), col, dpre)
 
 
 class DepthwiseBN:

@@ -101,3 +101,43 @@ def wgrad(x, dy, r, s, stride, pad, dil, out=None, flops=None):
         _lib.check(_lib.lib().aadg_conv_wgrad_bf16(x.data_ptr(), n, h, w, cin, ldx, dy.data_ptr(), ho, wo, cout, lddy,
                                                    r, s, stride, pad, dil, out.data_ptr(), _lib.stream_ptr()))
     return out
+
+
+def fprop_windows(x, wgt, r, s, ho, wo, out=None, stats=None, flops=None):
+    """valid stride-1 convolution over OVERLAPPING channel windows (aadg_conv_fprop_windows_bf16): x is a bf16 view
+    [N,H,W,cin] whose pixel stride x.stride(2) may be smaller than cin (torch.as_strided over the space-to-depth stem
+    buffer); wgt bf16 [r*s, cout, cin] -> y bf16 [N,ho,wo,cout]."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        raise RuntimeError("x must be a CUDA bf16 [N,H,W,C] view (no CPU path)")
+    n, h, w, cin = x.shape
+    ldx = x.stride(2)
+    assert x.stride(3) == 1 and x.stride(1) == w * ldx and x.stride(0) == h * w * ldx
+    cout = wgt.shape[1]
+    assert wgt.shape == (r * s, cout, cin) and wgt.dtype == torch.bfloat16 and wgt.is_contiguous()
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+    _, oh, ow, oc, ldy = _nhwc(out, "out")
+    assert (oh, ow, oc) == (ho, wo, cout)
+    ssum, ssq = stats if stats is not None else (None, None)
+    with _lib.on_device(x.device), _timed("fprop", flops or 2.0 * n * ho * wo * cout * cin * r * s,
+                                              (n, h, w, cin, ho, wo, cout, r, 1, 1)):
+        _lib.check(_lib.lib().aadg_conv_fprop_windows_bf16(x.data_ptr(), n, h, w, cin, ldx, wgt.data_ptr(), cout, r, s,
+                                                           out.data_ptr(), ho, wo, ldy,
+                                                           ssum.data_ptr() if ssum is not None else None,
+                                                           ssq.data_ptr() if ssq is not None else None, _lib.stream_ptr()))
+    return out
+
+
+def wgrad_windows(x, dy, r, s, out=None, flops=None):
+    """weight gradient of fprop_windows: dw fp32 [r*s, cout, cin] (accumulated into `out`)."""
+    n, h, w, cin = x.shape
+    ldx = x.stride(2)
+    _, ho, wo, cout, lddy = _nhwc(dy, "dy")
+    if out is None:
+        out = torch.zeros((r * s, cout, cin), dtype=torch.float32, device=x.device)
+    assert out.shape == (r * s, cout, cin) and out.dtype == torch.float32 and out.is_contiguous()
+    with _lib.on_device(x.device), _timed("wgrad", flops or 2.0 * n * ho * wo * cout * cin * r * s,
+                                              (n, h, w, cin, ho, wo, cout, r, 1, 1)):
+        _lib.check(_lib.lib().aadg_conv_wgrad_windows_bf16(x.data_ptr(), n, h, w, cin, ldx, dy.data_ptr(), ho, wo, cout,
+                                                           lddy, r, s, out.data_ptr(), _lib.stream_ptr()))
+    return out

@@ -176,6 +176,21 @@ def dwconv3x3_wgrad(x, dy, dil, dw, stride=1):
               stride, p(dw))
 
 
+def stem_s2d(img):
+    """fp32 NCHW image [n,3,h,w] -> (buffer, windows): the bf16 space-to-depth stem input [n, h/2+3, w/2+3, 16] with its
+    zero border (aadg_stem_s2d) and the overlapping view [n, h/2+3, w/2+3, 64] (pixel stride 16) whose rows are the
+    four-pixel windows the stem convolution contracts over (ops.conv.fprop_windows)."""
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous()
+    hs, ws = h // 2 + 3, w // 2 + 3
+    flat = torch.empty(n * hs * ws * 16 + 64, dtype=torch.bfloat16, device=img.device)
+    flat[-64:].zero_()                      # the spare tail the last rows' windows end in (kept finite)
+    _call("aadg_stem_s2d", p(img), n, h, w, p(flat))
+    buf = flat[:n * hs * ws * 16].view(n, hs, ws, 16)
+    windows = torch.as_strided(flat, (n, hs, ws, 64), (hs * ws * 16, ws * 16, 16, 1))
+    return buf, windows
+
+
 def im2col_stem(img, r, s, stride, pad, kp, row_pitch=None):
     """fp32 NCHW image -> bf16 patches [n,ho,wo,kp]; k = (r*S+s)*3+c, or r*row_pitch + s*3 + c when row_pitch is given."""
     img = img.contiguous()

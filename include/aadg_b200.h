@@ -195,6 +195,19 @@ int aadg_conv_dgrad_bf16(const void* dy, int n, int ho, int wo, int cout, int ld
 int aadg_conv_wgrad_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo,
                          int cout, int lddy, int r, int s, int stride, int pad, int dil, float* dw, void* stream);
 
+/* "Window" convolutions (the ResNet stem, smp encoder conv1 = Conv2d(3, 64, 7, stride 2, padding 3) behind
+ * models/__init__.py:17-23): a VALID, stride-1 convolution whose input pixel pitch `ldx` may be SMALLER than `cin` --
+ * every input "pixel" is a window of `cin` consecutive elements overlapping its neighbours.  The caller picks the
+ * output extent (ho <= h - r + 1, wo <= w - s + 1) and guarantees the reached windows lie inside the allocation (the
+ * last ones end cin - ldx elements past the tensor's nominal end).  Over the space-to-depth image of aadg_stem_s2d
+ * the 7x7 / stride-2 stem is r = 4, s = 1, cin = 64, ldx = 16.  stat_sum / stat_sq (both or neither): fused
+ * batch-norm statistics as in aadg_conv_fprop_stats_bf16.  wgt bf16 [r*s][cout][cin]. */
+int aadg_conv_fprop_windows_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* wgt, int cout, int r,
+                                 int s, void* y, int ho, int wo, int ldy, float* stat_sum, float* stat_sq, void* stream);
+/* its weight gradient: dw fp32 [r*s][cout][cin] += sum over output pixels of dy (x) window */
+int aadg_conv_wgrad_windows_bf16(const void* x, int n, int h, int w, int cin, int ldx, const void* dy, int ho, int wo,
+                                 int cout, int lddy, int r, int s, float* dw, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * HBM-bound layers of the segmentation net (bf16 NHWC, channel strides `ld*` in elements, channel
  * counts multiples of 8, <= 2048) — the cuDNN/ATen batch-norm, ReLU, pooling, up-sampling and
@@ -283,6 +296,11 @@ int aadg_im2col_stem(const float* img, int n, int h, int w, int r, int s, int st
  * >= r*row_pitch; even stride): every filter row starts on a 16-byte boundary, the pass is a run copy */
 int aadg_im2col_stem_rows(const float* img, int n, int h, int w, int r, int s, int stride, int pad, int row_pitch,
                           int kp, void* col, void* stream);
+/* stem input in space-to-depth form (replaces the im2col patch buffer for the 7x7 / stride-2 stem): img fp32
+ * [n,3,h,w] (h, w even; the Normalize_dg / ToTensor output of data/transform.py:149-236) -> out bf16
+ * [n, h/2+3, w/2+3, 16]: s2d pixel (Y+2, X+2) holds input pixels (2Y+py, 2X+px) at channel (py*2+px)*3 + c, channels
+ * 12..15 and the border (two rows / columns before, one after) are zero.  `out` needs 64 spare elements at its end. */
+int aadg_stem_s2d(const float* img, int n, int h, int w, void* out, void* stream);
 /* torch.optim.Adam step `step` (1-based) over flat fp32 buffers */
 int aadg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long count, float lr,
                    float beta1, float beta2, float eps, float weight_decay, int step, void* stream);

@@ -12,7 +12,7 @@ things a whole-network comparison mixes:
 Because the rounding points coincide, the ReLU / ReLU6 masks of the two sides coincide (they are "teacher-forced" by
 construction) and the backward comparison is free of mask flips.
 
-Rounding points (aadg_b200/nn/network.py): the input image (im2col_stem writes bf16 patches), every convolution output
+Rounding points (aadg_b200/nn/network.py): the input image (the stem input is written as bf16), every convolution output
 (`pre`), every ReLU / ReLU6 output, every batch-norm output that is stored without an activation (downsample
 branches, MobileNetV2 linear bottlenecks without identity), the block output of a MobileNetV2 identity block, the
 pooled ASPP vector, both bilinear up-samplings of the decoder.  Not rounded: batch-norm outputs that feed a residual

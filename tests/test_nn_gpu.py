@@ -369,8 +369,7 @@ def test_stem_teacher_forced():
     d = K_mod().maxpool_bwd(nhwc(dy).to(BF), arg, f1m.shape)
     dpre = torch.empty_like(pre)
     net.encoder.stem_bn.backward(d, pre, f1m, dpre)
-    from aadg_b200.ops import conv as C
-    C.wgrad(col, dpre, 1, 1, 1, 0, 1, out=net.encoder.stem_w.grad)
+    net.encoder.stem_wgrad(col, dpre, out=net.encoder.stem_w.grad)
     bad = _grad_report(net, ref, "encoder.conv1", 0.99) + _grad_report(net, ref, "encoder.bn1", 0.99)
     assert not bad, bad
 

@@ -213,14 +213,14 @@ def layer_residuals(arch, encoder, classes, size, n, dataset, fp64=False):
                 walk(v)
     walk(net.encoder)
     walk(net.decoder)
-    if hasattr(net.encoder, "stem_w"):               # the stems run as 1x1 GEMMs over im2col patches
+    if hasattr(net.encoder, "stem_w"):
         cname = net.encoder.stem_w.name[:-len(".weight")]
         xin, want = io[cname]
-        if encoder == "mobilenet_v2":
+        if encoder == "mobilenet_v2":      # 3x3 / stride-2 stem: a 1x1 GEMM over im2col patches
             col = K.im2col_stem(xin.contiguous(), 3, 3, 2, 1, 3 * NW.MBV2_STEM_RP, row_pitch=NW.MBV2_STEM_RP)
-        else:
-            col = K.im2col_stem(xin.contiguous(), 7, 7, 2, 3, NW.STEM_KP, row_pitch=NW.STEM_RP)
-        got = C.fprop(col, net.encoder.stem_w.bf16, 1, 1)
+            got = C.fprop(col, net.encoder.stem_w.bf16, 1, 1)
+        else:                              # 7x7 / stride-2 stem: window convolution over the space-to-depth image
+            _, got = net.encoder.stem_fprop(xin.contiguous())
         rows.append((l2err(nchw(got), want), "stem conv", cname, tuple(xin.shape), ""))
         check_bn(net.encoder.stem_bn, want, True, encoder == "mobilenet_v2")
     rows.sort(reverse=True)
@@ -328,7 +328,7 @@ def backward_layer_residuals(arch, encoder, classes, size, n, dataset):
                 walk(v)
     walk(net.encoder)
     walk(net.decoder)
-    if hasattr(net.encoder, "stem_w"):               # stem weight gradient: a 1x1 GEMM over the im2col patches
+    if hasattr(net.encoder, "stem_w"):               # stem weight gradient
         cname = net.encoder.stem_w.name[:-len(".weight")]
         m = mods[cname]
         xin, dy = io[cname], gout[cname].to(BF).float()
@@ -337,8 +337,8 @@ def backward_layer_residuals(arch, encoder, classes, size, n, dataset):
             col = K.im2col_stem(xin.contiguous(), 3, 3, 2, 1, 3 * NW.MBV2_STEM_RP, row_pitch=NW.MBV2_STEM_RP)
             dw = NW.stem_unpack_rows(C.wgrad(col, nhwc(dy).to(BF), 1, 1, 1, 0, 1), 3, 3, NW.MBV2_STEM_RP)
         else:
-            col = K.im2col_stem(xin.contiguous(), 7, 7, 2, 3, NW.STEM_KP, row_pitch=NW.STEM_RP)
-            dw = NW.stem_unpack(C.wgrad(col, nhwc(dy).to(BF), 1, 1, 1, 0, 1))
+            xw, _ = net.encoder.stem_fprop(xin.contiguous())
+            dw = NW.stem_unpack(net.encoder.stem_wgrad(xw, nhwc(dy).to(BF)))
         rows.append((l2err(dw, dw64), "stem wgrad", cname, str(tuple(xin.shape))))
     rows.sort(reverse=True)
     return rows
