@@ -1,14 +1,20 @@
 #!/usr/bin/env python
 """Headline benchmark: joint search+train images/sec of one AADG search step (BASELINE.json config 2).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a engine)
-    python bench.py --impl reference --steps K --warmup W     # the reference algorithm's CPU path
+    python bench.py --gpus N --steps K --warmup W             # our arm (sm_100a engine); torchrun for N > 1
+    python bench.py --gpus N --scaling strong                  # BASELINE config 3: config 2's 24 sources sharded over N GPUs
+    python bench.py --arch unet --backbone resnet34 --dataset vessel --size 1024 --items 1     # config 4 (per GPU)
+    python bench.py --impl reference --steps K --warmup W      # the reference algorithm's CPU path (oracle port)
 
-A step = augment (uint8 bank, M=6 policies x L=2 ops, Normalize_dg/ToTensor) -> DeepLabV3+/ResNet-50
-forward -> momentum-discriminator features -> 18 Sinkhorn divergences -> BCE backward -> Adam (+ the
-discriminator step) on B*D*M = 8*3*6 = 144 synthetic 512x512 fundus images per GPU (weak scaling:
-every rank owns its own 24 source images; gradients all-reduced, features all-gathered over NCCL).
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+A step = augment (uint8 bank, M=6 policies x L=2 ops, DGRandomScaleCrop, Normalize_dg/ToTensor) -> DeepLabV3+/ResNet-50
+forward -> momentum-discriminator features -> 18 Sinkhorn divergences -> BCE backward -> Adam (+ the discriminator
+step) on B*D*M = 8*3*6 = 144 synthetic 512x512 fundus images per GPU (weak scaling: every rank owns its own 24 source
+images; strong scaling: the 24 source images are sharded; gradients all-reduced in buckets from the backward pass,
+features all-gathered over NCCL).  The model part of the step replays a captured CUDA graph (--graph 0: eager).
+Prints ONE JSON line (rank 0): value / e2e / roofline (conv family vs the measured sustained bf16 peak, with the ncu
+DRAM traffic when profiles/r02_conv_traffic.json matches the launch list) / extra (BASELINE's second metric: Sinkhorn
+iterations/s at N = 65536 and the uint8 bank at batch 512 vs the measured HBM peak) / cpu_baseline.  DESIGN.md
+"Measurement" explains every field.
 """
 import argparse
 import json

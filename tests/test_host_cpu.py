@@ -266,3 +266,50 @@ def test_reference_arm_times_real_steps():
     assert line["ms_per_step"] * line["steps"] / 1e3 <= wall
     assert abs(line["value"] - line["images_per_timed_step"] / (line["ms_per_step"] / 1e3)) < 1e-6 * line["value"]
     assert line["e2e"]["value"] == line["value"] and line["gpu_launches"] == 0
+
+
+def test_space_to_depth_stem_index_maps_reproduce_the_7x7_stride2_convolution():
+    """The ResNet stem runs as a 4x1 window convolution over the 2x2 space-to-depth image (csrc: aadg_stem_s2d +
+    aadg_conv_fprop_windows_bf16; DESIGN.md "ResNet stem without im2col").  Its index maps are host code: restated here
+    in plain torch on the CPU -- s2d buffer with the zero border, overlapping four-pixel windows, the packed weights --
+    and compared with F.conv2d(7x7, stride 2, padding 3) and its weight gradient (smp encoder conv1 behind
+    models/__init__.py:17-23)."""
+    import torch
+    from aadg_b200.nn import network as NW
+    torch.manual_seed(0)
+    w = torch.randn(64, 3, 7, 7)
+    w4 = NW.stem_pack(w)
+    assert w4.shape == (4, 64, 64) and torch.equal(NW.stem_unpack(w4), w)
+    assert int(NW.stem_mask("cpu").sum()) == 147                     # every filter tap appears exactly once
+    assert float((w4 * (1 - NW.stem_mask("cpu"))).abs().sum()) == 0.0  # structural zeros
+    n, h, wd = 2, 20, 24
+    img = torch.randn(n, 3, h, wd)
+    hs, ws = h // 2 + 3, wd // 2 + 3
+    buf = torch.zeros(n, hs, ws, 16)
+    for py in range(2):
+        for px in range(2):
+            for c in range(3):
+                buf[:, 2:2 + h // 2, 2:2 + wd // 2, (py * 2 + px) * 3 + c] = img[:, c, py::2, px::2]
+    flat = torch.cat([buf.reshape(-1), torch.zeros(64)])
+    xw = torch.as_strided(flat, (n, hs, ws, 64), (hs * ws * 16, ws * 16, 16, 1))
+    ho, wo = h // 2, wd // 2
+    out = sum(torch.einsum("nhwk,ok->nhwo", xw[:, t:t + ho, 0:wo, :], w4[t]) for t in range(4))
+    ref = torch.nn.functional.conv2d(img, w, None, 2, 3).permute(0, 2, 3, 1)
+    assert float((out - ref).abs().max()) < 1e-4
+    dy = torch.randn(n, ho, wo, 64)
+    dw4 = torch.stack([torch.einsum("nhwo,nhwk->ok", dy, xw[:, t:t + ho, 0:wo, :]) for t in range(4)]) * NW.stem_mask("cpu")
+    gw = torch.nn.grad.conv2d_weight(img, w.shape, dy.permute(0, 3, 1, 2), 2, 3)
+    assert float((NW.stem_unpack(dw4) - gw).abs().max()) < 1e-3
+
+
+def test_resident_pool_flat_indices_are_the_collate_order():
+    """ResidentPools.flat_indices: [B, D] pool-local draws -> flat indices into the concatenated pools in the
+    reference's collate order b*D + d (data/transform.py:323-340), domains alongside; out-of-range draws raise"""
+    from aadg_b200.data.pool import ResidentPools
+    imgs = {"A": np.zeros((5, 8, 8, 3), np.uint8), "B": np.zeros((4, 8, 8, 3), np.uint8), "C": np.zeros((6, 8, 8, 3), np.uint8)}
+    msks = {k: np.zeros(v.shape[:3], np.uint8) for k, v in imgs.items()}
+    pools = ResidentPools(imgs, msks, device="cpu")
+    flat, dom = pools.flat_indices(np.array([[4, 0, 5], [1, 3, 2]]))
+    assert flat.tolist() == [4, 5 + 0, 9 + 5, 1, 5 + 3, 9 + 2] and dom == [0, 1, 2, 0, 1, 2]
+    with pytest.raises(IndexError):
+        pools.flat_indices(np.array([[5, 0, 0]]))
