@@ -80,7 +80,8 @@ def shutdown(engines=(), timeout_s=20.0):
     for e in engines:
         e.close()
     gc.collect()
-    torch.cuda.synchronize()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     dist.destroy_process_group()
     watchdog.cancel()
 

@@ -114,7 +114,9 @@ def _exchange_worker(rank, world, port, q):
     red.wait()               # the rest ([0, 10)) goes out here
     assert red.hi == 40 and not red.works
     q.put((rank, all_f.numpy(), all_dc.numpy(), grads.numpy(), shard_sources(24, rank, world), flat.numpy()))
-    dist.destroy_process_group()
+    from aadg_b200.host.search import shutdown
+    shutdown()               # the watchdog-guarded teardown bench.py and the scripts use
+    assert not dist.is_initialized()
 
 
 def test_world_size_2_exchange_gloo():
