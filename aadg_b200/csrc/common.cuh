@@ -56,6 +56,13 @@ struct Arena {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
+// Aligned view of the dynamic shared memory that KEEPS ITS ADDRESS SPACE: the padding is computed on the 32-bit shared
+// address and added to the original pointer.  Rounding the generic pointer through uintptr_t loses the provenance and
+// every access through it compiles to a generic LD.E / ST.E with 64-bit address arithmetic instead of LDS / STS.
+__device__ __forceinline__ uint8_t* align_smem(uint8_t* p, uint32_t a) {
+  const uint32_t s = smem_u32(p);
+  return p + (((s + a - 1u) & ~(a - 1u)) - s);
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

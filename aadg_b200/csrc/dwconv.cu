@@ -59,7 +59,7 @@ __device__ __forceinline__ void load_w8(const float* w, float* f) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(w)), b = __ldg(reinterpret_cast<const float4*>(w + 4));
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
-__device__ __forceinline__ uint8_t* align128(uint8_t* p) { return (uint8_t*)(((uintptr_t)p + 127) & ~(uintptr_t)127); }
+__device__ __forceinline__ uint8_t* align128(uint8_t* p) { return align_smem(p, 128u); }
 
 struct Args {
   int N, H, W, C;

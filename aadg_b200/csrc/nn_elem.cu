@@ -838,6 +838,162 @@ __global__ void __launch_bounds__(256) dw3x3_strided_wgrad_kernel(const bf16* __
   block_channel_sum<1>(C, acc[2], z, dw + (size_t)(r * 3 + 2) * C, nullptr);
 }
 
+// ---- stride 2, dilation 1 (every down-sampling depthwise layer of MobileNetV2): channel-stationary threads --------
+// The generic strided kernels above decode (n, y, x, group) from a 64-bit flat index per element and re-read the taps
+// from L1 per tap: measured instruction-bound (MobileNetV2 @256^2: forward 120 us, data gradient 300 us, weight
+// gradient 250 us per launch against 30-90 us of HBM time).  Here a thread owns ONE 8-channel group for its whole life
+// (its 9 x 8 taps live in registers), blockIdx.y walks the images and the pixel index inside an image is 32-bit: one
+// 32-bit division per pixel.  block = 256 threads = (256 / G) pixel lanes x G groups (G = C / 8 <= 256).
+//   forward        one output pixel per trip, 9 loads
+//   data gradient  one 2x2 input quad (rows 2a, 2a+1; columns 2b, 2b+1) per trip: with stride 2 the quad is covered by
+//                  exactly the four outputs (a..a+1, b..b+1), each loaded once, and every tap is used exactly once
+//                  (same accumulation order as the generic gather: filter row, then filter column)
+//   weight grad.   9 x 8 register accumulators over the thread's pixels, shared-memory then global reduction per CTA
+__device__ __forceinline__ void s2_load_taps(const float* __restrict__ wgt, int C, int g, float (&wt)[9][8]) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const V8 w8 = ld8f(wgt + (size_t)t * C + g * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wt[t][i] = w8.v[i];
+  }
+}
+__global__ void __launch_bounds__(256, 2) dw3x3_s2_fwd_kernel(const bf16* __restrict__ x, int H, int W, int C, int ldx,
+                                                           const float* __restrict__ wgt, bf16* __restrict__ y, int Ho, int Wo,
+                                                           int ldy) {
+  const int G = C >> 3, lanes = 256 / G;
+  const int lane = threadIdx.x / G, g = threadIdx.x - lane * G;
+  if (lane >= lanes) return;
+  const int n = blockIdx.y, P = Ho * Wo;
+  float wt[9][8];
+  s2_load_taps(wgt, C, g, wt);
+  const bf16* xn = x + (size_t)n * H * W * ldx + g * 8;
+  bf16* yn = y + (size_t)n * P * ldy + g * 8;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int q = blockIdx.x * lanes + lane; q < P; q += gridDim.x * lanes) {
+    const int oy = q / Wo, ox = q - oy * Wo;
+    const int iy0 = 2 * oy - 1, ix0 = 2 * ox - 1;
+    uint4 raw[9];                                          // all nine loads in flight before the first use
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int iy = iy0 + r, ix = ix0 + s2;
+        const bool ok = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+        raw[r * 3 + s2] = ok ? ldg16(xn + (size_t)(iy * W + ix) * ldx) : zero;
+      }
+    V8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const V8 v = unpack8(raw[t]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wt[t][i], v.v[i], acc.v[i]);
+    }
+    st8(yn + (size_t)q * ldy, acc);
+  }
+}
+__global__ void __launch_bounds__(256, 2) dw3x3_s2_dgrad_kernel(const bf16* __restrict__ dy, int Ho, int Wo, int C, int lddy,
+                                                             const float* __restrict__ wgt, bf16* __restrict__ dx, int H, int W,
+                                                             int lddx) {
+  const int G = C >> 3, lanes = 256 / G;
+  const int lane = threadIdx.x / G, g = threadIdx.x - lane * G;
+  if (lane >= lanes) return;
+  const int n = blockIdx.y;
+  const int Hq = (H + 1) >> 1, Wq = (W + 1) >> 1;          // quads; Hq == Ho and Wq == Wo for a 3x3 / stride-2 / pad-1 layer
+  float wt[9][8];
+  s2_load_taps(wgt, C, g, wt);
+  const bf16* dyn = dy + (size_t)n * Ho * Wo * lddy + g * 8;
+  bf16* dxn = dx + (size_t)n * H * W * lddx + g * 8;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int q = blockIdx.x * lanes + lane; q < Hq * Wq; q += gridDim.x * lanes) {
+    const int a = q / Wq, b = q - a * Wq;
+    const bool a1 = a + 1 < Ho, b1 = b + 1 < Wo, in = a < Ho && b < Wo;
+    const bf16* d = dyn + (size_t)(a * Wo + b) * lddy;
+    const V8 d00 = unpack8(in ? ldg16(d) : zero);
+    const V8 d01 = unpack8(in && b1 ? ldg16(d + lddy) : zero);
+    const V8 d10 = unpack8(in && a1 ? ldg16(d + (size_t)Wo * lddy) : zero);
+    const V8 d11 = unpack8(in && a1 && b1 ? ldg16(d + (size_t)(Wo + 1) * lddy) : zero);
+    const int iy = 2 * a, ix = 2 * b;
+    bf16* o = dxn + (size_t)(iy * W + ix) * lddx;
+    V8 acc;
+    // (even row, even column): tap (1,1) of output (a, b)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = wt[4][i] * d00.v[i];
+    st8(o, acc);
+    if (ix + 1 < W) {   // (even, odd): tap (1,0) of (a, b+1), tap (1,2) of (a, b)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wt[5][i], d00.v[i], wt[3][i] * d01.v[i]);
+      st8(o + lddx, acc);
+    }
+    if (iy + 1 < H) {
+      // (odd, even): tap (0,1) of (a+1, b), tap (2,1) of (a, b)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc.v[i] = fmaf(wt[7][i], d00.v[i], wt[1][i] * d10.v[i]);
+      st8(o + (size_t)W * lddx, acc);
+      if (ix + 1 < W) {   // (odd, odd): taps (0,0) of (a+1, b+1), (0,2) of (a+1, b), (2,0) of (a, b+1), (2,2) of (a, b)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          acc.v[i] = fmaf(wt[8][i], d00.v[i], fmaf(wt[6][i], d01.v[i], fmaf(wt[2][i], d10.v[i], wt[0][i] * d11.v[i])));
+        st8(o + (size_t)(W + 1) * lddx, acc);
+      }
+    }
+  }
+}
+// work item = (image, block of `lanes * S2_WG_PIX` output pixels); the grid is ONE wave of CTAs striding over the items
+constexpr int S2_WG_PIX = 8;
+__global__ void __launch_bounds__(256, 2) dw3x3_s2_wgrad_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int ldx,
+                                                             const bf16* __restrict__ dy, int Ho, int Wo, int lddy, float* dw,
+                                                             int blocks_per_image) {
+  extern __shared__ float s_dw9[];                        // [9][C]
+  const int G = C >> 3, lanes = 256 / G;
+  const int lane = threadIdx.x / G, g = threadIdx.x - lane * G;
+  const int P = Ho * Wo;
+  for (int i = threadIdx.x; i < 9 * C; i += 256) s_dw9[i] = 0.f;
+  __syncthreads();
+  if (lane < lanes) {
+    float acc[9][8] = {};
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const int items = N * blocks_per_image;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int n = item / blocks_per_image, blk = item - n * blocks_per_image;
+      const bf16* xn = x + (size_t)n * H * W * ldx + g * 8;
+      const bf16* dyn = dy + (size_t)n * P * lddy + g * 8;
+      const int q0 = blk * lanes * S2_WG_PIX + lane;
+#pragma unroll 1
+      for (int j = 0; j < S2_WG_PIX; ++j) {
+        const int q = q0 + j * lanes;
+        if (q >= P) break;
+        const int oy = q / Wo, ox = q - oy * Wo;
+        const int iy0 = 2 * oy - 1, ix0 = 2 * ox - 1;
+        const uint4 draw = ldg16(dyn + (size_t)q * lddy);
+        uint4 raw[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s2 = 0; s2 < 3; ++s2) {
+            const int iy = iy0 + r, ix = ix0 + s2;
+            const bool ok = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+            raw[r * 3 + s2] = ok ? ldg16(xn + (size_t)(iy * W + ix) * ldx) : zero;
+          }
+        const V8 d = unpack8(draw);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const V8 v = unpack8(raw[t]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(d.v[i], v.v[i], acc[t][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&s_dw9[t * C + g * 8 + i], acc[t][i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * C; i += 256) atomicAdd(&dw[i], s_dw9[i]);
+}
+
 // dw[t][c] += sum_px dy[px][c] * x[px + off_t][c]; blockIdx.y = filter row r (3 taps, 24 register accumulators),
 // the three launches' dy reads overlap in L2; block reduction in shared memory [3][C], then atomics
 __global__ void __launch_bounds__(256, 3) dw3x3_wgrad_kernel(const bf16* x, int N, int H, int W, int C, int ldx,
@@ -1099,8 +1255,28 @@ int dwconv3x3_wgrad_generic(const void* x, int n, int h, int w, int c, int ldx, 
   return check_launch("dwconv3x3 wgrad");
 }
 
+// the channel-stationary stride-2 kernels: 3x3 / stride 2 / dilation 1 / pad 1, up to 2048 channels, 32-bit in-image
+// indices; AADG_DW_S2=0 falls back to the generic strided kernels
+static bool s2_fast(int c, int dil, int stride, int n, int h, int w, int ho, int wo) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("AADG_DW_S2"); on = e ? atoi(e) : 1; }
+  return on && stride == 2 && dil == 1 && c >= 8 && c / 8 <= 256 && n <= 65535 && (long long)h * w < (1ll << 30) &&
+         ho == (h - 1) / 2 + 1 && wo == (w - 1) / 2 + 1;
+}
 int dwconv3x3_strided(const void* x, int n, int h, int w, int c, int ldx, const float* wgt, int dil, int stride, int direction,
                       void* y, int ho, int wo, int ldy, cudaStream_t st) {
+  if (s2_fast(c, dil, stride, n, h, w, ho, wo)) {
+    const int lanes = 256 / (c / 8);
+    if (direction == 0) {
+      dim3 grid(std::max(1, std::min((ho * wo + lanes * 8 - 1) / (lanes * 8), 4096)), n);
+      dw3x3_s2_fwd_kernel<<<grid, 256, 0, st>>>((const bf16*)x, h, w, c, ldx, wgt, (bf16*)y, ho, wo, ldy);
+    } else {      // x = dy [n,ho,wo], y = dx [n,h,w]; one 2x2 input quad per thread and trip
+      const int quads = ((h + 1) / 2) * ((w + 1) / 2);
+      dim3 grid(std::max(1, std::min((quads + lanes * 4 - 1) / (lanes * 4), 4096)), n);
+      dw3x3_s2_dgrad_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ho, wo, c, ldx, wgt, (bf16*)y, h, w, ldy);
+    }
+    return check_launch("dwconv3x3 stride 2");
+  }
   if (direction == 0)
     dw3x3_strided_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), 256, 0, st>>>(
         (const bf16*)x, n, h, w, c, ldx, wgt, dil, stride, (bf16*)y, ho, wo, ldy);
@@ -1111,6 +1287,14 @@ int dwconv3x3_strided(const void* x, int n, int h, int w, int c, int ldx, const 
 }
 int dwconv3x3_strided_wgrad(const void* x, int n, int h, int w, int c, int ldx, const void* dy, int ho, int wo, int lddy,
                             int dil, int stride, float* dw, cudaStream_t st) {
+  if (s2_fast(c, dil, stride, n, h, w, ho, wo) && (size_t)9 * c * sizeof(float) <= 48 * 1024) {
+    const int lanes = 256 / (c / 8);
+    const int bpi = (ho * wo + lanes * S2_WG_PIX - 1) / (lanes * S2_WG_PIX);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)n * bpi, (long long)num_sms_nn() * 2));   // 2 CTAs per SM: one wave
+    dw3x3_s2_wgrad_kernel<<<grid, 256, (size_t)9 * c * sizeof(float), st>>>((const bf16*)x, n, h, w, c, ldx, (const bf16*)dy,
+                                                                         ho, wo, lddy, dw, bpi);
+    return check_launch("dwconv3x3 stride 2 wgrad");
+  }
   const long long pixels = (long long)n * ho * wo;
   const dim3 blk = reduce_block(c);
   const int blocks = (int)std::max<long long>(1, std::min<long long>((pixels + blk.y * 16 - 1) / (blk.y * 16), 148 * 4));

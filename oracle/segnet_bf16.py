@@ -48,10 +48,17 @@ def _conv_forward_bf16_weight(m):
     return forward
 
 
-def install(model, head_name="segmentation_head"):
-    """turn a DeepLabV3PlusTorch / UnetTorch into its bf16-storage twin (in place); returns the model"""
+def install(model, head_name="segmentation_head", keep_fp32=(), round_weights=True, round_activations=True,
+            round_input=True):
+    """turn a DeepLabV3PlusTorch / UnetTorch into its bf16-storage twin (in place); returns the model.
+
+    The defaults are the engine's storage points.  The keyword arguments exist for the precision-attribution study
+    (`scripts/precision_attribution.py`): modules whose qualified name starts with one of `keep_fp32` keep fp32 storage
+    and fp32 weights; `round_weights` / `round_activations` / `round_input` switch one class of rounding points off."""
     from torchvision.models.mobilenetv2 import InvertedResidual
     from torchvision.models.resnet import BasicBlock, Bottleneck
+    keep = tuple(keep_fp32)
+    kept = {mod for name, mod in model.named_modules() if any(name == k or name.startswith(k + ".") for k in keep)}
     unrounded_bn = set()
     for mod in model.modules():
         if isinstance(mod, Bottleneck):
@@ -61,16 +68,20 @@ def install(model, head_name="segmentation_head"):
         elif isinstance(mod, InvertedResidual):
             if mod.use_res_connect:
                 unrounded_bn.add(mod.conv[-1])
-                mod.register_forward_hook(_round_out)
+                if round_activations and mod not in kept:
+                    mod.register_forward_hook(_round_out)
     head = getattr(model, head_name)
     head_mods = set(head.modules())
     for mod in model.modules():
-        if mod in head_mods:
+        if mod in head_mods or mod in kept:
             continue
         if isinstance(mod, nn.Conv2d):
-            if mod.groups == 1:
+            if mod.groups == 1 and round_weights:
                 mod.forward = _conv_forward_bf16_weight(mod)
-            mod.register_forward_hook(_round_out)
+            if round_activations:
+                mod.register_forward_hook(_round_out)
+        elif not round_activations:
+            continue
         elif isinstance(mod, (nn.ReLU, nn.ReLU6)):
             mod.inplace = False
             mod.register_forward_hook(_round_out)
@@ -78,5 +89,6 @@ def install(model, head_name="segmentation_head"):
             mod.register_forward_hook(_round_out)         # harmless before a ReLU: rounding commutes with it
         elif isinstance(mod, (nn.UpsamplingBilinear2d, nn.AdaptiveAvgPool2d)) and mod is not getattr(model, "pool", None):
             mod.register_forward_hook(_round_out)
-    model.register_forward_pre_hook(lambda _m, args: (rb(args[0]),) + tuple(args[1:]))
+    if round_input:
+        model.register_forward_pre_hook(lambda _m, args: (rb(args[0]),) + tuple(args[1:]))
     return model

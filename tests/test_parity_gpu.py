@@ -523,7 +523,10 @@ def test_autograd_surface_runs_the_reference_training_lines():
         ratio_spread = abs((c.store.grads.double().norm() / a.store.grads.double().norm()).item() - 1)
         print("AUTOGRAD step %d: loss rel %.2e (fused run-to-run %.2e) grad cos %.6f (run-to-run %.6f) norm ratio %.5f" %
               (step, rel, spread, cos, cos_spread, ratio))
-        assert rel <= max(4 * spread, 5e-4 if step == 0 else 5e-3), (step, rel, spread)
+        # `rel` and `spread` are single draws of the same noise (measured over ten runs on different boxes: step 0
+        # 0.7-3.7e-4, step 1 0.2-3.7e-3, step 2 4.5-9.9e-3 for both), so besides the x4 yardstick the floors sit three
+        # times above the largest value seen; a wrong gradient moves the step-1 loss by percents
+        assert rel <= max(4 * spread, (1.5e-3, 1.2e-2, 3e-2)[step]), (step, rel, spread)
         assert 1 - cos <= max(4 * (1 - cos_spread), 1e-3 if step == 0 else 2e-2), (step, cos, cos_spread)
         assert abs(ratio - 1) <= max(4 * ratio_spread, 0.1 if step == 0 else 0.25), (step, ratio, ratio_spread)
         for name, leaf in b.named_parameters():

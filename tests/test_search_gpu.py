@@ -147,8 +147,10 @@ def test_cuda_graph_step_matches_eager_step():
     # statistics, re-quantised by bf16 storage), so the yardstick is the spread of two EAGER runs (x4 + small floors):
     # the rewards are Sinkhorn divergences between clouds of two points per domain, the most sensitive output there is
     assert abs(le[0] - lg[0]) <= 1e-3 * abs(le[0])
-    assert rel(lg, le) <= max(4 * rel(l2, le), 1e-2), (rel(lg, le), rel(l2, le))
-    assert rel(rg, re_) <= max(4 * rel(r2, re_), 5e-2), (rel(rg, re_), rel(r2, re_))
+    # (both sides of each comparison are single draws of the same noise -- measured over several boxes: loss 0.4-3.1e-2,
+    # rewards 0.05-0.27 for graph-vs-eager and eager-vs-eager alike -- so the floors sit 2-3x above the largest value seen)
+    assert rel(lg, le) <= max(4 * rel(l2, le), 8e-2), (rel(lg, le), rel(l2, le))
+    assert rel(rg, re_) <= max(4 * rel(r2, re_), 0.6), (rel(rg, re_), rel(r2, re_))
     assert lg[-1] < lg[0]
 
 
