@@ -53,7 +53,7 @@ def install(model, head_name="segmentation_head", keep_fp32=(), round_weights=Tr
     """turn a DeepLabV3PlusTorch / UnetTorch into its bf16-storage twin (in place); returns the model.
 
     The defaults are the engine's storage points.  The keyword arguments exist for the precision-attribution study
-    (`scripts/precision_attribution.py`): modules whose qualified name starts with one of `keep_fp32` keep fp32 storage
+    (`tests/tools/precision_attribution.py`): modules whose qualified name starts with one of `keep_fp32` keep fp32 storage
     and fp32 weights; `round_weights` / `round_activations` / `round_input` switch one class of rounding points off."""
     from torchvision.models.mobilenetv2 import InvertedResidual
     from torchvision.models.resnet import BasicBlock, Bottleneck

@@ -426,7 +426,17 @@ def test_engine_vs_fp32_oracle_on_conditioned_weights(arch, encoder, classes, si
     # 1 - cosine).  Gradients that bf16 storage leaves well conditioned (twin cosine >= 0.99) are additionally held to 0.97.
     offenders = sorted(((name, round(cos, 4), round(twin_cos.get(name, 1.0), 4)) for name, cos, _ in rows
                         if (1 - cos) > 3 * (1 - twin_cos.get(name, 1.0)) + 0.02), key=lambda r: r[1])
-    judged = sorted((r for r in rows if twin_cos.get(r[0], 0.0) >= 0.99), key=lambda r: r[1])
+    # The ASPP pooling branch normalises n values per channel (its map is 1x1): a channel whose n pre-BN values nearly
+    # coincide has invstd up to eps^-1/2 = 316 and a gradient row that is amplified noise.  Repeating one engine step 300
+    # times on fixed weights (scripts/stress_repeat.py, profiles/r02_stress_repeat_resnet18.log, n = 8) gives that
+    # convolution's weight gradient a median run-to-run cosine of 0.9991 with a tail down to 0.948, 88 % of the deviation
+    # in ONE output channel; against the fp32 oracle one suite run in ~15 saw 0.81.  Those parameters are held to a
+    # sanity floor here and count fully in the whole-gradient cosine below.
+    chaotic = lambda nm: nm.startswith("decoder.aspp.0.convs.4.")      # noqa: E731
+    pool_rows = [r for r in rows if chaotic(r[0])]
+    rows_judged = [r for r in rows if not chaotic(r[0])]
+    offenders = [o for o in offenders if not chaotic(o[0])]
+    judged = sorted((r for r in rows_judged if twin_cos.get(r[0], 0.0) >= 0.99), key=lambda r: r[1])
 
     def flat(table_names, getter):
         return torch.cat([getter(nm).reshape(-1).double() for nm in table_names])
@@ -454,6 +464,7 @@ def test_engine_vs_fp32_oracle_on_conditioned_weights(arch, encoder, classes, si
     assert (1 - cos_e) <= 2 * (1 - cos_t) + 2e-3, (cos_e, cos_t)
     assert len(offenders) <= 0.02 * len(rows), offenders[:8]
     assert not judged or judged[0][1] >= 0.97, judged[:4]
+    assert all(r[1] >= 0.5 for r in pool_rows), pool_rows
 
 
 def test_training_trajectory_50_steps_vs_fp32_oracle():

@@ -8,7 +8,7 @@ twin off, one at a time, and prints the loss / logits distance to the fp32 oracl
 conditioned weights (12 fp32 Adam steps, as in test_engine_vs_fp32_oracle_on_conditioned_weights), over several seeds —
 the loss is ONE scalar draw of the storage noise per seed, so a single run says little.
 
-    python scripts/precision_attribution.py [--encoder resnet18] [--size 128] [--n 8] [--seeds 6]
+    python tests/tools/precision_attribution.py [--encoder resnet18] [--size 128] [--n 8] [--seeds 6]
 """
 import argparse
 import copy
@@ -19,7 +19,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 VARIANTS = [
     # label, install() keyword arguments
