@@ -315,3 +315,38 @@ def test_resident_pool_flat_indices_are_the_collate_order():
     assert flat.tolist() == [4, 5 + 0, 9 + 5, 1, 5 + 3, 9 + 2] and dom == [0, 1, 2, 0, 1, 2]
     with pytest.raises(IndexError):
         pools.flat_indices(np.array([[5, 0, 0]]))
+
+
+def test_stride2_depthwise_quad_form_is_the_transpose_of_the_forward():
+    """the data gradient of `dw3x3_s2_dgrad_kernel` (csrc/nn_elem.cu) is written per 2x2 input quad: quad (a, b) reads
+    the four outputs (a..a+1, b..b+1) and uses every filter tap exactly once.  Restated in numpy and checked against
+    the scatter-form transpose of the forward definition y[oy,ox] = sum w[r][s] x[2oy+r-1, 2ox+s-1] (torch Conv2d with
+    stride 2 / padding 1, models: MobileNetV2's down-sampling blocks), odd and even sizes."""
+    rng = np.random.RandomState(3)
+    for h, w in [(6, 8), (7, 5), (1, 1), (2, 3), (33, 30)]:
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        wt = rng.randn(3, 3)
+        dy = rng.randn(ho, wo)
+        want = np.zeros((h, w))
+        for oy in range(ho):
+            for ox in range(wo):
+                for r in range(3):
+                    for s in range(3):
+                        iy, ix = 2 * oy + r - 1, 2 * ox + s - 1
+                        if 0 <= iy < h and 0 <= ix < w:
+                            want[iy, ix] += wt[r, s] * dy[oy, ox]
+        got = np.full((h, w), np.nan)
+        d = lambda a, b: dy[a, b] if a < ho and b < wo else 0.0      # noqa: E731
+        for a in range((h + 1) // 2):
+            for b in range((w + 1) // 2):
+                iy, ix = 2 * a, 2 * b
+                got[iy, ix] = wt[1, 1] * d(a, b)
+                if ix + 1 < w:
+                    got[iy, ix + 1] = wt[1, 0] * d(a, b + 1) + wt[1, 2] * d(a, b)
+                if iy + 1 < h:
+                    got[iy + 1, ix] = wt[0, 1] * d(a + 1, b) + wt[2, 1] * d(a, b)
+                    if ix + 1 < w:
+                        got[iy + 1, ix + 1] = (wt[0, 0] * d(a + 1, b + 1) + wt[0, 2] * d(a + 1, b) + wt[2, 0] * d(a, b + 1)
+                                               + wt[2, 2] * d(a, b))
+        assert not np.isnan(got).any()                 # every input pixel is written exactly once
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
