@@ -350,3 +350,37 @@ def test_stride2_depthwise_quad_form_is_the_transpose_of_the_forward():
                                                + wt[2, 2] * d(a, b))
         assert not np.isnan(got).any()                 # every input pixel is written exactly once
         np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+
+
+def test_statistical_wrapper_needs_a_failure_to_reproduce():
+    """tests/conftest.py `statistical`: a single-draw noise test is re-run once after a failed assertion and the second
+    verdict stands; the wrapped function keeps its signature (pytest parametrisation / fixtures see through it)."""
+    import inspect
+    from conftest import statistical
+    calls = []
+
+    @statistical
+    def flaky(a, b=2):
+        calls.append((a, b))
+        assert len(calls) > 1, "first draw unlucky"
+        return a + b
+
+    assert flaky(1, b=3) == 4 and calls == [(1, 3), (1, 3)]
+    assert list(inspect.signature(flaky).parameters) == ["a", "b"]
+
+    @statistical
+    def broken():
+        calls.append("x")
+        assert False, "always"
+
+    n = len(calls)
+    with pytest.raises(AssertionError):
+        broken()
+    assert len(calls) == n + 2                     # ran twice, failed twice
+
+    @statistical
+    def crashes():
+        raise ValueError("not an assertion")       # only assertion failures are retried
+
+    with pytest.raises(ValueError):
+        crashes()

@@ -17,6 +17,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from conftest import statistical
+
 pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 
@@ -362,6 +364,7 @@ def test_every_layer_backward_teacher_forced_vs_float64(arch, encoder, classes, 
 
 
 @pytest.mark.parametrize("arch,encoder,classes,size,n,dataset", CASES)
+@statistical
 def test_engine_within_the_bf16_noise_envelope_at_random_init(arch, encoder, classes, size, n, dataset):
     """Whole network at random initialisation.  bf16 storage re-quantises every layer, so ANY difference in fp32
     summation order (the engine's own two runs differ: its statistics and weight gradients use fp32 atomics) grows
@@ -396,6 +399,7 @@ def test_engine_within_the_bf16_noise_envelope_at_random_init(arch, encoder, cla
 
 
 @pytest.mark.parametrize("arch,encoder,classes,size,n,dataset", CASES[:3])
+@statistical
 def test_engine_vs_fp32_oracle_on_conditioned_weights(arch, encoder, classes, size, n, dataset):
     """the north-star tolerance against the PLAIN fp32 oracle, on weights conditioned by 12 fp32 Adam steps of the
     oracle.  ResNets: loss within 5e-4 relative, logits within 2e-2 relative L2, Dice (samplewise F1) within 1e-3.
@@ -472,6 +476,7 @@ def test_engine_vs_fp32_oracle_on_conditioned_weights(arch, encoder, classes, si
     assert all(r[1] >= 0.3 for r in pool_rows), pool_rows
 
 
+@statistical
 def test_training_trajectory_50_steps_vs_fp32_oracle():
     """50 Adam steps from identical weights on identical data (search_dg.py:140-142,164-172): the engine's loss curve
     stays within 4 % of the fp32 oracle's and its Dice within 0.04 at every step (measured: 1.7-2.6 % / 0.008-0.025;
@@ -504,6 +509,7 @@ def test_training_trajectory_50_steps_vs_fp32_oracle():
     assert curve[-1][1] < 0.1 * curve[0][1]
 
 
+@statistical
 def test_autograd_surface_runs_the_reference_training_lines():
     """`seg_output, feature = model(input)` ... `model_optimizer.zero_grad(); seg_loss.backward(); model_optimizer.step()`
     (search_dg.py:132,140-142,170-172) verbatim, with torch.optim.Adam over `model.parameters()`, against the engine's own

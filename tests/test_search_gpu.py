@@ -7,6 +7,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import statistical
+
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -118,6 +120,7 @@ def test_warmup_to_search_transition():
     assert abs(float(model.store.hyper[0]) - 1e-4) < 1e-9
 
 
+@statistical
 def test_cuda_graph_step_matches_eager_step():
     """the captured step (graph=True) and the eager step walk the same trajectory: same decisions, same dropout seeds
     and Adam step counts from device memory; differences are the summation order of the gradient atomics"""
