@@ -30,7 +30,18 @@ VARIANTS = [
     ("only the weights rounded", {"round_activations": False, "round_input": False}),
     ("only the activations rounded", {"round_weights": False, "round_input": False}),
     ("only the input image rounded", {"round_weights": False, "round_activations": False}),
+    # 255 x = 2k - 255 is an odd integer of <= 8 significant bits: exact in bf16; the stem is linear, so its bf16 weights
+    # can carry the 1/255 (DESIGN.md "Precision")
+    ("all points, stem fed the exact 255 x (weights / 255)", {"round_input": False, "exact_stem": True}),
 ]
+
+
+def exact_stem(model):
+    """stem convolution evaluated as conv(bf16(255 x), bf16(w / 255)) (its output hook still rounds the result)"""
+    from oracle.segnet_bf16 import rb
+    enc = model.encoder
+    conv = enc.conv1 if hasattr(enc, "conv1") else enc.features[0][0]
+    conv.forward = lambda x: conv._conv_forward(rb(x * 255.0), rb(conv.weight / 255.0), conv.bias)
 
 
 def synth(n, size, classes, seed, device):
@@ -79,7 +90,11 @@ def main():
             logits_r, _ = ref(x)
             loss_r = F.binary_cross_entropy(torch.sigmoid(logits_r), target).item()
             for label, kw in VARIANTS:
+                kw = dict(kw)
+                stem = kw.pop("exact_stem", False)
                 twin = segnet_bf16.install(copy.deepcopy(ref), **kw)
+                if stem:
+                    exact_stem(twin)
                 logits_t, _ = twin(x)
                 loss_t = F.binary_cross_entropy(torch.sigmoid(logits_t), target).item()
                 loss_err[label].append(abs(loss_t - loss_r) / loss_r)
@@ -87,11 +102,11 @@ def main():
         print("seed %d: fp32 loss %.5f" % (seed, loss_r), flush=True)
     print("\nPRECISION_ATTRIBUTION deeplabv3plus/%s %d^2 n=%d, %d seeds, %d conditioning steps, device %s" %
           (args.encoder, args.size, args.n, args.seeds, args.presteps, device))
-    print("%-52s %12s %12s %12s %12s" % ("rounding points of the bf16-storage oracle", "loss median", "loss max",
+    print("%-56s %12s %12s %12s %12s" % ("rounding points of the bf16-storage oracle", "loss median", "loss max",
                                          "logits med", "logits max"))
     for label, _ in VARIANTS:
         le, ge = np.array(loss_err[label]), np.array(logit_err[label])
-        print("%-52s %12.2e %12.2e %12.2e %12.2e" % (label, np.median(le), le.max(), np.median(ge), ge.max()))
+        print("%-56s %12.2e %12.2e %12.2e %12.2e" % (label, np.median(le), le.max(), np.median(ge), ge.max()))
 
 
 if __name__ == "__main__":
