@@ -1,4 +1,5 @@
-"""CPU: the C-ABI library builds, loads and exports every symbol include/*.h declares."""
+"""CPU: the C-ABI library builds, loads and exports every symbol include/*.h declares, and its entry points reject bad
+arguments (host-side checks, no device needed)."""
 import ctypes
 import glob
 import os
@@ -57,3 +58,34 @@ def test_ops_refuse_cpu_tensors():
     from aadg_b200.data.decisions import ROW_DTYPE
     with pytest.raises(RuntimeError):
         u8.apply_policy(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), None, np.zeros(1, ROW_DTYPE))
+
+
+def test_entry_points_reject_bad_arguments_before_touching_the_device(built):
+    """error behaviour of the boundary (include/aadg_b200.h: 0 / negative AADG_E* + aadg_last_error()): argument checks
+    run on the host before any CUDA call, so they can be exercised without a GPU.  The fake pointers are 16-byte
+    aligned and never dereferenced."""
+    from aadg_b200 import _lib
+    l = _lib.lib()
+    EINVAL = -1
+    P = 0x100000
+
+    def err():
+        return l.aadg_last_error().decode()
+    # depthwise: channels must be a multiple of 8
+    assert l.aadg_dwconv3x3_strided(P, 1, 8, 8, 12, 16, P, 1, 2, 0, P, 4, 4, 16, None) == EINVAL
+    assert "multiple of 8" in err()
+    # ... and the output size is fixed by the geometry (MobileNetV2's padding = dilation convention)
+    assert l.aadg_dwconv3x3_strided(P, 1, 8, 8, 16, 16, P, 1, 2, 0, P, 5, 4, 16, None) == EINVAL
+    assert "output size mismatch" in err()
+    assert l.aadg_dwconv3x3_strided_wgrad(P, 1, 9, 9, 16, 16, P, 4, 5, 16, 1, 2, P, None) == EINVAL
+    # channel strides that break the 16-byte access rule
+    assert l.aadg_dwconv3x3_strided(P, 1, 8, 8, 16, 12, P, 1, 2, 0, P, 4, 4, 16, None) == EINVAL
+    assert "16-byte" in err()
+    # tensor-core convolution: channels in multiples of 8, sane geometry
+    assert l.aadg_conv_fprop_bf16(P, 1, 8, 8, 12, 16, P, 64, 3, 3, 1, 1, 1, P, 8, 8, 64, 0, 0, None) < 0
+    assert l.aadg_conv_fprop_bf16(P, 0, 8, 8, 16, 16, P, 64, 3, 3, 1, 1, 1, P, 8, 8, 64, 0, 0, None) < 0
+    # stem im2col: patch length must hold R*S*3 values in multiples of 8
+    assert l.aadg_im2col_stem(P, 1, 32, 32, 7, 7, 2, 3, 100, P, None) == EINVAL
+    assert "kp" in err()
+    # a successful query leaves the codes alone
+    assert l.aadg_version() == 1
