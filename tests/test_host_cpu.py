@@ -384,3 +384,28 @@ def test_statistical_wrapper_needs_a_failure_to_reproduce():
 
     with pytest.raises(ValueError):
         crashes()
+
+
+def test_bench_partitions_config2_like_survey_8e():
+    """bench.py: weak scaling keeps 144 images per GPU, strong scaling shards config 2's 24 source images 12 / 6 / 3
+    per GPU (BASELINE config 3) and keeps the global batch at 144; the workload string is the same for
+    every N (the driver compares configs across the scaling run)."""
+    import argparse
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    base = dict(items=8, dataset="optic", arch="deeplabv3plus", backbone="resnet50", size=512, graph=1, no_scale_crop=False)
+    weak = argparse.Namespace(scaling="weak", **base)
+    strong = argparse.Namespace(scaling="strong", **base)
+    for n, per in [(1, 24), (2, 12), (4, 6), (8, 3)]:
+        assert bench.sources_per_gpu(strong, n) == per and bench.sources_per_gpu(weak, n) == 24
+        cs, cw = bench.workload_config(strong, n), bench.workload_config(weak, n)
+        assert cs["global_images_per_step"] == 144 and cs["images_per_step_per_gpu"] == per * 6
+        assert cw["global_images_per_step"] == 144 * n and cw["images_per_step_per_gpu"] == 144
+        assert cs["workload"] == cw["workload"] == bench.workload_config(weak, 1)["workload"]
+    with pytest.raises(SystemExit):
+        bench.sources_per_gpu(strong, 5)
+    vessel = argparse.Namespace(scaling="strong", **dict(base, dataset="vessel", arch="unet", backbone="resnet34", size=1024))
+    assert bench.sources_per_gpu(vessel, 8) == 4          # config 4: 32 source rows, 4 per GPU at 8 GPUs
